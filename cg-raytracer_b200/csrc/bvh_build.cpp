@@ -1,0 +1,209 @@
+// Range-based host BVH build with the reference's split rule. See bvh_build.h.
+// Parity notes (reference = src/bounding_volume_hierarchy.cpp):
+//  * axis choice           :286-289  (x > y) ? ((x > z) ? 0 : 2) : ((y > z) ? 1 : 2) on the node's AABB extents
+//  * single-mesh split     :192-207  std::sort of the node's triangle list by centroid[axis] with `<`, halves [0,n/2) [n/2,n)
+//                                    (libstdc++ std::sort is deterministic for a given sequence + comparator outcome, so sorting
+//                                    an index range with the same comparator outcome reproduces the same permutation)
+//  * multi-mesh split      :168-179, :88-110  std::sort of the MESHES by the centroid[axis] of each mesh's median triangle
+//  * child AABBs           :235-268  min/max via ternaries over the referenced vertices, seeded from the first triangle's
+//                                    first vertex of the first mesh (index round-tripped through float, :237)
+//  * leaf rule             :320-322  level+1 == maxDepth-1, or one mesh with one triangle; root :58
+//  * numbering             :343-372  BFS over a growing vector, the two children pushed consecutively
+#include "bvh_build.h"
+
+#include <algorithm>
+#include <cstddef>
+
+namespace cgrt {
+namespace {
+
+struct Item {
+    std::vector<int32_t> meshIds; // >1: whole meshes in their current order
+    int32_t mesh = -1;            // ==1 mesh: fragment [begin,end) of perm[mesh]
+    int32_t begin = 0, end = 0;
+    bool single() const { return meshIds.empty(); }
+};
+
+struct Builder {
+    const std::vector<MeshView>& meshes;
+    std::vector<std::vector<float>> keys[3];     // keys[axis][mesh][tri] = centroid coordinate ((p0+p1)+p2)/3.0f
+    std::vector<std::vector<int32_t>> perm;      // perm[mesh] = current triangle order
+    std::vector<float> medianKey[3];             // medianKey[axis][mesh], NaN-free cache flag below
+    std::vector<char> medianKnown[3];
+
+    explicit Builder(const std::vector<MeshView>& m) : meshes(m)
+    {
+        const size_t nm = meshes.size();
+        perm.resize(nm);
+        for (int a = 0; a < 3; a++) {
+            keys[a].resize(nm);
+            medianKey[a].assign(nm, 0.0f);
+            medianKnown[a].assign(nm, 0);
+        }
+        for (size_t m_ = 0; m_ < nm; m_++) {
+            const MeshView& mv = meshes[m_];
+            perm[m_].resize(mv.nt);
+            for (int a = 0; a < 3; a++) keys[a][m_].resize(mv.nt);
+            for (int32_t t = 0; t < mv.nt; t++) {
+                perm[m_][t] = t;
+                const uint32_t* tri = mv.triangles + 3 * (size_t)t;
+                const float* p0 = mv.vertices + 6 * (size_t)tri[0];
+                const float* p1 = mv.vertices + 6 * (size_t)tri[1];
+                const float* p2 = mv.vertices + 6 * (size_t)tri[2];
+                for (int a = 0; a < 3; a++) keys[a][m_][t] = ((p0[a] + p1[a]) + p2[a]) / 3.0f; // bvh.cpp:127-128
+            }
+        }
+    }
+
+    const float* pos(int32_t mesh, int32_t tri, int corner) const
+    {
+        const MeshView& mv = meshes[mesh];
+        return mv.vertices + 6 * (size_t)mv.triangles[3 * (size_t)tri + corner];
+    }
+
+    // centroid[axis] of the median triangle of the mesh after sorting its triangles by that axis (bvh.cpp:92-99)
+    float meshMedian(int32_t mesh, int axis)
+    {
+        if (!medianKnown[axis][mesh]) {
+            std::vector<float> k = keys[axis][mesh];
+            std::sort(k.begin(), k.end(), [](float a, float b) { return a < b; });
+            medianKey[axis][mesh] = k[k.size() / 2];
+            medianKnown[axis][mesh] = 1;
+        }
+        return medianKey[axis][mesh];
+    }
+
+    template <typename F>
+    void forEachTriangle(const Item& it, F f) const
+    {
+        if (it.single()) {
+            for (int32_t i = it.begin; i < it.end; i++) f(it.mesh, perm[it.mesh][i]);
+        } else {
+            for (int32_t m : it.meshIds)
+                for (int32_t t = 0; t < meshes[m].nt; t++) f(m, perm[m][t]); // whole meshes keep their original order
+        }
+    }
+
+    void boxOf(const Item& it, float lo[3], float hi[3]) const
+    { // getBoundingBoxFromMeshes bvh.cpp:235-268
+        const int32_t m0 = it.single() ? it.mesh : it.meshIds[0];
+        const int32_t t0 = it.single() ? perm[m0][it.begin] : perm[m0][0];
+        const float firstTriangleVertex = (float)meshes[m0].triangles[3 * (size_t)t0]; // bvh.cpp:237 (uint -> float -> index)
+        const float* seed = meshes[m0].vertices + 6 * (size_t)firstTriangleVertex;
+        float min_x, max_x, min_y, max_y, min_z, max_z;
+        min_x = max_x = seed[0];
+        min_y = max_y = seed[1];
+        min_z = max_z = seed[2];
+        forEachTriangle(it, [&](int32_t m, int32_t t) {
+            for (int i = 0; i < 3; i++) {
+                const float* p = pos(m, t, i);
+                min_x = (p[0] < min_x) ? p[0] : min_x;
+                min_y = (p[1] < min_y) ? p[1] : min_y;
+                min_z = (p[2] < min_z) ? p[2] : min_z;
+                max_x = (p[0] > max_x) ? p[0] : max_x;
+                max_y = (p[1] > max_y) ? p[1] : max_y;
+                max_z = (p[2] > max_z) ? p[2] : max_z;
+            }
+        });
+        lo[0] = min_x; lo[1] = min_y; lo[2] = min_z;
+        hi[0] = max_x; hi[1] = max_y; hi[2] = max_z;
+    }
+
+    bool singleTriangle(const Item& it) const { return it.single() && (it.end - it.begin) == 1; }
+
+    Item wholeMesh(int32_t m) const
+    {
+        Item it;
+        it.mesh = m;
+        it.begin = 0;
+        it.end = meshes[m].nt;
+        return it;
+    }
+};
+
+} // namespace
+
+void buildReferenceBVH(const std::vector<MeshView>& meshes, int maxDepth, BuiltBVH& out)
+{
+    out.nodes.clear();
+    out.leafTris.clear();
+    out.numLevels = 0;
+    if (meshes.empty()) return; // bvh.cpp:52-55
+
+    Builder B(meshes);
+    std::vector<Item> items; // parallel to out.nodes
+
+    Item root;
+    if (meshes.size() == 1) root = B.wholeMesh(0);
+    else
+        for (size_t m = 0; m < meshes.size(); m++) root.meshIds.push_back((int32_t)m);
+
+    auto pushNode = [&](Item&& it, int level, bool isLeaf) {
+        HostNode n;
+        B.boxOf(it, n.lo, n.hi);
+        n.child0 = n.child1 = -1;
+        n.firstTri = 0;
+        n.triCount = 0;
+        n.level = level;
+        n.isLeaf = isLeaf ? 1 : 0;
+        out.nodes.push_back(n);
+        items.push_back(std::move(it));
+    };
+
+    const bool rootLeaf = (maxDepth - 1 == 0) || B.singleTriangle(root); // bvh.cpp:58
+    pushNode(std::move(root), 0, rootLeaf);
+
+    for (size_t cur = 0; cur < out.nodes.size(); cur++) { // createTree bvh.cpp:343-372
+        if (out.nodes[cur].isLeaf) continue;
+        const HostNode nd = out.nodes[cur];
+        const float x = nd.hi[0] - nd.lo[0], y = nd.hi[1] - nd.lo[1], z = nd.hi[2] - nd.lo[2];
+        const int axis = (x > y) ? ((x > z) ? 0 : 2) : ((y > z) ? 1 : 2); // bvh.cpp:286-289
+        Item L, R;
+        Item& it = items[cur];
+        if (!it.single()) {
+            // getChildMeshesMultipleMeshes bvh.cpp:168-179 / sortMeshesByCentres :88-110
+            std::vector<int32_t> ids = it.meshIds;
+            for (int32_t m : ids) (void)B.meshMedian(m, axis);
+            std::sort(ids.begin(), ids.end(),
+                      [&](int32_t a, int32_t b) { return B.medianKey[axis][a] < B.medianKey[axis][b]; });
+            const size_t half = ids.size() / 2;
+            if (half == 1) L = B.wholeMesh(ids[0]);
+            else L.meshIds.assign(ids.begin(), ids.begin() + half);
+            if (ids.size() - half == 1) R = B.wholeMesh(ids[half]);
+            else R.meshIds.assign(ids.begin() + half, ids.end());
+        } else {
+            // getChildMeshesOneMesh bvh.cpp:192-207 / sortTrianglesByCentres :122-134
+            std::vector<int32_t>& p = B.perm[it.mesh];
+            const std::vector<float>& k = B.keys[axis][it.mesh];
+            std::sort(p.begin() + it.begin, p.begin() + it.end, [&](int32_t a, int32_t b) { return k[a] < k[b]; });
+            const int32_t n = it.end - it.begin;
+            L.mesh = R.mesh = it.mesh;
+            L.begin = it.begin;
+            L.end = it.begin + n / 2;
+            R.begin = L.end;
+            R.end = it.end;
+        }
+        const bool areLeaf = (nd.level + 1 == maxDepth - 1); // bvh.cpp:320
+        const bool lLeaf = areLeaf || B.singleTriangle(L);
+        const bool rLeaf = areLeaf || B.singleTriangle(R);
+        const int32_t lastIndex = (int32_t)out.nodes.size();
+        out.nodes[cur].child0 = lastIndex;
+        out.nodes[cur].child1 = lastIndex + 1;
+        items[cur] = Item();
+        pushNode(std::move(L), nd.level + 1, lLeaf);
+        pushNode(std::move(R), nd.level + 1, rLeaf);
+    }
+
+    int maxLevel = 0;
+    for (size_t i = 0; i < out.nodes.size(); i++) {
+        HostNode& n = out.nodes[i];
+        if (n.level > maxLevel) maxLevel = n.level;
+        if (!n.isLeaf) continue;
+        n.firstTri = (int32_t)out.leafTris.size();
+        B.forEachTriangle(items[i], [&](int32_t m, int32_t t) { out.leafTris.push_back(LeafTri{m, t}); });
+        n.triCount = (int32_t)out.leafTris.size() - n.firstTri;
+    }
+    out.numLevels = maxLevel + 1; // numLevels() bvh.cpp:214-224
+}
+
+} // namespace cgrt

@@ -1,0 +1,978 @@
+// extern "C" boundary of libcgrt_b200.so (include/cgrt_b200.h). Host logic only: scene flattening, BVH build (bvh_build.cpp),
+// uploads, per-frame constants, queue allocation, kernel sequencing. No CPU implementation of the path lives here: every
+// query is answered by the kernels in cgrt_kernels.cu, and every entry fails loudly when no CUDA device is usable.
+#include "../../include/cgrt_b200.h"
+#include "bvh_build.h"
+#include "cgrt_kernels.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace cgrt;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                                      \
+    do {                                                                                                              \
+        cudaError_t e_ = (call);                                                                                      \
+        if (e_ != cudaSuccess) {                                                                                      \
+            char buf_[512];                                                                                           \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail((e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? CGRT_ERR_NO_DEVICE           \
+                                                                                        : CGRT_ERR_CUDA,               \
+                        buf_);                                                                                        \
+        }                                                                                                             \
+    } while (0)
+
+static int useDevice(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(CGRT_ERR_NO_DEVICE, std::string("no usable CUDA device (the product has no CPU path): ") +
+                                            (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= n) return fail(CGRT_ERR_INVALID, "device ordinal out of range");
+    CK(cudaSetDevice(device));
+    return CGRT_OK;
+}
+
+struct DeviceInfo {
+    int numSMs = 0;
+};
+static int deviceInfo(int device, DeviceInfo& di)
+{
+    static std::mutex mu;
+    static std::map<int, DeviceInfo> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(device);
+    if (it == cache.end()) {
+        DeviceInfo d;
+        CK(cudaDeviceGetAttribute(&d.numSMs, cudaDevAttrMultiProcessorCount, device));
+        it = cache.emplace(device, d).first;
+    }
+    di = it->second;
+    return CGRT_OK;
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int ensure(size_t count)
+    {
+        if (count <= n && p) return CGRT_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? CGRT_ERR_OOM : CGRT_ERR_CUDA,
+                                          std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        n = count;
+        return CGRT_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+// ---- tile partition --------------------------------------------------------------------------------------------------
+// Interleaved screen tiles: tile (tx,ty) belongs to rank (tx + ty*skew) mod world, skew coprime to world so that the
+// compact lit region of a frame spreads evenly over the GPUs.
+struct TileLayout {
+    int tileW, tileH, tilesX, tilesY, world, skew, maxTiles;
+    std::vector<std::vector<int>> lists; // per rank: owned global tile ids, increasing
+};
+static int gcdInt(int a, int b) { return b == 0 ? a : gcdInt(b, a % b); }
+static void makeTileLayout(const cgrt_render_params& p, TileLayout& L)
+{
+    L.tileW = p.tile_w > 0 ? p.tile_w : 8;
+    L.tileH = p.tile_h > 0 ? p.tile_h : 8;
+    L.tilesX = (p.width + L.tileW - 1) / L.tileW;
+    L.tilesY = (p.height + L.tileH - 1) / L.tileH;
+    L.world = p.world > 0 ? p.world : 1;
+    L.skew = 1;
+    if (L.world > 1) {
+        L.skew = 3;
+        while (gcdInt(L.skew, L.world) != 1) L.skew++;
+    }
+    L.lists.assign(L.world, std::vector<int>());
+    for (int ty = 0; ty < L.tilesY; ty++)
+        for (int tx = 0; tx < L.tilesX; tx++) L.lists[(tx + ty * L.skew) % L.world].push_back(ty * L.tilesX + tx);
+    L.maxTiles = 0;
+    for (auto& l : L.lists) L.maxTiles = std::max(L.maxTiles, (int)l.size());
+}
+
+static int checkRenderParams(const cgrt_render_params* p)
+{
+    if (!p) return fail(CGRT_ERR_INVALID, "null render params");
+    if (p->width <= 0 || p->height <= 0) return fail(CGRT_ERR_INVALID, "width/height must be positive");
+    if ((int64_t)p->width * p->height > (int64_t)1 << 28) return fail(CGRT_ERR_INVALID, "frame too large");
+    if (p->trace_limit < 0 || p->trace_limit > CGRT_MAX_LEVELS) return fail(CGRT_ERR_INVALID, "trace_limit out of range");
+    if (p->world < 1 || p->rank < 0 || p->rank >= p->world) return fail(CGRT_ERR_INVALID, "rank/world invalid");
+    if (p->tile_w < 0 || p->tile_h < 0 || p->tile_w > 64 || p->tile_h > 64) return fail(CGRT_ERR_INVALID, "tile size invalid");
+    return CGRT_OK;
+}
+
+// ---- camera constants (host, libm): Trackball::position / generateRay, glm::quat(euler), quat * vec3 ---------------------
+static void crossH(const float a[3], const float b[3], float r[3])
+{
+    r[0] = a[1] * b[2] - b[1] * a[2];
+    r[1] = a[2] * b[0] - b[2] * a[0];
+    r[2] = a[0] * b[1] - b[0] * a[1];
+}
+static void cameraConstants(const cgrt_camera& c, FrameParams& P)
+{
+    // glm::quat(eulerAngles): c = cos(e*0.5), s = sin(e*0.5)
+    const float hx = c.euler[0] * 0.5f, hy = c.euler[1] * 0.5f, hz = c.euler[2] * 0.5f;
+    const float cx = std::cos(hx), cy = std::cos(hy), cz = std::cos(hz);
+    const float sx = std::sin(hx), sy = std::sin(hy), sz = std::sin(hz);
+    P.qw = cx * cy * cz + sx * sy * sz;
+    P.qx = sx * cy * cz - cx * sy * sz;
+    P.qy = cx * sy * cz + sx * cy * sz;
+    P.qz = cx * cy * sz - sx * sy * cz;
+    // position = lookAt + q * (0, 0, -dist)   (framework/src/trackball.cpp:70-73)
+    const float q[3] = {P.qx, P.qy, P.qz};
+    const float v[3] = {0.0f, 0.0f, -c.dist};
+    float uv[3], uuv[3];
+    crossH(q, v, uv);
+    crossH(q, uv, uuv);
+    P.camX = c.look_at[0] + (v[0] + ((uv[0] * P.qw) + uuv[0]) * 2.0f);
+    P.camY = c.look_at[1] + (v[1] + ((uv[1] * P.qw) + uuv[1]) * 2.0f);
+    P.camZ = c.look_at[2] + (v[2] + ((uv[2] * P.qw) + uuv[2]) * 2.0f);
+    P.halfH = std::tan(c.fovy / 2.0f);   // framework/src/trackball.cpp:94
+    P.halfW = c.aspect * P.halfH;        // :95
+}
+
+// ---- the scene object --------------------------------------------------------------------------------------------------
+struct cgrt_scene {
+    int device = 0;
+    DeviceInfo di;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+
+    BuiltBVH bvh;
+    std::vector<int32_t> leafGlobalId; // leaf order -> global triangle id
+    int64_t nTris = 0;
+    int nMeshes = 0;
+
+    DevBuf<float4> nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres;
+    DevBuf<int> origToLeaf;
+    DevScene dev{};
+
+    std::vector<cgrt_point_light> lights;
+
+    // per-frame parameter block: pinned ring -> device block
+    static const int RING = 64;
+    unsigned char* hParamRing = nullptr; // RING x paramBlockBytes, pinned
+    size_t paramBlockBytes = 0;
+    int ringPos = 0;
+    DevBuf<unsigned char> dParamBlock;
+
+    // wavefront queues
+    DevBuf<float4> hitQ, bounceQ, pathState;
+    DevBuf<uint8_t> lit;
+    DevBuf<int> pathPix, counts, tileList;
+    std::vector<int> tileListHost;
+    int tileKey[6] = {0, 0, 0, 0, 0, 0};
+    DevBuf<float> frame; // internal framebuffer for the host-pointer render
+    float* hFramePinned = nullptr;
+    size_t hFramePinnedFloats = 0;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t lastStream = nullptr;
+    uint64_t lastLaunches = 0;
+    FrameParams lastParams{};
+    bool haveLast = false;
+};
+
+static void destroyScene(cgrt_scene* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
+    s->triN0.release(); s->triN1.release(); s->triN2.release(); s->mats.release(); s->spheres.release();
+    s->origToLeaf.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
+    s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->frame.release();
+    if (s->hParamRing) cudaFreeHost(s->hParamRing);
+    if (s->hFramePinned) cudaFreeHost(s->hFramePinned);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static int uploadSpheres(cgrt_scene* s, const float* spheres, int n)
+{
+    std::vector<float4> h((size_t)std::max(n, 0) * 3);
+    for (int i = 0; i < n; i++) {
+        const float* p = spheres + 12 * (size_t)i;
+        h[3 * i + 0] = make_float4(p[0], p[1], p[2], p[3]);
+        h[3 * i + 1] = make_float4(p[4], p[5], p[6], p[10]);
+        h[3 * i + 2] = make_float4(p[7], p[8], p[9], p[11]);
+    }
+    int rc = s->spheres.ensure(h.size());
+    if (rc) return rc;
+    if (n > 0) CK(cudaMemcpy(s->spheres.p, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    s->dev.spheres = s->spheres.p;
+    s->dev.nSpheres = n;
+    return CGRT_OK;
+}
+
+extern "C" {
+
+int cgrt_version(void) { return CGRT_VERSION; }
+const char* cgrt_last_error(void) { return g_err.c_str(); }
+
+int cgrt_device_count(int* count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (count) *count = (e == cudaSuccess) ? n : 0;
+    if (e != cudaSuccess || n == 0)
+        return fail(CGRT_ERR_NO_DEVICE, std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0"));
+    return CGRT_OK;
+}
+
+int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, cgrt_scene** out)
+{
+    if (!d || !out) return fail(CGRT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (d->n_meshes < 0 || d->n_spheres < 0) return fail(CGRT_ERR_INVALID, "negative counts");
+    const int device = opt ? opt->device : 0;
+    int maxDepth = (opt && opt->bvh_max_depth > 0) ? opt->bvh_max_depth : 12; // src/bounding_volume_hierarchy.cpp:48
+    if (maxDepth > CGRT_MAX_BVH_DEPTH) return fail(CGRT_ERR_INVALID, "bvh_max_depth exceeds the traversal stack");
+    int rc = useDevice(device);
+    if (rc) return rc;
+
+    // ---- validate + view the meshes
+    std::vector<MeshView> views;
+    size_t vo = 0, to = 0;
+    int32_t gid = 0;
+    for (int m = 0; m < d->n_meshes; m++) {
+        const int nv = d->mesh_vertex_count[m], nt = d->mesh_triangle_count[m];
+        if (nv <= 0 || nt <= 0)
+            return fail(CGRT_ERR_INVALID, "mesh without vertices/triangles (the reference dereferences triangles[0], bvh.cpp:237)");
+        MeshView v;
+        v.vertices = d->vertices + 6 * vo;
+        v.triangles = d->triangles + 3 * to;
+        v.nv = nv;
+        v.nt = nt;
+        v.triOffset = gid;
+        for (size_t i = 0; i < (size_t)nt * 3; i++)
+            if (v.triangles[i] >= (uint32_t)nv) return fail(CGRT_ERR_INVALID, "triangle index out of range");
+        views.push_back(v);
+        vo += nv;
+        to += nt;
+        gid += nt;
+    }
+
+    cgrt_scene* s = new cgrt_scene();
+    s->device = device;
+    s->nTris = gid;
+    s->nMeshes = d->n_meshes;
+    rc = deviceInfo(device, s->di);
+    if (rc) { destroyScene(s); return rc; }
+
+    // ---- host build with the reference split rule
+    buildReferenceBVH(views, maxDepth, s->bvh);
+    const size_t T = s->bvh.leafTris.size();
+    const size_t NN = s->bvh.nodes.size();
+
+    // ---- flatten: 32-byte nodes + leaf-ordered SoA triangles
+    std::vector<float4> hNodes(NN * 2);
+    for (size_t i = 0; i < NN; i++) {
+        const HostNode& n = s->bvh.nodes[i];
+        uint32_t a, b;
+        if (n.isLeaf) { a = (uint32_t)n.firstTri; b = (uint32_t)n.triCount; }
+        else { a = (uint32_t)n.child0; b = 0u; }
+        float fa, fb;
+        std::memcpy(&fa, &a, 4);
+        std::memcpy(&fb, &b, 4);
+        hNodes[2 * i] = make_float4(n.lo[0], n.lo[1], n.lo[2], fa);
+        hNodes[2 * i + 1] = make_float4(n.hi[0], n.hi[1], n.hi[2], fb);
+    }
+    std::vector<float4> hv[3], hn[3];
+    for (int k = 0; k < 3; k++) { hv[k].resize(T); hn[k].resize(T); }
+    std::vector<int> hOrigToLeaf((size_t)gid, 0);
+    s->leafGlobalId.resize(T);
+    for (size_t i = 0; i < T; i++) {
+        const LeafTri lt = s->bvh.leafTris[i];
+        const MeshView& mv = views[lt.mesh];
+        const int32_t g = mv.triOffset + lt.tri;
+        s->leafGlobalId[i] = g;
+        hOrigToLeaf[g] = (int)i;
+        for (int k = 0; k < 3; k++) {
+            const float* vtx = mv.vertices + 6 * (size_t)mv.triangles[3 * (size_t)lt.tri + k];
+            float w = 0.0f;
+            if (k == 0) std::memcpy(&w, &g, 4);
+            if (k == 1) std::memcpy(&w, &lt.mesh, 4);
+            hv[k][i] = make_float4(vtx[0], vtx[1], vtx[2], w);
+            hn[k][i] = make_float4(vtx[3], vtx[4], vtx[5], 0.0f);
+        }
+    }
+    std::vector<float4> hMats((size_t)d->n_meshes * 2);
+    for (int m = 0; m < d->n_meshes; m++) {
+        const float* p = d->materials + 8 * (size_t)m;
+        hMats[2 * m] = make_float4(p[0], p[1], p[2], p[6]);
+        hMats[2 * m + 1] = make_float4(p[3], p[4], p[5], p[7]);
+    }
+
+#define UP(buf, vec)                                                                                         \
+    do {                                                                                                     \
+        rc = s->buf.ensure((vec).size());                                                                    \
+        if (rc) { destroyScene(s); return rc; }                                                              \
+        if (!(vec).empty()) {                                                                                \
+            cudaError_t e_ = cudaMemcpy(s->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice); \
+            if (e_ != cudaSuccess) { destroyScene(s); return fail(CGRT_ERR_CUDA, cudaGetErrorString(e_)); }   \
+        }                                                                                                    \
+    } while (0)
+    UP(nodes, hNodes);
+    UP(triV0, hv[0]); UP(triV1, hv[1]); UP(triV2, hv[2]);
+    UP(triN0, hn[0]); UP(triN1, hn[1]); UP(triN2, hn[2]);
+    UP(mats, hMats);
+    UP(origToLeaf, hOrigToLeaf);
+#undef UP
+    rc = s->triPl.ensure(T);
+    if (rc) { destroyScene(s); return rc; }
+
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+    if (e != cudaSuccess) { destroyScene(s); return fail(CGRT_ERR_CUDA, cudaGetErrorString(e)); }
+
+    launchSetupPlanes(s->triV0.p, s->triV1.p, s->triV2.p, s->triPl.p, (int)T, s->stream);
+    e = cudaStreamSynchronize(s->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { destroyScene(s); return fail(CGRT_ERR_CUDA, std::string("plane set-up kernel: ") + cudaGetErrorString(e)); }
+
+    s->dev.nodes = s->nodes.p;
+    s->dev.triPl = s->triPl.p;
+    s->dev.triV0 = s->triV0.p; s->dev.triV1 = s->triV1.p; s->dev.triV2 = s->triV2.p;
+    s->dev.triN0 = s->triN0.p; s->dev.triN1 = s->triN1.p; s->dev.triN2 = s->triN2.p;
+    s->dev.mats = s->mats.p;
+    s->dev.origToLeaf = s->origToLeaf.p;
+    s->dev.nNodes = (int)NN;
+    s->dev.nTris = (int)T;
+    s->dev.nMeshes = d->n_meshes;
+    rc = uploadSpheres(s, d->spheres, d->n_spheres);
+    if (rc) { destroyScene(s); return rc; }
+    *out = s;
+    return CGRT_OK;
+}
+
+void cgrt_scene_destroy(cgrt_scene* s) { destroyScene(s); }
+
+int cgrt_scene_set_lights(cgrt_scene* s, const cgrt_point_light* lights, int32_t n)
+{
+    if (!s || n < 0 || (n > 0 && !lights)) return fail(CGRT_ERR_INVALID, "bad lights");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->lights.assign(lights, lights + n);
+    return CGRT_OK;
+}
+
+int cgrt_scene_set_spheres(cgrt_scene* s, const float* spheres, int32_t n)
+{
+    if (!s || n < 0 || (n > 0 && !spheres)) return fail(CGRT_ERR_INVALID, "bad spheres");
+    std::lock_guard<std::mutex> lk(s->mu);
+    int rc = useDevice(s->device);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    return uploadSpheres(s, spheres, n);
+}
+
+int cgrt_bvh_num_levels(const cgrt_scene* s) { return s ? s->bvh.numLevels : 0; }
+int cgrt_bvh_num_nodes(const cgrt_scene* s) { return s ? (int)s->bvh.nodes.size() : 0; }
+int64_t cgrt_scene_num_triangles(const cgrt_scene* s) { return s ? s->nTris : 0; }
+
+int cgrt_bvh_export_nodes(const cgrt_scene* s, int32_t* meta, float* aabb)
+{
+    if (!s || !meta || !aabb) return fail(CGRT_ERR_INVALID, "null argument");
+    for (size_t i = 0; i < s->bvh.nodes.size(); i++) {
+        const HostNode& n = s->bvh.nodes[i];
+        meta[5 * i + 0] = n.isLeaf;
+        meta[5 * i + 1] = n.level;
+        meta[5 * i + 2] = n.child0;
+        meta[5 * i + 3] = n.child1;
+        meta[5 * i + 4] = n.isLeaf ? n.triCount : 0;
+        for (int k = 0; k < 3; k++) {
+            aabb[6 * i + k] = n.lo[k];
+            aabb[6 * i + 3 + k] = n.hi[k];
+        }
+    }
+    return CGRT_OK;
+}
+
+int cgrt_bvh_leaf_triangles(const cgrt_scene* s, int32_t node, int32_t* out, int32_t cap)
+{
+    if (!s || node < 0 || node >= (int)s->bvh.nodes.size()) return -1;
+    const HostNode& n = s->bvh.nodes[node];
+    if (!n.isLeaf) return 0;
+    for (int i = 0; i < n.triCount && i < cap; i++) out[i] = s->leafGlobalId[n.firstTri + i];
+    return n.triCount;
+}
+
+// ---- batch queries -------------------------------------------------------------------------------------------------
+int cgrt_intersect_closest_device(cgrt_scene* s, const cgrt_ray* d_rays, size_t n, cgrt_hit* d_hits, uint32_t* d_counts,
+                                  void* stream)
+{
+    if (!s || (n && (!d_rays || !d_hits))) return fail(CGRT_ERR_INVALID, "null argument");
+    int rc = useDevice(s->device);
+    if (rc) return rc;
+    DevScene S;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        S = s->dev;
+    }
+    launchClosestBatch(S, (const float4*)d_rays, n, (float4*)d_hits, d_counts, s->di.numSMs, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return CGRT_OK;
+}
+
+int cgrt_intersect_any_device(cgrt_scene* s, const cgrt_ray* d_rays, const float* d_max_dist, float eps, size_t n,
+                              uint8_t* d_occluded, void* stream)
+{
+    if (!s || (n && (!d_rays || !d_max_dist || !d_occluded))) return fail(CGRT_ERR_INVALID, "null argument");
+    int rc = useDevice(s->device);
+    if (rc) return rc;
+    DevScene S;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        S = s->dev;
+    }
+    launchAnyBatch(S, (const float4*)d_rays, d_max_dist, eps, n, d_occluded, s->di.numSMs, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return CGRT_OK;
+}
+
+// scratch helper for the host-pointer forms: device copies of inputs/outputs, freed on scope exit
+struct Scratch {
+    std::vector<void*> ptrs;
+    cudaStream_t st = nullptr;
+    ~Scratch()
+    {
+        for (void* p : ptrs) cudaFree(p);
+        if (st) cudaStreamDestroy(st);
+    }
+    int alloc(void** p, size_t bytes)
+    {
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+        if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? CGRT_ERR_OOM : CGRT_ERR_CUDA,
+                                          std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        ptrs.push_back(*p);
+        return CGRT_OK;
+    }
+    int stream()
+    {
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        return CGRT_OK;
+    }
+};
+#define RC(x)              \
+    do {                   \
+        int rc_ = (x);     \
+        if (rc_) return rc_; \
+    } while (0)
+
+int cgrt_intersect_closest(cgrt_scene* s, const cgrt_ray* rays, size_t n, cgrt_hit* hits, uint32_t* counts)
+{
+    if (!s || (n && (!rays || !hits))) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(s->device));
+    if (n == 0) return CGRT_OK;
+    Scratch sc;
+    RC(sc.stream());
+    void *dR, *dH, *dC = nullptr;
+    RC(sc.alloc(&dR, n * sizeof(cgrt_ray)));
+    RC(sc.alloc(&dH, n * sizeof(cgrt_hit)));
+    if (counts) RC(sc.alloc(&dC, n * 2 * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(dR, rays, n * sizeof(cgrt_ray), cudaMemcpyHostToDevice, sc.st));
+    RC(cgrt_intersect_closest_device(s, (const cgrt_ray*)dR, n, (cgrt_hit*)dH, (uint32_t*)dC, sc.st));
+    CK(cudaMemcpyAsync(hits, dH, n * sizeof(cgrt_hit), cudaMemcpyDeviceToHost, sc.st));
+    if (counts) CK(cudaMemcpyAsync(counts, dC, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc.st));
+    CK(cudaStreamSynchronize(sc.st));
+    return CGRT_OK;
+}
+
+int cgrt_intersect_any(cgrt_scene* s, const cgrt_ray* rays, const float* max_dist, float eps, size_t n, uint8_t* occluded)
+{
+    if (!s || (n && (!rays || !max_dist || !occluded))) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(s->device));
+    if (n == 0) return CGRT_OK;
+    Scratch sc;
+    RC(sc.stream());
+    void *dR, *dM, *dO;
+    RC(sc.alloc(&dR, n * sizeof(cgrt_ray)));
+    RC(sc.alloc(&dM, n * sizeof(float)));
+    RC(sc.alloc(&dO, n));
+    CK(cudaMemcpyAsync(dR, rays, n * sizeof(cgrt_ray), cudaMemcpyHostToDevice, sc.st));
+    CK(cudaMemcpyAsync(dM, max_dist, n * sizeof(float), cudaMemcpyHostToDevice, sc.st));
+    RC(cgrt_intersect_any_device(s, (const cgrt_ray*)dR, (const float*)dM, eps, n, (uint8_t*)dO, sc.st));
+    CK(cudaMemcpyAsync(occluded, dO, n, cudaMemcpyDeviceToHost, sc.st));
+    CK(cudaStreamSynchronize(sc.st));
+    return CGRT_OK;
+}
+
+int cgrt_intersect_brute(cgrt_scene* s, const cgrt_ray* rays, size_t n, cgrt_hit* hits)
+{
+    if (!s || (n && (!rays || !hits))) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(s->device));
+    if (n == 0) return CGRT_OK;
+    Scratch sc;
+    RC(sc.stream());
+    void *dR, *dH;
+    RC(sc.alloc(&dR, n * sizeof(cgrt_ray)));
+    RC(sc.alloc(&dH, n * sizeof(cgrt_hit)));
+    CK(cudaMemcpyAsync(dR, rays, n * sizeof(cgrt_ray), cudaMemcpyHostToDevice, sc.st));
+    DevScene S;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        S = s->dev;
+    }
+    launchBruteBatch(S, (const float4*)dR, n, (float4*)dH, s->di.numSMs, sc.st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hits, dH, n * sizeof(cgrt_hit), cudaMemcpyDeviceToHost, sc.st));
+    CK(cudaStreamSynchronize(sc.st));
+    return CGRT_OK;
+}
+
+// ---- unit predicates -------------------------------------------------------------------------------------------------
+struct UnitIO {
+    Scratch sc;
+    int in(void** d, const void* h, size_t bytes)
+    {
+        RC(sc.alloc(d, bytes));
+        CK(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, sc.st));
+        return CGRT_OK;
+    }
+    int out(void* h, const void* d, size_t bytes)
+    {
+        CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, sc.st));
+        return CGRT_OK;
+    }
+    int finish()
+    {
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(sc.st));
+        return CGRT_OK;
+    }
+};
+
+int cgrt_ray_aabb(int device, const float* boxes, const cgrt_ray* rays, size_t n, uint8_t* hit, float* t)
+{
+    if (n && (!boxes || !rays || !hit || !t)) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(device));
+    if (!n) return CGRT_OK;
+    UnitIO io;
+    RC(io.sc.stream());
+    void *dB, *dR, *dH, *dT;
+    RC(io.in(&dB, boxes, n * 24));
+    RC(io.in(&dR, rays, n * 32));
+    RC(io.sc.alloc(&dH, n));
+    RC(io.sc.alloc(&dT, n * 4));
+    launchUnitAabb((const float*)dB, (const float4*)dR, n, (uint8_t*)dH, (float*)dT, io.sc.st);
+    RC(io.out(hit, dH, n));
+    RC(io.out(t, dT, n * 4));
+    return io.finish();
+}
+
+int cgrt_ray_triangle(int device, const float* tris, const cgrt_ray* rays, size_t n, cgrt_hit* out)
+{
+    if (n && (!tris || !rays || !out)) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(device));
+    if (!n) return CGRT_OK;
+    UnitIO io;
+    RC(io.sc.stream());
+    void *dT, *dR, *dO;
+    RC(io.in(&dT, tris, n * 72));
+    RC(io.in(&dR, rays, n * 32));
+    RC(io.sc.alloc(&dO, n * 32));
+    launchUnitTriangle((const float*)dT, (const float4*)dR, n, (float4*)dO, io.sc.st);
+    RC(io.out(out, dO, n * 32));
+    return io.finish();
+}
+
+int cgrt_ray_plane(int device, const float* planes, const cgrt_ray* rays, size_t n, uint8_t* hit, float* t)
+{
+    if (n && (!planes || !rays || !hit || !t)) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(device));
+    if (!n) return CGRT_OK;
+    UnitIO io;
+    RC(io.sc.stream());
+    void *dP, *dR, *dH, *dT;
+    RC(io.in(&dP, planes, n * 16));
+    RC(io.in(&dR, rays, n * 32));
+    RC(io.sc.alloc(&dH, n));
+    RC(io.sc.alloc(&dT, n * 4));
+    launchUnitPlane((const float4*)dP, (const float4*)dR, n, (uint8_t*)dH, (float*)dT, io.sc.st);
+    RC(io.out(hit, dH, n));
+    RC(io.out(t, dT, n * 4));
+    return io.finish();
+}
+
+int cgrt_triangle_plane(int device, const float* tris, size_t n, float* planes)
+{
+    if (n && (!tris || !planes)) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(device));
+    if (!n) return CGRT_OK;
+    UnitIO io;
+    RC(io.sc.stream());
+    void *dT, *dP;
+    RC(io.in(&dT, tris, n * 36));
+    RC(io.sc.alloc(&dP, n * 16));
+    launchUnitTrianglePlane((const float*)dT, n, (float4*)dP, io.sc.st);
+    RC(io.out(planes, dP, n * 16));
+    return io.finish();
+}
+
+int cgrt_point_in_triangle(int device, const float* in, size_t n, uint8_t* inside)
+{
+    if (n && (!in || !inside)) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(device));
+    if (!n) return CGRT_OK;
+    UnitIO io;
+    RC(io.sc.stream());
+    void *dI, *dO;
+    RC(io.in(&dI, in, n * 60));
+    RC(io.sc.alloc(&dO, n));
+    launchUnitPointInTriangle((const float*)dI, n, (uint8_t*)dO, io.sc.st);
+    RC(io.out(inside, dO, n));
+    return io.finish();
+}
+
+int cgrt_ray_sphere(int device, const float* spheres, const cgrt_ray* rays, size_t n, float* out)
+{
+    if (n && (!spheres || !rays || !out)) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(device));
+    if (!n) return CGRT_OK;
+    UnitIO io;
+    RC(io.sc.stream());
+    void *dS, *dR, *dO;
+    RC(io.in(&dS, spheres, n * 16));
+    RC(io.in(&dR, rays, n * 32));
+    RC(io.sc.alloc(&dO, n * 20));
+    launchUnitSphere((const float4*)dS, (const float4*)dR, n, (float*)dO, io.sc.st);
+    RC(io.out(out, dO, n * 20));
+    return io.finish();
+}
+
+int cgrt_generate_rays(int device, const cgrt_camera* cam, int32_t width, int32_t height, cgrt_ray* rays)
+{
+    if (!cam || !rays || width <= 0 || height <= 0) return fail(CGRT_ERR_INVALID, "bad argument");
+    RC(useDevice(device));
+    FrameParams P;
+    std::memset(&P, 0, sizeof P);
+    cameraConstants(*cam, P);
+    P.width = width;
+    P.height = height;
+    UnitIO io;
+    RC(io.sc.stream());
+    void *dP, *dR;
+    RC(io.in(&dP, &P, sizeof P));
+    const size_t n = (size_t)width * height;
+    RC(io.sc.alloc(&dR, n * 32));
+    launchGenerateRays((const FrameParams*)dP, (int)n, (float4*)dR, io.sc.st);
+    RC(io.out(rays, dR, n * 32));
+    return io.finish();
+}
+
+// ---- rendering -----------------------------------------------------------------------------------------------------
+size_t cgrt_tile_buffer_floats(const cgrt_render_params* p)
+{
+    if (checkRenderParams(p)) return 0;
+    if (p->world == 1) return (size_t)p->width * p->height * 3;
+    TileLayout L;
+    makeTileLayout(*p, L);
+    return (size_t)L.maxTiles * L.tileW * L.tileH * 3;
+}
+
+static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, FrameParams& P,
+                        const int** dTileList)
+{
+    TileLayout L;
+    makeTileLayout(*p, L);
+    std::memset(&P, 0, sizeof P);
+    cameraConstants(*cam, P);
+    P.width = p->width;
+    P.height = p->height;
+    P.nLights = (int)s->lights.size();
+    P.traceLimit = p->trace_limit;
+    P.tileW = L.tileW;
+    P.tileH = L.tileH;
+    P.tilesX = L.tilesX;
+    P.world = L.world;
+    P.rank = p->rank;
+    const std::vector<int>& mine = L.lists[p->rank];
+    P.nSlots = (int)mine.size() * L.tileW * L.tileH;
+    *dTileList = nullptr;
+    if (L.world > 1) {
+        const int key[6] = {p->width, p->height, L.tileW, L.tileH, L.world, p->rank};
+        if (std::memcmp(key, s->tileKey, sizeof key) != 0 || !s->tileList.p) {
+            RC(s->tileList.ensure(mine.size()));
+            CK(cudaDeviceSynchronize()); // a previous frame may still read the old list
+            if (!mine.empty())
+                CK(cudaMemcpy(s->tileList.p, mine.data(), mine.size() * sizeof(int), cudaMemcpyHostToDevice));
+            std::memcpy(s->tileKey, key, sizeof key);
+        }
+        *dTileList = s->tileList.p;
+    }
+    // queues sized for the worst case (every pixel hits, every hit bounces); only the used prefix is touched
+    const size_t cap = (size_t)std::max(P.nSlots, 1);
+    const int nL = std::max(P.nLights, 1);
+    const int levels = std::max(P.traceLimit - 1, 1);
+    RC(s->hitQ.ensure(cap * 3));
+    RC(s->bounceQ.ensure(cap * 2));
+    RC(s->lit.ensure(cap * nL));
+    RC(s->pathPix.ensure(cap));
+    RC(s->pathState.ensure(cap * 2 * levels));
+    RC(s->counts.ensure(CGRT_CNT_TOTAL));
+    // parameter block: FrameParams header + lights (2 x float4 each)
+    const size_t need = CGRT_PARAM_BLOCK_HEADER + (size_t)nL * 32;
+    if (need > s->paramBlockBytes || !s->hParamRing) {
+        CK(cudaDeviceSynchronize());
+        if (s->hParamRing) cudaFreeHost(s->hParamRing);
+        s->hParamRing = nullptr;
+        s->paramBlockBytes = std::max(need, (size_t)CGRT_PARAM_BLOCK_HEADER + 16 * 32);
+        CK(cudaMallocHost((void**)&s->hParamRing, s->paramBlockBytes * cgrt_scene::RING));
+        RC(s->dParamBlock.ensure(s->paramBlockBytes));
+    }
+    return CGRT_OK;
+}
+
+static_assert(sizeof(FrameParams) <= CGRT_PARAM_BLOCK_HEADER, "FrameParams must fit the parameter block header");
+
+int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, float* d_out, void* stream)
+{
+    if (!s || !cam || !d_out) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(checkRenderParams(p));
+    RC(useDevice(s->device));
+    std::lock_guard<std::mutex> lk(s->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    FrameParams P;
+    const int* dTiles = nullptr;
+    RC(prepareFrame(s, cam, p, P, &dTiles));
+    // per-frame upload (camera constants + lights, read live from the scene like src/main.cpp:835-876 allows)
+    unsigned char* slot = s->hParamRing + (size_t)s->ringPos * s->paramBlockBytes;
+    s->ringPos = (s->ringPos + 1) % cgrt_scene::RING;
+    std::memcpy(slot, &P, sizeof P);
+    float4* hl = (float4*)(slot + CGRT_PARAM_BLOCK_HEADER);
+    for (size_t i = 0; i < s->lights.size(); i++) {
+        const cgrt_point_light& l = s->lights[i];
+        hl[2 * i] = make_float4(l.position[0], l.position[1], l.position[2], 0.0f);
+        hl[2 * i + 1] = make_float4(l.color[0], l.color[1], l.color[2], 0.0f);
+    }
+    const size_t bytes = CGRT_PARAM_BLOCK_HEADER + s->lights.size() * 32;
+    CK(cudaMemcpyAsync(s->dParamBlock.p, slot, bytes, cudaMemcpyHostToDevice, st));
+    WaveBuffers B;
+    B.hitQ = s->hitQ.p;
+    B.bounceQ = s->bounceQ.p;
+    B.lit = s->lit.p;
+    B.pathPix = s->pathPix.p;
+    B.pathState = s->pathState.p;
+    B.counts = s->counts.p;
+    B.cap = (size_t)std::max(P.nSlots, 1);
+    CK(cudaEventRecord(s->ev0, st));
+    const int launches = launchWavefront(s->dev, (const FrameParams*)s->dParamBlock.p, P,
+                                         (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), B, dTiles, d_out,
+                                         s->di.numSMs, st);
+    CK(cudaEventRecord(s->ev1, st));
+    CK(cudaGetLastError());
+    s->lastStream = st;
+    s->lastLaunches = (uint64_t)launches;
+    s->lastParams = P;
+    s->haveLast = true;
+    return CGRT_OK;
+}
+
+int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
+{
+    if (!s || !stats) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(s->device));
+    std::lock_guard<std::mutex> lk(s->mu);
+    std::memset(stats, 0, sizeof *stats);
+    if (!s->haveLast) return fail(CGRT_ERR_INVALID, "no frame rendered yet");
+    CK(cudaStreamSynchronize(s->lastStream));
+    int counts[CGRT_CNT_TOTAL];
+    CK(cudaMemcpy(counts, s->counts.p, sizeof counts, cudaMemcpyDeviceToHost));
+    const FrameParams& P = s->lastParams;
+    // logical rays: primary = pixels of this rank inside the image
+    uint64_t primary = 0;
+    {
+        cgrt_render_params rp;
+        std::memset(&rp, 0, sizeof rp);
+        rp.width = P.width; rp.height = P.height; rp.world = P.world; rp.rank = P.rank; rp.tile_w = P.tileW; rp.tile_h = P.tileH;
+        TileLayout L;
+        makeTileLayout(rp, L);
+        for (int g : L.lists[P.rank]) {
+            const int ty = g / L.tilesX, tx = g % L.tilesX;
+            const int w = std::min(L.tileW, P.width - tx * L.tileW), h = std::min(L.tileH, P.height - ty * L.tileH);
+            primary += (uint64_t)w * h;
+        }
+    }
+    stats->primary = primary;
+    stats->primary_hit = (uint64_t)counts[CGRT_CNT_HIT + 0];
+    for (int l = 0; l < P.traceLimit; l++) {
+        stats->shadow += (uint64_t)counts[CGRT_CNT_HIT + l] * (uint64_t)P.nLights;
+        if (l >= 1) stats->bounce += (uint64_t)counts[CGRT_CNT_BOUNCE + l];
+    }
+    if (P.traceLimit == 0) stats->primary = 0;
+    stats->kernel_launches = s->lastLaunches;
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    stats->device_ms = ms;
+    return CGRT_OK;
+}
+
+int cgrt_render(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, float* rgb, cgrt_render_stats* stats)
+{
+    if (!s || !cam || !rgb) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(checkRenderParams(p));
+    RC(useDevice(s->device));
+    const size_t frameFloats = (size_t)p->width * p->height * 3;
+    const size_t outFloats = cgrt_tile_buffer_floats(p);
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        RC(s->frame.ensure(std::max(frameFloats, outFloats)));
+    }
+    RC(cgrt_render_device(s, cam, p, s->frame.p, s->stream));
+    if (p->world == 1) {
+        CK(cudaMemcpyAsync(rgb, s->frame.p, frameFloats * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+    } else {
+        // scatter this rank's tiles into the caller's full-size frame (other pixels untouched)
+        std::vector<float> tiles(outFloats);
+        CK(cudaMemcpyAsync(tiles.data(), s->frame.p, outFloats * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        TileLayout L;
+        makeTileLayout(*p, L);
+        const std::vector<int>& mine = L.lists[p->rank];
+        const int tpx = L.tileW * L.tileH;
+        for (size_t lt = 0; lt < mine.size(); lt++) {
+            const int g = mine[lt], ty = g / L.tilesX, tx = g % L.tilesX;
+            for (int q = 0; q < tpx; q++) {
+                const int x = tx * L.tileW + q % L.tileW, y = ty * L.tileH + q / L.tileW;
+                if (x >= p->width || y >= p->height) continue;
+                const float* src = tiles.data() + 3 * (lt * tpx + q);
+                float* dst = rgb + 3 * ((size_t)(p->height - 1 - y) * p->width + x);
+                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+            }
+        }
+    }
+    if (stats) RC(cgrt_render_collect_stats(s, stats));
+    return CGRT_OK;
+}
+
+// cached tile lists of every rank for the assemble step on rank 0
+struct AssembleCache {
+    int key[6] = {0, 0, 0, 0, 0, 0};
+    int* dLists = nullptr;
+    int* dCounts = nullptr;
+    TileLayout L;
+};
+static std::mutex g_asmMu;
+static std::map<int, AssembleCache> g_asm; // per device
+
+int cgrt_assemble_tiles(int device, const cgrt_render_params* p, const float* d_gathered, float* d_frame, void* stream)
+{
+    if (!d_gathered || !d_frame) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(checkRenderParams(p));
+    RC(useDevice(device));
+    DeviceInfo di;
+    RC(deviceInfo(device, di));
+    std::lock_guard<std::mutex> lk(g_asmMu);
+    AssembleCache& c = g_asm[device];
+    TileLayout L;
+    makeTileLayout(*p, L);
+    const int key[6] = {p->width, p->height, L.tileW, L.tileH, L.world, 1};
+    if (std::memcmp(key, c.key, sizeof key) != 0) {
+        CK(cudaDeviceSynchronize());
+        if (c.dLists) cudaFree(c.dLists);
+        if (c.dCounts) cudaFree(c.dCounts);
+        c.dLists = c.dCounts = nullptr;
+        std::vector<int> lists((size_t)L.world * std::max(L.maxTiles, 1), 0), counts(L.world, 0);
+        for (int r = 0; r < L.world; r++) {
+            counts[r] = (int)L.lists[r].size();
+            std::copy(L.lists[r].begin(), L.lists[r].end(), lists.begin() + (size_t)r * L.maxTiles);
+        }
+        CK(cudaMalloc((void**)&c.dLists, lists.size() * sizeof(int)));
+        CK(cudaMalloc((void**)&c.dCounts, counts.size() * sizeof(int)));
+        CK(cudaMemcpy(c.dLists, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c.dCounts, counts.data(), counts.size() * sizeof(int), cudaMemcpyHostToDevice));
+        std::memcpy(c.key, key, sizeof key);
+        c.L = L;
+    }
+    const size_t perRank = (size_t)L.maxTiles * L.tileW * L.tileH * 3;
+    launchAssemble(d_gathered, perRank, c.dLists, c.dCounts, L.maxTiles, L.world, L.tileW, L.tileH, L.tilesX, p->width,
+                   p->height, d_frame, di.numSMs, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return CGRT_OK;
+}
+
+int cgrt_quantize_rgba8(int device, const float* d_frame, size_t n_pixels, uint8_t* d_rgba8, void* stream)
+{
+    if (n_pixels && (!d_frame || !d_rgba8)) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(device));
+    launchQuantize(d_frame, n_pixels, d_rgba8, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return CGRT_OK;
+}
+
+// ---- memory helpers ------------------------------------------------------------------------------------------------
+int cgrt_device_malloc(int device, size_t bytes, void** out)
+{
+    if (!out) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(device));
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? CGRT_ERR_OOM : CGRT_ERR_CUDA, cudaGetErrorString(e));
+    return CGRT_OK;
+}
+int cgrt_device_free(int device, void* p)
+{
+    RC(useDevice(device));
+    CK(cudaFree(p));
+    return CGRT_OK;
+}
+int cgrt_host_alloc_pinned(size_t bytes, void** out)
+{
+    if (!out) return fail(CGRT_ERR_INVALID, "null argument");
+    CK(cudaMallocHost(out, bytes ? bytes : 1));
+    return CGRT_OK;
+}
+int cgrt_host_free_pinned(void* p)
+{
+    CK(cudaFreeHost(p));
+    return CGRT_OK;
+}
+int cgrt_memcpy_h2d(int device, void* dst, const void* src, size_t bytes)
+{
+    RC(useDevice(device));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return CGRT_OK;
+}
+int cgrt_memcpy_d2h(int device, void* dst, const void* src, size_t bytes)
+{
+    RC(useDevice(device));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return CGRT_OK;
+}
+int cgrt_device_synchronize(int device)
+{
+    RC(useDevice(device));
+    CK(cudaDeviceSynchronize());
+    return CGRT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,605 @@
+// sm_100a kernels of the hot path: batch queries, the unit predicates, and the wavefront renderer.
+// Strict build: -fmad=false, IEEE div/sqrt. No tensor cores (the path is not a dense contraction), no OptiX.
+#include "cgrt_kernels.h"
+#include "cgrt_device.cuh"
+
+#include <float.h>
+
+namespace cgrt {
+
+// =================================================================================================================
+// Scene set-up: planes of all triangles (trianglePlane, src/ray_tracing.cpp:74-82) computed once, on the device.
+// =================================================================================================================
+__global__ void k_setup_planes(const float4* __restrict__ v0, const float4* __restrict__ v1, const float4* __restrict__ v2,
+                               float4* __restrict__ pl, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pl[i] = trianglePlaneDev(mk3(v0[i]), mk3(v1[i]), mk3(v2[i]));
+}
+
+// =================================================================================================================
+// Batch closest hit: one thread per ray.  BoundingVolumeHierarchy::intersect, src/bounding_volume_hierarchy.cpp:850-881
+// =================================================================================================================
+RT_DEV void writeHit(const DevScene& S, const V3& o, const V3& d, float tIn, bool hit, const TraceResult& R, float4* out)
+{
+    float4 h0 = make_float4(hit ? R.t : tIn, i2f(-1), 0.0f, 0.0f);
+    float4 h1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (hit) {
+        if (R.sphere >= 0) {
+            const int srcTri = R.tri >= 0 ? f2i(__ldg(S.triV0 + R.tri).w) : -1;
+            h0.y = i2f(-2 - R.sphere);
+            h0.z = i2f(srcTri);
+            h1.y = R.sphereN.x; h1.z = R.sphereN.y; h1.w = R.sphereN.z;
+        } else {
+            const int i = R.tri;
+            const float4 v0 = __ldg(S.triV0 + i), v1 = __ldg(S.triV1 + i), v2 = __ldg(S.triV2 + i);
+            const float4 n0 = __ldg(S.triN0 + i), n1 = __ldg(S.triN1 + i), n2 = __ldg(S.triN2 + i);
+            const float4 pl = __ldg(S.triPl + i);
+            float al, be, ga;
+            V3 nn;
+            hitEpilogue(mk3(v0), mk3(v1), mk3(v2), mk3(n0), mk3(n1), mk3(n2), mk3(pl), o, d, R.t, al, be, ga, nn);
+            h0.y = v0.w; // global id bits
+            h0.z = al; h0.w = be;
+            h1.x = ga; h1.y = nn.x; h1.z = nn.y; h1.w = nn.z;
+        }
+    }
+    out[0] = h0;
+    out[1] = h1;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_closest_batch(DevScene S, const float4* __restrict__ rays, size_t n,
+                                                       float4* __restrict__ hits, uint32_t* __restrict__ counts)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 r0 = __ldg(rays + 2 * i), r1 = __ldg(rays + 2 * i + 1);
+        const V3 o = mk3(r0), d = mk3(r1);
+        TraceResult R;
+        uint32_t nBox = 0, nTri = 0;
+        const bool hit = traverseStrict<false, COUNT>(S, o, d, r0.w, 0.0f, 0.0f, R, nBox, nTri);
+        writeHit(S, o, d, r0.w, hit, R, hits + 2 * i);
+        if (COUNT) {
+            counts[2 * i] = nBox;
+            counts[2 * i + 1] = nTri;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_any_batch(DevScene S, const float4* __restrict__ rays,
+                                                   const float* __restrict__ maxDist, float eps, size_t n,
+                                                   uint8_t* __restrict__ occluded)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 r0 = __ldg(rays + 2 * i), r1 = __ldg(rays + 2 * i + 1);
+        TraceResult R;
+        uint32_t nBox = 0, nTri = 0;
+        const bool sh = traverseStrict<true, false>(S, mk3(r0), mk3(r1), r0.w, eps, __ldg(maxDist + i), R, nBox, nTri);
+        occluded[i] = sh ? 1 : 0;
+    }
+}
+
+// intersectRayWithShape(const Mesh&, ...) over every mesh in scene order, src/ray_tracing.cpp:202-213
+__global__ void __launch_bounds__(128) k_brute_batch(DevScene S, const float4* __restrict__ rays, size_t n,
+                                                     float4* __restrict__ hits)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 r0 = __ldg(rays + 2 * i), r1 = __ldg(rays + 2 * i + 1);
+        const V3 o = mk3(r0), d = mk3(r1);
+        TraceResult R;
+        R.sphere = -1;
+        R.tri = -1;
+        float t = r0.w;
+        for (int g = 0; g < S.nTris; g++) {
+            const int k = __ldg(S.origToLeaf + g);
+            const float4 pl = __ldg(S.triPl + k);
+            float tt;
+            if (planeTest(mk3(pl), pl.w, o, d, t, tt)) {
+                const float4 v0 = __ldg(S.triV0 + k), v1 = __ldg(S.triV1 + k), v2 = __ldg(S.triV2 + k);
+                if (pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), mk3(pl), o + d * tt)) {
+                    t = tt;
+                    R.tri = k;
+                }
+            }
+        }
+        R.t = t;
+        writeHit(S, o, d, r0.w, R.tri >= 0, R, hits + 2 * i);
+    }
+}
+
+// =================================================================================================================
+// Unit predicates (src/ray_tracing.h:10-20), one element per thread
+// =================================================================================================================
+__global__ void k_unit_aabb(const float* __restrict__ boxes, const float4* __restrict__ rays, size_t n,
+                            uint8_t* __restrict__ hit, float* __restrict__ t)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* b = boxes + 6 * i;
+    const float4 r0 = rays[2 * i], r1 = rays[2 * i + 1];
+    float th;
+    const bool h = slabTest(mk3(b[0], b[1], b[2]), mk3(b[3], b[4], b[5]), mk3(r0), mk3(r1), r0.w, th);
+    hit[i] = h;
+    t[i] = h ? th : r0.w;
+}
+
+__global__ void k_unit_triangle(const float* __restrict__ tris, const float4* __restrict__ rays, size_t n,
+                                float4* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* q = tris + 18 * i;
+    const V3 v0 = mk3(q[0], q[1], q[2]), v1 = mk3(q[3], q[4], q[5]), v2 = mk3(q[6], q[7], q[8]);
+    const V3 n0 = mk3(q[9], q[10], q[11]), n1 = mk3(q[12], q[13], q[14]), n2 = mk3(q[15], q[16], q[17]);
+    const float4 r0 = rays[2 * i], r1 = rays[2 * i + 1];
+    const V3 o = mk3(r0), d = mk3(r1);
+    const float4 pl = trianglePlaneDev(v0, v1, v2);
+    float4 h0 = make_float4(r0.w, i2f(0), 0.0f, 0.0f), h1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float tt;
+    if (planeTest(mk3(pl), pl.w, o, d, r0.w, tt) && pointInTriangleDev(v0, v1, v2, mk3(pl), o + d * tt)) {
+        float al, be, ga;
+        V3 nn;
+        hitEpilogue(v0, v1, v2, n0, n1, n2, mk3(pl), o, d, tt, al, be, ga, nn);
+        h0 = make_float4(tt, i2f(1), al, be);
+        h1 = make_float4(ga, nn.x, nn.y, nn.z);
+    }
+    out[2 * i] = h0;
+    out[2 * i + 1] = h1;
+}
+
+__global__ void k_unit_plane(const float4* __restrict__ planes, const float4* __restrict__ rays, size_t n,
+                             uint8_t* __restrict__ hit, float* __restrict__ t)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 pl = planes[i], r0 = rays[2 * i], r1 = rays[2 * i + 1];
+    float tt;
+    const bool h = planeTest(mk3(pl), pl.w, mk3(r0), mk3(r1), r0.w, tt);
+    hit[i] = h;
+    t[i] = h ? tt : r0.w;
+}
+
+__global__ void k_unit_triangle_plane(const float* __restrict__ tris, size_t n, float4* __restrict__ planes)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* q = tris + 9 * i;
+    planes[i] = trianglePlaneDev(mk3(q[0], q[1], q[2]), mk3(q[3], q[4], q[5]), mk3(q[6], q[7], q[8]));
+}
+
+__global__ void k_unit_point_in_triangle(const float* __restrict__ in, size_t n, uint8_t* __restrict__ inside)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* q = in + 15 * i;
+    inside[i] = pointInTriangleDev(mk3(q[0], q[1], q[2]), mk3(q[3], q[4], q[5]), mk3(q[6], q[7], q[8]),
+                                   mk3(q[9], q[10], q[11]), mk3(q[12], q[13], q[14]));
+}
+
+__global__ void k_unit_sphere(const float4* __restrict__ spheres, const float4* __restrict__ rays, size_t n,
+                              float* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 s = spheres[i], r0 = rays[2 * i], r1 = rays[2 * i + 1];
+    float ts;
+    V3 nn = mk3(0.0f, 0.0f, 0.0f);
+    const bool h = sphereTest(mk3(s), s.w, mk3(r0), mk3(r1), r0.w, ts, nn);
+    float* o = out + 5 * i;
+    o[0] = h ? ts : r0.w;
+    o[1] = i2f(h ? 1 : 0);
+    o[2] = nn.x; o[3] = nn.y; o[4] = nn.z;
+}
+
+// =================================================================================================================
+// Wavefront renderer.  renderRayTracing + getFinalColor/trace/shade/shading/pointInShadow (src/main.cpp:61-310, 648-697)
+// =================================================================================================================
+// Trackball::generateRay (framework/src/trackball.cpp:92-103) with the host-evaluated constants of FrameParams; the pixel ->
+// NDC mapping is main.cpp:691-693 (pixel corners, left-to-right evaluation).
+RT_DEV V3 quatRotate(const float4& q /* x,y,z,w */, const V3& v)
+{
+    const V3 qv = mk3(q.x, q.y, q.z);
+    const V3 uv = cross3(qv, v);
+    const V3 uuv = cross3(qv, uv);
+    return v + ((uv * q.w) + uuv) * 2.0f;
+}
+RT_DEV V3 primaryDirection(const FrameParams& P, int x, int y)
+{
+    const float px = float(x) / P.width * 2.0f - 1.0f;
+    const float py = float(y) / P.height * 2.0f - 1.0f;
+    const V3 cam = normalize3(mk3(-px * P.halfW, py * P.halfH, 1.0f));
+    return quatRotate(make_float4(P.qx, P.qy, P.qz, P.qw), cam);
+}
+
+// local pixel slot -> (x, y, output index). Slots enumerate this rank's tiles (8x4 pixel patches per warp for coherence).
+RT_DEV bool slotToPixel(const FrameParams& P, const int* __restrict__ tileList, int slot, int& x, int& y, int& outIdx)
+{
+    const int tpx = P.tileW * P.tileH;
+    const int lt = slot / tpx, q = slot - lt * tpx;
+    const int g = tileList ? __ldg(tileList + lt) : lt;
+    const int ty = g / P.tilesX, tx = g - ty * P.tilesX;
+    x = tx * P.tileW + q % P.tileW;
+    y = ty * P.tileH + q / P.tileW;
+    if (x >= P.width || y >= P.height) return false;
+    outIdx = (P.world == 1) ? ((P.height - 1 - y) * P.width + x) : slot; // Screen::setPixel row flip, src/screen.cpp:34
+    return true;
+}
+
+// warp-aggregated queue push: one atomic per warp, slots handed out by lane rank (ballot / popc / shfl)
+RT_DEV int warpPush(int* counter, bool want)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0u) return -1;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return want ? base + __popc(mask & ((1u << lane) - 1u)) : -1;
+}
+
+RT_DEV void storeRGB(float* fb, int idx, const V3& c)
+{
+    fb[3 * (size_t)idx + 0] = c.x;
+    fb[3 * (size_t)idx + 1] = c.y;
+    fb[3 * (size_t)idx + 2] = c.z;
+}
+
+// colour of a path whose trace() at `level` returned `c`: unwind shade() of the levels above,
+// color = directColor + reflectedColor * ks  (src/main.cpp:263), innermost first, exactly as the recursion returns.
+RT_DEV V3 foldPath(const float4* __restrict__ pathState, size_t cap, int level, int pathId, V3 c)
+{
+    for (int j = level - 1; j >= 0; j--) {
+        const float4 dr = pathState[((size_t)j * cap + pathId) * 2];
+        const float4 ks = pathState[((size_t)j * cap + pathId) * 2 + 1];
+        c = mk3(dr) + c * mk3(ks);
+    }
+    return c;
+}
+
+// Hit record (3 x float4) of the shade queue:  [P | matId] [N | outIdx] [D | pathId]
+RT_DEV void pushHitRecord(const DevScene& S, const WaveBuffers& B, int level, bool hit, const TraceResult& R, const V3& o,
+                          const V3& d, int outIdx, int pathId)
+{
+    const int slot = warpPush(B.counts + CGRT_CNT_HIT + level, hit);
+    if (!hit) return;
+    V3 nn;
+    int mat;
+    if (R.sphere >= 0) {
+        nn = R.sphereN;
+        // hitInfo.material stays at the last accepted triangle's material (or the default HitInfo), bvh.cpp:878-879
+        mat = R.tri >= 0 ? f2i(__ldg(S.triV1 + R.tri).w) : -1;
+    } else {
+        const int i = R.tri;
+        const float4 v0 = __ldg(S.triV0 + i), v1 = __ldg(S.triV1 + i), v2 = __ldg(S.triV2 + i);
+        const float4 n0 = __ldg(S.triN0 + i), n1 = __ldg(S.triN1 + i), n2 = __ldg(S.triN2 + i);
+        const float4 pl = __ldg(S.triPl + i);
+        float al, be, ga;
+        hitEpilogue(mk3(v0), mk3(v1), mk3(v2), mk3(n0), mk3(n1), mk3(n2), mk3(pl), o, d, R.t, al, be, ga, nn);
+        mat = f2i(v1.w);
+    }
+    const V3 P = o + d * R.t; // pointOn, src/main.cpp:164
+    float4* rec = B.hitQ + 3 * (size_t)slot;
+    rec[0] = make_float4(P.x, P.y, P.z, i2f(mat));
+    rec[1] = make_float4(nn.x, nn.y, nn.z, i2f(outIdx));
+    rec[2] = make_float4(d.x, d.y, d.z, i2f(pathId));
+}
+
+// ---- level 0: ray generation + closest hit ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_primary(DevScene S, const FrameParams* __restrict__ Pp, WaveBuffers B,
+                                                 const int* __restrict__ tileList, float* __restrict__ fb)
+{
+    const FrameParams P = *Pp;
+    const int n = P.nSlots;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int slot = base + threadIdx.x;
+        int x = 0, y = 0, outIdx = 0;
+        const bool valid = slot < n && slotToPixel(P, tileList, slot, x, y, outIdx);
+        bool hit = false;
+        TraceResult R;
+        V3 o = mk3(P.camX, P.camY, P.camZ), d = mk3(0.0f, 0.0f, 0.0f);
+        if (valid) {
+            d = primaryDirection(P, x, y);
+            uint32_t nb = 0, nt = 0;
+            hit = traverseStrict<false, false>(S, o, d, FLT_MAX, 0.0f, 0.0f, R, nb, nt);
+            if (!hit) storeRGB(fb, outIdx, mk3(0.0f, 0.0f, 0.0f)); // trace(): miss -> black, src/main.cpp:288-294
+        } else if (slot < n && P.world > 1) {
+            storeRGB(fb, slot, mk3(0.0f, 0.0f, 0.0f)); // padding pixels of edge tiles in the tile-major buffer
+        }
+        pushHitRecord(S, B, 0, hit, R, o, d, outIdx, -1);
+    }
+}
+
+// ---- level >= 1: closest hit over the compacted bounce queue --------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_bounce_closest(DevScene S, WaveBuffers B, int level, float* __restrict__ fb)
+{
+    const int n = B.counts[CGRT_CNT_BOUNCE + level];
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool valid = i < n;
+        bool hit = false;
+        TraceResult R;
+        V3 o = mk3(0.0f, 0.0f, 0.0f), d = o;
+        int pathId = -1, outIdx = 0;
+        if (valid) {
+            const float4 r0 = B.bounceQ[2 * (size_t)i], r1 = B.bounceQ[2 * (size_t)i + 1];
+            o = mk3(r0);
+            d = mk3(r1);
+            pathId = f2i(r1.w);
+            outIdx = B.pathPix[pathId];
+            uint32_t nb = 0, nt = 0;
+            hit = traverseStrict<false, false>(S, o, d, r0.w, 0.0f, 0.0f, R, nb, nt);
+            if (!hit) // reflected colour is black; unwind the levels above (src/main.cpp:288-294 then :263)
+                storeRGB(fb, outIdx, foldPath(B.pathState, B.cap, level, pathId, mk3(0.0f, 0.0f, 0.0f)));
+        }
+        pushHitRecord(S, B, level, hit, R, o, d, outIdx, pathId);
+    }
+}
+
+// ---- any-hit shadow rays: one thread per (hit, light).  pointInShadow, src/main.cpp:104-135 -------------------------------
+__global__ void __launch_bounds__(128) k_shadow(DevScene S, const FrameParams* __restrict__ Pp,
+                                                const float4* __restrict__ lights, WaveBuffers B, int level)
+{
+    const int nL = Pp->nLights;
+    const int n = B.counts[CGRT_CNT_HIT + level] * nL;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int h = i / nL, l = i - h * nL;
+        const float4 a = B.hitQ[3 * (size_t)h];
+        const V3 pointOn = mk3(a);
+        const V3 lightPos = mk3(__ldg(lights + 2 * l));
+        const V3 fromPosToLight = lightPos - pointOn;
+        const V3 dir = normalize3(fromPosToLight);
+        const float epsilon = 0.001f;
+        const V3 org = pointOn + epsilon * dir;
+        TraceResult R;
+        uint32_t nb = 0, nt = 0;
+        const bool shadowed =
+            traverseStrict<true, false>(S, org, dir, FLT_MAX, epsilon, length3(fromPosToLight), R, nb, nt);
+        B.lit[i] = shadowed ? 0 : 1;
+    }
+}
+
+// ---- shading + bounce emission: one thread per hit.  shading/shade, src/main.cpp:61-98, 220-264 ---------------------------
+__global__ void __launch_bounds__(128) k_shade(DevScene S, const FrameParams* __restrict__ Pp,
+                                               const float4* __restrict__ lights, WaveBuffers B, int level,
+                                               float* __restrict__ fb)
+{
+    const int nL = Pp->nLights;
+    const int traceLimit = Pp->traceLimit;
+    const int n = B.counts[CGRT_CNT_HIT + level];
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int h = base + threadIdx.x;
+        const bool valid = h < n;
+        bool bounce = false;
+        V3 P = mk3(0.0f, 0.0f, 0.0f), N = P, D = P, result = P, ks = P;
+        int outIdx = 0, pathId = -1;
+        if (valid) {
+            const float4 a = B.hitQ[3 * (size_t)h], b = B.hitQ[3 * (size_t)h + 1], c = B.hitQ[3 * (size_t)h + 2];
+            P = mk3(a); N = mk3(b); D = mk3(c);
+            const int mat = f2i(a.w);
+            outIdx = f2i(b.w);
+            pathId = f2i(c.w);
+            // default-constructed HitInfo material when only a sphere was hit: kd unspecified in the reference (we use 0),
+            // ks 0, shininess 1 (src/mesh.h:17-23)
+            float4 m0 = make_float4(0.0f, 0.0f, 0.0f, 1.0f), m1 = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+            if (mat >= 0) { m0 = __ldg(S.mats + 2 * mat); m1 = __ldg(S.mats + 2 * mat + 1); }
+            const V3 kd = mk3(m0);
+            ks = mk3(m1);
+            const float shininess = m0.w;
+            for (int l = 0; l < nL; l++) { // point-light loop, src/main.cpp:220-232
+                const V3 lightPos = mk3(__ldg(lights + 2 * l)), lightCol = mk3(__ldg(lights + 2 * l + 1));
+                const V3 fromPosToLight = normalize3(lightPos - P);
+                if (!B.lit[(size_t)h * nL + l]) continue;
+                V3 diffuse = mk3(0.0f, 0.0f, 0.0f), specular = diffuse;
+                const float diffuseCos = dot3(fromPosToLight, N); // diffuseOneLight, src/main.cpp:84-98
+                if (!(diffuseCos <= 0)) diffuse = (lightCol * kd) * diffuseCos;
+                const V3 reflected = normalize3(reflect3(D, N)); // specularOneLight, src/main.cpp:61-82
+                const float specularCos = dot3(reflected, fromPosToLight);
+                if (!(specularCos <= 0)) {
+                    // pow(float,float): evaluated in double and narrowed, which reproduces a correctly rounded powf
+                    const float pw = (float)pow((double)specularCos, (double)shininess);
+                    specular = (lightCol * ks) * pw;
+                }
+                result = result + diffuse;
+                result = result + specular;
+            }
+            V3 colour;
+            bool terminal = true;
+            if (ks.z <= 0.01f) { // comma operator: only ks.z decides, src/main.cpp:246
+                colour = result;
+            } else if (level + 1 >= traceLimit) { // trace(level+1) returns black without a ray, src/main.cpp:267-272
+                colour = result + mk3(0.0f, 0.0f, 0.0f) * ks;
+            } else {
+                terminal = false;
+                bounce = true;
+            }
+            if (terminal) storeRGB(fb, outIdx, foldPath(B.pathState, B.cap, level, pathId, colour));
+        }
+        const int slot = warpPush(B.counts + CGRT_CNT_BOUNCE + level + 1, bounce);
+        if (bounce) {
+            // ComputeReflectedRay, src/main.cpp:252-256: t = |incoming direction|, origin offset by 0.001 along the reflection
+            const V3 reflected = normalize3(reflect3(D, N));
+            const float tmax = length3(D);
+            const float epsilon = 0.001f;
+            const V3 org = P + epsilon * reflected;
+            if (level == 0) {
+                pathId = slot; // a path is born at its first bounce; its id indexes pathState / pathPix
+                B.pathPix[pathId] = outIdx;
+            }
+            B.bounceQ[2 * (size_t)slot] = make_float4(org.x, org.y, org.z, tmax);
+            B.bounceQ[2 * (size_t)slot + 1] = make_float4(reflected.x, reflected.y, reflected.z, i2f(pathId));
+            float4* st = B.pathState + ((size_t)level * B.cap + pathId) * 2;
+            st[0] = make_float4(result.x, result.y, result.z, 0.0f);
+            st[1] = make_float4(ks.x, ks.y, ks.z, 0.0f);
+        }
+    }
+}
+
+// ---- primary rays only (cgrt_generate_rays) --------------------------------------------------------------------------------
+__global__ void k_generate_rays(const FrameParams* __restrict__ Pp, float4* __restrict__ rays)
+{
+    const FrameParams P = *Pp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.width * P.height) return;
+    const int y = i / P.width, x = i - y * P.width;
+    const V3 d = primaryDirection(P, x, y);
+    rays[2 * (size_t)i] = make_float4(P.camX, P.camY, P.camZ, FLT_MAX);
+    rays[2 * (size_t)i + 1] = make_float4(d.x, d.y, d.z, 0.0f);
+}
+
+// ---- rank 0: de-interleave gathered tile buffers into the Screen layout -----------------------------------------------------
+__global__ void k_assemble(const float* __restrict__ gathered, size_t perRankFloats, const int* __restrict__ tileLists,
+                           const int* __restrict__ tileCounts, int maxTiles, int world, int tileW, int tileH, int tilesX,
+                           int width, int height, float* __restrict__ frame)
+{
+    const int tpx = tileW * tileH;
+    const size_t total = (size_t)world * maxTiles * tpx;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / ((size_t)maxTiles * tpx));
+        const int rem = (int)(i - (size_t)r * maxTiles * tpx);
+        const int lt = rem / tpx, q = rem - lt * tpx;
+        if (lt >= tileCounts[r]) continue;
+        const int g = tileLists[(size_t)r * maxTiles + lt];
+        const int ty = g / tilesX, tx = g - ty * tilesX;
+        const int x = tx * tileW + q % tileW, y = ty * tileH + q / tileW;
+        if (x >= width || y >= height) continue;
+        const float* src = gathered + (size_t)r * perRankFloats + 3 * (size_t)rem;
+        float* dst = frame + 3 * ((size_t)(height - 1 - y) * width + x);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    }
+}
+
+// Screen::writeBitmapToFile quantisation, src/screen.cpp:38-49: clamp(c,0,1) = min(max(c,0),1), *255.0f, truncate
+__global__ void k_quantize(const float* __restrict__ frame, size_t nPixels, uint8_t* __restrict__ rgba)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nPixels) return;
+    uchar4 o;
+    float c[3];
+    for (int k = 0; k < 3; k++) {
+        float v = frame[3 * i + k];
+        v = v < 0.0f ? 0.0f : v; // glm::max(x, 0): (x < 0) ? 0 : x
+        v = 1.0f < v ? 1.0f : v; // glm::min(x, 1): (1 < x) ? 1 : x
+        c[k] = v * 255.0f;
+    }
+    o.x = (unsigned char)c[0]; o.y = (unsigned char)c[1]; o.z = (unsigned char)c[2]; o.w = 255;
+    reinterpret_cast<uchar4*>(rgba)[i] = o;
+}
+
+// =================================================================================================================
+// Launch wrappers
+// =================================================================================================================
+static inline int gridFor(size_t n, int block, int maxBlocks)
+{
+    size_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > (size_t)maxBlocks) g = maxBlocks;
+    return (int)g;
+}
+
+void launchSetupPlanes(const float4* v0, const float4* v1, const float4* v2, float4* pl, int n, cudaStream_t st)
+{
+    if (n > 0) k_setup_planes<<<(n + 255) / 256, 256, 0, st>>>(v0, v1, v2, pl, n);
+}
+
+void launchClosestBatch(const DevScene& S, const float4* rays, size_t n, float4* hits, uint32_t* counts, int numSMs,
+                        cudaStream_t st)
+{
+    if (n == 0) return;
+    const int grid = gridFor(n, 128, numSMs * 16);
+    if (counts) k_closest_batch<true><<<grid, 128, 0, st>>>(S, rays, n, hits, counts);
+    else k_closest_batch<false><<<grid, 128, 0, st>>>(S, rays, n, hits, nullptr);
+}
+
+void launchAnyBatch(const DevScene& S, const float4* rays, const float* maxDist, float eps, size_t n, uint8_t* occluded,
+                    int numSMs, cudaStream_t st)
+{
+    if (n == 0) return;
+    k_any_batch<<<gridFor(n, 128, numSMs * 16), 128, 0, st>>>(S, rays, maxDist, eps, n, occluded);
+}
+
+void launchBruteBatch(const DevScene& S, const float4* rays, size_t n, float4* hits, int numSMs, cudaStream_t st)
+{
+    if (n == 0) return;
+    k_brute_batch<<<gridFor(n, 128, numSMs * 16), 128, 0, st>>>(S, rays, n, hits);
+}
+
+void launchUnitAabb(const float* boxes, const float4* rays, size_t n, uint8_t* hit, float* t, cudaStream_t st)
+{
+    if (n) k_unit_aabb<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(boxes, rays, n, hit, t);
+}
+void launchUnitTriangle(const float* tris, const float4* rays, size_t n, float4* out, cudaStream_t st)
+{
+    if (n) k_unit_triangle<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(tris, rays, n, out);
+}
+void launchUnitPlane(const float4* planes, const float4* rays, size_t n, uint8_t* hit, float* t, cudaStream_t st)
+{
+    if (n) k_unit_plane<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(planes, rays, n, hit, t);
+}
+void launchUnitTrianglePlane(const float* tris, size_t n, float4* planes, cudaStream_t st)
+{
+    if (n) k_unit_triangle_plane<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(tris, n, planes);
+}
+void launchUnitPointInTriangle(const float* in, size_t n, uint8_t* inside, cudaStream_t st)
+{
+    if (n) k_unit_point_in_triangle<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(in, n, inside);
+}
+void launchUnitSphere(const float4* spheres, const float4* rays, size_t n, float* out, cudaStream_t st)
+{
+    if (n) k_unit_sphere<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(spheres, rays, n, out);
+}
+
+void launchGenerateRays(const FrameParams* dP, int nPixels, float4* rays, cudaStream_t st)
+{
+    if (nPixels) k_generate_rays<<<(nPixels + 127) / 128, 128, 0, st>>>(dP, rays);
+}
+
+// One frame of the wavefront. Every queue length lives in device memory (B.counts), so the sequence needs no host round trip:
+// the grids are sized for the worst case the host knows (nSlots) and the kernels loop over the device-side count.
+int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
+                    const WaveBuffers& B, const int* dTileList, float* fb, int numSMs, cudaStream_t st)
+{
+    int launches = 0;
+    cudaMemsetAsync(B.counts, 0, sizeof(int) * CGRT_CNT_TOTAL, st);
+    if (hP.traceLimit <= 0) { // trace(0, ...) returns black for every pixel without casting a ray, src/main.cpp:267-272
+        const size_t px = hP.world == 1 ? (size_t)hP.width * hP.height : (size_t)hP.nSlots;
+        cudaMemsetAsync(fb, 0, px * 3 * sizeof(float), st);
+        return 0;
+    }
+    const int persistent = numSMs * 16; // 16 CTAs x 128 threads = 2048 threads/SM when registers allow
+    const int gPrimary = gridFor((size_t)hP.nSlots, 128, 1 << 30);
+    k_primary<<<gPrimary, 128, 0, st>>>(S, dP, B, dTileList, fb);
+    launches++;
+    const int gHit = gridFor((size_t)hP.nSlots, 128, persistent);
+    const int gShadow = gridFor((size_t)hP.nSlots * (hP.nLights > 0 ? hP.nLights : 1), 128, persistent);
+    for (int level = 0; level < hP.traceLimit; level++) {
+        if (level > 0) {
+            k_bounce_closest<<<gHit, 128, 0, st>>>(S, B, level, fb);
+            launches++;
+        }
+        if (hP.nLights > 0) {
+            k_shadow<<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level);
+            launches++;
+        }
+        k_shade<<<gHit, 128, 0, st>>>(S, dP, dLights, B, level, fb);
+        launches++;
+    }
+    return launches;
+}
+
+void launchAssemble(const float* gathered, size_t perRankFloats, const int* tileLists, const int* tileCounts, int maxTiles,
+                    int world, int tileW, int tileH, int tilesX, int width, int height, float* frame, int numSMs,
+                    cudaStream_t st)
+{
+    const size_t total = (size_t)world * maxTiles * tileW * tileH;
+    if (total == 0) return;
+    k_assemble<<<gridFor(total, 256, numSMs * 8), 256, 0, st>>>(gathered, perRankFloats, tileLists, tileCounts, maxTiles,
+                                                               world, tileW, tileH, tilesX, width, height, frame);
+}
+
+void launchQuantize(const float* frame, size_t nPixels, uint8_t* rgba, cudaStream_t st)
+{
+    if (nPixels) k_quantize<<<(unsigned)((nPixels + 255) / 256), 256, 0, st>>>(frame, nPixels, rgba);
+}
+
+} // namespace cgrt

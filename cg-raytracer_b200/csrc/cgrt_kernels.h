@@ -1,0 +1,92 @@
+// Host-visible declarations of the kernel launchers (cgrt_kernels.cu) and the structures they share with cgrt_capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+// ---- HBM layout -----------------------------------------------------------------------------------------------------------
+// nodes     : 2 x float4 per node (32 B, 32-byte aligned):  [lo.xyz | a]  [hi.xyz | b]
+//               inner node: a = index of the left child (right child = a + 1, createTree pushes them consecutively,
+//                           src/bounding_volume_hierarchy.cpp:358-364), b = 0
+//               leaf      : a = first triangle (leaf order), b = triangle count (> 0)
+// triPl     : float4 per triangle (leaf order): plane normal.xyz, D     (trianglePlane, src/ray_tracing.cpp:74-82, precomputed
+//             on the device with the same expression tree -> same bits as the reference's per-test recomputation)
+// triV0/1/2 : float4 per triangle: position.xyz ; triV0.w = global triangle id (bit-cast), triV1.w = mesh/material id
+// triN0/1/2 : float4 per triangle: vertex normal.xyz (read only for the final hit)
+// mats      : 2 x float4 per mesh:  [kd.xyz | shininess] [ks.xyz | transparency]        (src/mesh.h:17-23)
+// spheres   : 3 x float4 per sphere: [center | radius] [kd | shininess] [ks | transparency]  (src/scene.h:36-40)
+struct DevScene {
+    const float4* nodes;
+    const float4* triPl;
+    const float4* triV0;
+    const float4* triV1;
+    const float4* triV2;
+    const float4* triN0;
+    const float4* triN1;
+    const float4* triN2;
+    const float4* mats;
+    const float4* spheres;
+    const int* origToLeaf; // global triangle id -> leaf-order index (brute-force path only)
+    int nNodes;
+    int nTris;
+    int nSpheres;
+    int nMeshes;
+};
+
+
+namespace cgrt {
+
+#define CGRT_STACK 32                           // traversal stack: one pending sibling per level below the root (reference depth 12)
+#define CGRT_MAX_BVH_DEPTH (CGRT_STACK + 1)     // largest cgrt_scene_options::bvh_max_depth the stack supports
+#define CGRT_MAX_LEVELS 16                      // upper bound on cgrt_render_params::trace_limit
+#define CGRT_CNT_HIT 0                          // counts[CGRT_CNT_HIT + level]    = hits found at `level`
+#define CGRT_CNT_BOUNCE CGRT_MAX_LEVELS         // counts[CGRT_CNT_BOUNCE + level] = rays queued for `level` (level >= 1)
+#define CGRT_CNT_TOTAL (2 * CGRT_MAX_LEVELS + 1)
+#define CGRT_PARAM_BLOCK_HEADER 128             // bytes reserved for FrameParams in the per-frame block; lights follow
+
+// Per-frame constants, evaluated on the host with libm exactly as Trackball does (framework/src/trackball.cpp:70-73, 92-103)
+// so that device sinf/cosf/tanf never enter the picture. Uploaded once per render together with the lights.
+struct FrameParams {
+    float camX, camY, camZ; // Trackball::position()
+    float halfW, halfH;     // aspect * tan(fovy/2), tan(fovy/2)
+    float qx, qy, qz, qw;   // glm::quat(m_rotationEulerAngles)
+    int width, height;
+    int nLights;
+    int traceLimit;
+    int nSlots;             // local pixel slots = owned tiles * tileW * tileH
+    int tileW, tileH, tilesX;
+    int world, rank;
+};
+
+// Queues of the wavefront (all sized for the worst case `cap` = nSlots; only the used prefix is ever touched).
+struct WaveBuffers {
+    float4* hitQ;      // 3 x float4 per hit:   [P | matId] [N | outIdx] [D | pathId]
+    float4* bounceQ;   // 2 x float4 per ray:   [origin | tmax] [direction | pathId]
+    uint8_t* lit;      // [hit][light] 1 = light reaches the point
+    int* pathPix;      // [pathId] output index of the path's pixel
+    float4* pathState; // [level][pathId] 2 x float4: directColor, ks of the shade() frame waiting for its reflection
+    int* counts;       // CGRT_CNT_TOTAL queue lengths
+    size_t cap;
+};
+
+void launchSetupPlanes(const float4* v0, const float4* v1, const float4* v2, float4* pl, int n, cudaStream_t st);
+void launchClosestBatch(const DevScene& S, const float4* rays, size_t n, float4* hits, uint32_t* counts, int numSMs,
+                        cudaStream_t st);
+void launchAnyBatch(const DevScene& S, const float4* rays, const float* maxDist, float eps, size_t n, uint8_t* occluded,
+                    int numSMs, cudaStream_t st);
+void launchBruteBatch(const DevScene& S, const float4* rays, size_t n, float4* hits, int numSMs, cudaStream_t st);
+void launchUnitAabb(const float* boxes, const float4* rays, size_t n, uint8_t* hit, float* t, cudaStream_t st);
+void launchUnitTriangle(const float* tris, const float4* rays, size_t n, float4* out, cudaStream_t st);
+void launchUnitPlane(const float4* planes, const float4* rays, size_t n, uint8_t* hit, float* t, cudaStream_t st);
+void launchUnitTrianglePlane(const float* tris, size_t n, float4* planes, cudaStream_t st);
+void launchUnitPointInTriangle(const float* in, size_t n, uint8_t* inside, cudaStream_t st);
+void launchUnitSphere(const float4* spheres, const float4* rays, size_t n, float* out, cudaStream_t st);
+void launchGenerateRays(const FrameParams* dP, int nPixels, float4* rays, cudaStream_t st);
+int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
+                    const WaveBuffers& B, const int* dTileList, float* fb, int numSMs, cudaStream_t st);
+void launchAssemble(const float* gathered, size_t perRankFloats, const int* tileLists, const int* tileCounts, int maxTiles,
+                    int world, int tileW, int tileH, int tilesX, int width, int height, float* frame, int numSMs,
+                    cudaStream_t st);
+void launchQuantize(const float* frame, size_t nPixels, uint8_t* rgba, cudaStream_t st);
+
+} // namespace cgrt
