@@ -67,7 +67,7 @@ EXPORTS = [
     "cgrt_intersect_closest_device", "cgrt_intersect_any", "cgrt_intersect_any_device", "cgrt_intersect_brute",
     "cgrt_ray_aabb", "cgrt_ray_triangle", "cgrt_ray_plane", "cgrt_triangle_plane", "cgrt_point_in_triangle",
     "cgrt_ray_sphere", "cgrt_generate_rays", "cgrt_render", "cgrt_render_device", "cgrt_render_collect_stats",
-    "cgrt_tile_buffer_floats", "cgrt_assemble_tiles", "cgrt_quantize_rgba8", "cgrt_device_malloc", "cgrt_device_free",
+    "cgrt_tile_buffer_floats", "cgrt_tile_list", "cgrt_assemble_tiles", "cgrt_quantize_rgba8", "cgrt_device_malloc", "cgrt_device_free",
     "cgrt_host_alloc_pinned", "cgrt_host_free_pinned", "cgrt_memcpy_h2d", "cgrt_memcpy_d2h", "cgrt_device_synchronize",
 ]
 
@@ -115,6 +115,7 @@ def load_library(path=None):
         "cgrt_render_device": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp, vp]),
         "cgrt_render_collect_stats": (C.c_int, [vp, C.POINTER(RenderStats)]),
         "cgrt_tile_buffer_floats": (sz, [C.POINTER(RenderParams)]),
+        "cgrt_tile_list": (C.c_int, [C.POINTER(RenderParams), i32, i32p, i32]),
         "cgrt_assemble_tiles": (C.c_int, [C.c_int, C.POINTER(RenderParams), vp, vp, vp]),
         "cgrt_quantize_rgba8": (C.c_int, [C.c_int, vp, sz, vp, vp]),
         "cgrt_device_malloc": (C.c_int, [C.c_int, sz, C.POINTER(vp)]),
@@ -337,8 +338,118 @@ def ray_sphere(spheres, rays, device=0):
     return out[:, 0].copy(), out[:, 1].copy().view(np.int32).astype(bool), out[:, 2:5].copy()
 
 
+def tile_list(params, rank):
+    """Global tile ids owned by `rank` under the interleaved partition (host arithmetic only, no GPU needed)."""
+    lib = load_library()
+    n = lib.cgrt_tile_list(C.byref(params), rank, None, 0)
+    if n < 0:
+        raise CgrtError(CGRT_ERR_INVALID, "cgrt_tile_list: bad arguments")
+    out = np.zeros(max(n, 1), np.int32)
+    lib.cgrt_tile_list(C.byref(params), rank, out.ctypes.data_as(C.POINTER(C.c_int32)), n)
+    return out[:n]
+
+
+def tile_buffer_floats(params):
+    return int(load_library().cgrt_tile_buffer_floats(C.byref(params)))
+
+
 def generate_rays(cam, W, H, device=0):
     lib = load_library()
     rays = np.zeros(W * H, RAY_DTYPE)
     check(lib.cgrt_generate_rays(device, C.byref(cam), W, H, _vp(rays)))
     return rays
+
+
+# -- host-side data formats (include/cgrt_host_c.h): OBJ/MTL loader, scene presets, BMP writer ----------------------------
+HOST_EXPORTS = ["cgrt_host_set_default_device", "cgrt_host_scene_load_preset", "cgrt_host_scene_load_obj",
+                "cgrt_host_scene_dragon_standin", "cgrt_host_scene_destroy", "cgrt_host_scene_desc",
+                "cgrt_host_scene_counts", "cgrt_host_scene_lights", "cgrt_write_bmp"]
+
+
+def _host_sigs(lib):
+    if getattr(lib, "_cgrt_host_ready", False):
+        return lib
+    vp = C.c_void_p
+    lib.cgrt_host_set_default_device.argtypes = [C.c_int]
+    lib.cgrt_host_set_default_device.restype = None
+    lib.cgrt_host_scene_load_preset.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
+    lib.cgrt_host_scene_load_obj.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    lib.cgrt_host_scene_dragon_standin.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    lib.cgrt_host_scene_destroy.argtypes = [vp]
+    lib.cgrt_host_scene_destroy.restype = None
+    lib.cgrt_host_scene_desc.argtypes = [vp, C.POINTER(SceneDesc)]
+    lib.cgrt_host_scene_counts.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.cgrt_host_scene_counts.restype = C.c_int64
+    lib.cgrt_host_scene_lights.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    lib.cgrt_write_bmp.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.c_int, C.c_int]
+    lib._cgrt_host_ready = True
+    return lib
+
+
+class HostScene:
+    """A Scene produced by the host loader (loadScene / loadMesh / the dragon stand-in), exposed as flat numpy arrays
+    with the attribute names Scene() expects (vcount, tcount, vertices, triangles, materials, spheres) plus `lights`."""
+
+    def __init__(self, handle, name):
+        lib = _host_sigs(load_library())
+        self.name = name
+        nv, nt = C.c_int64(0), C.c_int64(0)
+        nm = int(lib.cgrt_host_scene_counts(handle, C.byref(nv), C.byref(nt)))
+        d = SceneDesc()
+        if lib.cgrt_host_scene_desc(handle, C.byref(d)) != 0:
+            raise CgrtError(CGRT_ERR_INVALID, "cgrt_host_scene_desc failed")
+        def arr(ptr, count, dtype):
+            if count == 0:
+                return np.zeros(0, dtype)
+            return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
+        self.vcount = arr(d.mesh_vertex_count, nm, np.int32)
+        self.tcount = arr(d.mesh_triangle_count, nm, np.int32)
+        self.vertices = arr(d.vertices, nv.value * 6, np.float32).reshape(-1, 6)
+        self.triangles = arr(d.triangles, nt.value * 3, np.uint32).reshape(-1, 3)
+        self.materials = arr(d.materials, nm * 8, np.float32).reshape(-1, 8)
+        self.spheres = arr(d.spheres, d.n_spheres * 12, np.float32).reshape(-1, 12)
+        nl = lib.cgrt_host_scene_lights(handle, None, 0)
+        self.lights = np.zeros((nl, 6), np.float32)
+        if nl:
+            lib.cgrt_host_scene_lights(handle, _fp(self.lights), nl)
+        lib.cgrt_host_scene_destroy(handle)
+
+    @property
+    def n_triangles(self):
+        return int(self.tcount.sum())
+
+
+def load_preset(preset, data_dir):
+    lib = _host_sigs(load_library())
+    h = C.c_void_p()
+    rc = lib.cgrt_host_scene_load_preset(preset.encode(), str(data_dir).encode(), C.byref(h))
+    if rc != 0:
+        raise CgrtError(rc, f"loadScene({preset}, {data_dir}) failed")
+    return HostScene(h, preset)
+
+
+def load_obj(path, normalize=False):
+    lib = _host_sigs(load_library())
+    h = C.c_void_p()
+    rc = lib.cgrt_host_scene_load_obj(str(path).encode(), int(normalize), C.byref(h))
+    if rc != 0:
+        raise CgrtError(rc, f"loadMesh({path}) failed")
+    return HostScene(h, str(path))
+
+
+def dragon_standin(segments_u=340, segments_v=128):
+    lib = _host_sigs(load_library())
+    h = C.c_void_p()
+    rc = lib.cgrt_host_scene_dragon_standin(segments_u, segments_v, C.byref(h))
+    if rc != 0:
+        raise CgrtError(rc, "dragon stand-in failed")
+    return HostScene(h, f"dragon-standin-{2 * segments_u * segments_v}tri")
+
+
+def write_bmp(path, rgb):
+    lib = _host_sigs(load_library())
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    H, W = rgb.shape[:2]
+    rc = lib.cgrt_write_bmp(str(path).encode(), _fp(rgb), W, H)
+    if rc != 0:
+        raise CgrtError(rc, f"write_bmp({path}) failed")

@@ -699,6 +699,16 @@ size_t cgrt_tile_buffer_floats(const cgrt_render_params* p)
     return (size_t)L.maxTiles * L.tileW * L.tileH * 3;
 }
 
+int cgrt_tile_list(const cgrt_render_params* p, int32_t rank, int32_t* out, int32_t cap)
+{
+    if (checkRenderParams(p) || rank < 0 || rank >= p->world) return -1;
+    TileLayout L;
+    makeTileLayout(*p, L);
+    const std::vector<int>& l = L.lists[rank];
+    for (size_t i = 0; i < l.size() && (int32_t)i < cap; i++) out[i] = l[i];
+    return (int)l.size();
+}
+
 static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, FrameParams& P,
                         const int** dTileList)
 {

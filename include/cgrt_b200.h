@@ -187,6 +187,9 @@ int cgrt_render(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params*
 int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, float* d_out, void* stream);
 int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats);
 size_t cgrt_tile_buffer_floats(const cgrt_render_params* p);
+/* global ids (ty * tilesX + tx, tilesX = ceil(width / tile_w)) of the tiles `rank` owns, increasing; returns the count
+ * (-1 on bad arguments). Pure host arithmetic: callable without a GPU. */
+int cgrt_tile_list(const cgrt_render_params* p, int32_t rank, int32_t* out, int32_t cap);
 /* rank 0 after the gather: d_gathered = [world][cgrt_tile_buffer_floats] -> d_frame [H][W][3] in Screen layout */
 int cgrt_assemble_tiles(int device, const cgrt_render_params* p, const float* d_gathered, float* d_frame, void* stream);
 /* Screen::writeBitmapToFile quantisation (src/screen.cpp:38-49): clamp to [0,1], *255, truncate; rgba8[H*W*4], alpha 255 */
