@@ -38,7 +38,7 @@ class SceneDesc(C.Structure):
 
 
 class SceneOptions(C.Structure):
-    _fields_ = [("device", C.c_int32), ("bvh_max_depth", C.c_int32), ("reserved", C.c_int32 * 6)]
+    _fields_ = [("device", C.c_int32), ("bvh_max_depth", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class Camera(C.Structure):
@@ -48,16 +48,21 @@ class Camera(C.Structure):
 
 class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("trace_limit", C.c_int32), ("rank", C.c_int32),
-                ("world", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("world", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("flags", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class RenderStats(C.Structure):
     _fields_ = [("primary", C.c_uint64), ("primary_hit", C.c_uint64), ("shadow", C.c_uint64), ("bounce", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("device_ms", C.c_float), ("reserved", C.c_float * 3)]
+                ("kernel_launches", C.c_uint64), ("box_tests", C.c_uint64 * 3), ("tri_tests", C.c_uint64 * 3),
+                ("device_ms", C.c_float), ("class_ms", C.c_float * 4), ("class_launches", C.c_uint32 * 4),
+                ("reserved", C.c_float * 3)]
 
     def as_dict(self):
         return dict(primary=int(self.primary), primary_hit=int(self.primary_hit), shadow=int(self.shadow),
-                    bounce=int(self.bounce), kernel_launches=int(self.kernel_launches), device_ms=float(self.device_ms))
+                    bounce=int(self.bounce), kernel_launches=int(self.kernel_launches), device_ms=float(self.device_ms),
+                    box_tests=[int(v) for v in self.box_tests], tri_tests=[int(v) for v in self.tri_tests],
+                    class_ms=[float(v) for v in self.class_ms], class_launches=[int(v) for v in self.class_launches])
 
 
 EXPORTS = [
@@ -166,9 +171,15 @@ def make_camera(W, H, fovy_deg=50.0, dist=3.0, look_at=(0.0, 0.0, 0.0), euler_de
     return c
 
 
-def render_params(W, H, trace_limit=2, rank=0, world=1, tile_w=0, tile_h=0):
+K_PRIMARY, K_BOUNCE, K_SHADOW, K_SHADE = 0, 1, 2, 3
+KERNEL_CLASS_NAMES = ["k_primary", "k_bounce_closest", "k_shadow", "k_shade"]
+RENDER_PROFILE_ALL, RENDER_COUNT = 0xF, 0x100
+
+
+def render_params(W, H, trace_limit=2, rank=0, world=1, tile_w=0, tile_h=0, flags=0):
     p = RenderParams()
     p.width, p.height, p.trace_limit, p.rank, p.world, p.tile_w, p.tile_h = W, H, trace_limit, rank, world, tile_w, tile_h
+    p.flags = flags
     return p
 
 
@@ -176,7 +187,7 @@ class Scene:
     """Device-resident scene + BVH (cgrt_scene). `flat` needs the attributes of oracle.bindings.FlatScene /
     host loader output: vcount, tcount, vertices[.,6], triangles[.,3], materials[.,8], spheres[.,12]."""
 
-    def __init__(self, flat, lights=None, device=0, bvh_max_depth=12):
+    def __init__(self, flat, lights=None, device=0, bvh_max_depth=12, host_only=False):
         self.lib = load_library()
         self.device = device
         self._keep = (np.ascontiguousarray(flat.vcount, np.int32), np.ascontiguousarray(flat.tcount, np.int32),
@@ -195,6 +206,7 @@ class Scene:
         o = SceneOptions()
         o.device = device
         o.bvh_max_depth = bvh_max_depth
+        o.flags = 1 if host_only else 0  # CGRT_SCENE_HOST_ONLY
         h = C.c_void_p()
         check(self.lib.cgrt_scene_create(C.byref(d), C.byref(o), C.byref(h)))
         self.h = h
@@ -268,9 +280,9 @@ class Scene:
         check(self.lib.cgrt_intersect_brute(self.h, _vp(rays), rays.shape[0], _vp(hits)))
         return hits
 
-    def render(self, cam, W, H, trace_limit=2, rank=0, world=1, tile=(0, 0), out=None):
+    def render(self, cam, W, H, trace_limit=2, rank=0, world=1, tile=(0, 0), out=None, flags=0):
         """Full C-ABI host path: returns (rgb[H,W,3] in Screen layout, stats dict)."""
-        p = render_params(W, H, trace_limit, rank, world, tile[0], tile[1])
+        p = render_params(W, H, trace_limit, rank, world, tile[0], tile[1], flags)
         rgb = np.zeros((H, W, 3), np.float32) if out is None else out
         st = RenderStats()
         check(self.lib.cgrt_render(self.h, C.byref(cam), C.byref(p), _vp(rgb), C.byref(st)))

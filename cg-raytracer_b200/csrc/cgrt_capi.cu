@@ -35,6 +35,9 @@ static int fail(int code, const std::string& msg)
         }                                                                                                             \
     } while (0)
 
+static int useDevice(int device);
+static int useSceneDevice(const cgrt_scene* s);
+
 static int useDevice(int device)
 {
     int n = 0;
@@ -167,6 +170,7 @@ struct cgrt_scene {
 
     BuiltBVH bvh;
     std::vector<int32_t> leafGlobalId; // leaf order -> global triangle id
+    bool hostOnly = false;             // built with CGRT_SCENE_HOST_ONLY: no device state, queries are refused
     int64_t nTris = 0;
     int nMeshes = 0;
 
@@ -187,6 +191,10 @@ struct cgrt_scene {
     DevBuf<float4> hitQ, bounceQ, pathState;
     DevBuf<uint8_t> lit;
     DevBuf<int> pathPix, counts, tileList;
+    DevBuf<unsigned long long> tests;
+    std::vector<cudaEvent_t> traceEvents;
+    WaveTrace trace{};
+    bool lastCounted = false;
     std::vector<int> tileListHost;
     int tileKey[6] = {0, 0, 0, 0, 0, 0};
     DevBuf<float> frame; // internal framebuffer for the host-pointer render
@@ -200,14 +208,28 @@ struct cgrt_scene {
     bool haveLast = false;
 };
 
+static int useSceneDevice(const cgrt_scene* s)
+{
+    if (s->hostOnly)
+        return fail(CGRT_ERR_NO_DEVICE, "scene was created with CGRT_SCENE_HOST_ONLY (BVH introspection only): "
+                                        "queries need a device-resident scene; there is no CPU path");
+    return useDevice(s->device);
+}
+
 static void destroyScene(cgrt_scene* s)
 {
     if (!s) return;
+    if (s->hostOnly) {
+        delete s;
+        return;
+    }
     cudaSetDevice(s->device);
     s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
     s->triN0.release(); s->triN1.release(); s->triN2.release(); s->mats.release(); s->spheres.release();
     s->origToLeaf.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->frame.release();
+    s->tests.release();
+    for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->hParamRing) cudaFreeHost(s->hParamRing);
     if (s->hFramePinned) cudaFreeHost(s->hFramePinned);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -256,7 +278,8 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     const int device = opt ? opt->device : 0;
     int maxDepth = (opt && opt->bvh_max_depth > 0) ? opt->bvh_max_depth : 12; // src/bounding_volume_hierarchy.cpp:48
     if (maxDepth > CGRT_MAX_BVH_DEPTH) return fail(CGRT_ERR_INVALID, "bvh_max_depth exceeds the traversal stack");
-    int rc = useDevice(device);
+    const bool hostOnly = opt && (opt->flags & CGRT_SCENE_HOST_ONLY);
+    int rc = hostOnly ? CGRT_OK : useDevice(device);
     if (rc) return rc;
 
     // ---- validate + view the meshes
@@ -285,13 +308,22 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     s->device = device;
     s->nTris = gid;
     s->nMeshes = d->n_meshes;
-    rc = deviceInfo(device, s->di);
-    if (rc) { destroyScene(s); return rc; }
+    s->hostOnly = hostOnly;
+    if (!hostOnly) {
+        rc = deviceInfo(device, s->di);
+        if (rc) { destroyScene(s); return rc; }
+    }
 
     // ---- host build with the reference split rule
     buildReferenceBVH(views, maxDepth, s->bvh);
     const size_t T = s->bvh.leafTris.size();
     const size_t NN = s->bvh.nodes.size();
+    s->leafGlobalId.resize(T);
+    for (size_t i = 0; i < T; i++) s->leafGlobalId[i] = views[s->bvh.leafTris[i].mesh].triOffset + s->bvh.leafTris[i].tri;
+    if (hostOnly) { // BVH introspection only (builder tests on machines without a GPU); every query entry refuses it
+        *out = s;
+        return CGRT_OK;
+    }
 
     // ---- flatten: 32-byte nodes + leaf-ordered SoA triangles
     std::vector<float4> hNodes(NN * 2);
@@ -389,7 +421,7 @@ int cgrt_scene_set_spheres(cgrt_scene* s, const float* spheres, int32_t n)
 {
     if (!s || n < 0 || (n > 0 && !spheres)) return fail(CGRT_ERR_INVALID, "bad spheres");
     std::lock_guard<std::mutex> lk(s->mu);
-    int rc = useDevice(s->device);
+    int rc = useSceneDevice(s);
     if (rc) return rc;
     CK(cudaDeviceSynchronize());
     return uploadSpheres(s, spheres, n);
@@ -431,7 +463,7 @@ int cgrt_intersect_closest_device(cgrt_scene* s, const cgrt_ray* d_rays, size_t 
                                   void* stream)
 {
     if (!s || (n && (!d_rays || !d_hits))) return fail(CGRT_ERR_INVALID, "null argument");
-    int rc = useDevice(s->device);
+    int rc = useSceneDevice(s);
     if (rc) return rc;
     DevScene S;
     {
@@ -447,7 +479,7 @@ int cgrt_intersect_any_device(cgrt_scene* s, const cgrt_ray* d_rays, const float
                               uint8_t* d_occluded, void* stream)
 {
     if (!s || (n && (!d_rays || !d_max_dist || !d_occluded))) return fail(CGRT_ERR_INVALID, "null argument");
-    int rc = useDevice(s->device);
+    int rc = useSceneDevice(s);
     if (rc) return rc;
     DevScene S;
     {
@@ -491,7 +523,7 @@ struct Scratch {
 int cgrt_intersect_closest(cgrt_scene* s, const cgrt_ray* rays, size_t n, cgrt_hit* hits, uint32_t* counts)
 {
     if (!s || (n && (!rays || !hits))) return fail(CGRT_ERR_INVALID, "null argument");
-    RC(useDevice(s->device));
+    RC(useSceneDevice(s));
     if (n == 0) return CGRT_OK;
     Scratch sc;
     RC(sc.stream());
@@ -510,7 +542,7 @@ int cgrt_intersect_closest(cgrt_scene* s, const cgrt_ray* rays, size_t n, cgrt_h
 int cgrt_intersect_any(cgrt_scene* s, const cgrt_ray* rays, const float* max_dist, float eps, size_t n, uint8_t* occluded)
 {
     if (!s || (n && (!rays || !max_dist || !occluded))) return fail(CGRT_ERR_INVALID, "null argument");
-    RC(useDevice(s->device));
+    RC(useSceneDevice(s));
     if (n == 0) return CGRT_OK;
     Scratch sc;
     RC(sc.stream());
@@ -529,7 +561,7 @@ int cgrt_intersect_any(cgrt_scene* s, const cgrt_ray* rays, const float* max_dis
 int cgrt_intersect_brute(cgrt_scene* s, const cgrt_ray* rays, size_t n, cgrt_hit* hits)
 {
     if (!s || (n && (!rays || !hits))) return fail(CGRT_ERR_INVALID, "null argument");
-    RC(useDevice(s->device));
+    RC(useSceneDevice(s));
     if (n == 0) return CGRT_OK;
     Scratch sc;
     RC(sc.stream());
@@ -749,6 +781,7 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
     RC(s->pathPix.ensure(cap));
     RC(s->pathState.ensure(cap * 2 * levels));
     RC(s->counts.ensure(CGRT_CNT_TOTAL));
+    RC(s->tests.ensure(6));
     // parameter block: FrameParams header + lights (2 x float4 each)
     const size_t need = CGRT_PARAM_BLOCK_HEADER + (size_t)nL * 32;
     if (need > s->paramBlockBytes || !s->hParamRing) {
@@ -768,7 +801,7 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
 {
     if (!s || !cam || !d_out) return fail(CGRT_ERR_INVALID, "null argument");
     RC(checkRenderParams(p));
-    RC(useDevice(s->device));
+    RC(useSceneDevice(s));
     std::lock_guard<std::mutex> lk(s->mu);
     cudaStream_t st = (cudaStream_t)stream;
     FrameParams P;
@@ -793,12 +826,24 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
     B.pathPix = s->pathPix.p;
     B.pathState = s->pathState.p;
     B.counts = s->counts.p;
+    B.tests = s->tests.p;
     B.cap = (size_t)std::max(P.nSlots, 1);
+    const int maxKernels = 3 * CGRT_MAX_LEVELS + 1;
+    if ((p->flags & CGRT_RENDER_PROFILE_ALL) && s->traceEvents.empty()) {
+        s->traceEvents.resize(2 * maxKernels);
+        for (cudaEvent_t& e : s->traceEvents) CK(cudaEventCreate(&e));
+    }
+    std::memset(&s->trace, 0, sizeof s->trace);
+    s->trace.ev = s->traceEvents.data();
+    s->trace.maxKernels = maxKernels;
+    s->trace.classMask = p->flags & CGRT_RENDER_PROFILE_ALL;
+    const bool countTests = (p->flags & CGRT_RENDER_COUNT) != 0;
     CK(cudaEventRecord(s->ev0, st));
     const int launches = launchWavefront(s->dev, (const FrameParams*)s->dParamBlock.p, P,
                                          (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), B, dTiles, d_out,
-                                         s->di.numSMs, st);
+                                         s->di.numSMs, countTests, &s->trace, st);
     CK(cudaEventRecord(s->ev1, st));
+    s->lastCounted = countTests;
     CK(cudaGetLastError());
     s->lastStream = st;
     s->lastLaunches = (uint64_t)launches;
@@ -810,7 +855,7 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
 int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
 {
     if (!s || !stats) return fail(CGRT_ERR_INVALID, "null argument");
-    RC(useDevice(s->device));
+    RC(useSceneDevice(s));
     std::lock_guard<std::mutex> lk(s->mu);
     std::memset(stats, 0, sizeof *stats);
     if (!s->haveLast) return fail(CGRT_ERR_INVALID, "no frame rendered yet");
@@ -843,6 +888,20 @@ int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
     float ms = 0.0f;
     CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     stats->device_ms = ms;
+    for (int c = 0; c < 4; c++) stats->class_launches[c] = (uint32_t)s->trace.launches[c];
+    for (int k = 0; k < s->trace.n; k++) {
+        float kms = 0.0f;
+        CK(cudaEventElapsedTime(&kms, s->trace.ev[2 * k], s->trace.ev[2 * k + 1]));
+        stats->class_ms[s->trace.cls[k]] += kms;
+    }
+    if (s->lastCounted) {
+        unsigned long long t[6];
+        CK(cudaMemcpy(t, s->tests.p, sizeof t, cudaMemcpyDeviceToHost));
+        for (int c = 0; c < 3; c++) {
+            stats->box_tests[c] = t[2 * c];
+            stats->tri_tests[c] = t[2 * c + 1];
+        }
+    }
     return CGRT_OK;
 }
 
@@ -850,7 +909,7 @@ int cgrt_render(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params*
 {
     if (!s || !cam || !rgb) return fail(CGRT_ERR_INVALID, "null argument");
     RC(checkRenderParams(p));
-    RC(useDevice(s->device));
+    RC(useSceneDevice(s));
     const size_t frameFloats = (size_t)p->width * p->height * 3;
     const size_t outFloats = cgrt_tile_buffer_floats(p);
     {

@@ -285,7 +285,18 @@ RT_DEV void pushHitRecord(const DevScene& S, const WaveBuffers& B, int level, bo
     rec[2] = make_float4(d.x, d.y, d.z, i2f(pathId));
 }
 
+// CGRT_RENDER_COUNT: warp-reduce the per-ray test counts, one 64-bit atomic per warp and counter
+RT_DEV void accumulateTests(unsigned long long* tests, int cls, uint32_t nBox, uint32_t nTri)
+{
+    const uint32_t sb = __reduce_add_sync(0xffffffffu, nBox), stt = __reduce_add_sync(0xffffffffu, nTri);
+    if ((threadIdx.x & 31) == 0) {
+        if (sb) atomicAdd(tests + 2 * cls, (unsigned long long)sb);
+        if (stt) atomicAdd(tests + 2 * cls + 1, (unsigned long long)stt);
+    }
+}
+
 // ---- level 0: ray generation + closest hit ------------------------------------------------------------------------------
+template <bool COUNT>
 __global__ void __launch_bounds__(128) k_primary(DevScene S, const FrameParams* __restrict__ Pp, WaveBuffers B,
                                                  const int* __restrict__ tileList, float* __restrict__ fb)
 {
@@ -298,19 +309,21 @@ __global__ void __launch_bounds__(128) k_primary(DevScene S, const FrameParams* 
         bool hit = false;
         TraceResult R;
         V3 o = mk3(P.camX, P.camY, P.camZ), d = mk3(0.0f, 0.0f, 0.0f);
+        uint32_t nb = 0, nt = 0;
         if (valid) {
             d = primaryDirection(P, x, y);
-            uint32_t nb = 0, nt = 0;
-            hit = traverseStrict<false, false>(S, o, d, FLT_MAX, 0.0f, 0.0f, R, nb, nt);
+            hit = traverseStrict<false, COUNT>(S, o, d, FLT_MAX, 0.0f, 0.0f, R, nb, nt);
             if (!hit) storeRGB(fb, outIdx, mk3(0.0f, 0.0f, 0.0f)); // trace(): miss -> black, src/main.cpp:288-294
         } else if (slot < n && P.world > 1) {
             storeRGB(fb, slot, mk3(0.0f, 0.0f, 0.0f)); // padding pixels of edge tiles in the tile-major buffer
         }
+        if (COUNT) accumulateTests(B.tests, 0, nb, nt);
         pushHitRecord(S, B, 0, hit, R, o, d, outIdx, -1);
     }
 }
 
 // ---- level >= 1: closest hit over the compacted bounce queue --------------------------------------------------------------
+template <bool COUNT>
 __global__ void __launch_bounds__(128) k_bounce_closest(DevScene S, WaveBuffers B, int level, float* __restrict__ fb)
 {
     const int n = B.counts[CGRT_CNT_BOUNCE + level];
@@ -321,41 +334,55 @@ __global__ void __launch_bounds__(128) k_bounce_closest(DevScene S, WaveBuffers 
         TraceResult R;
         V3 o = mk3(0.0f, 0.0f, 0.0f), d = o;
         int pathId = -1, outIdx = 0;
+        uint32_t nb = 0, nt = 0;
         if (valid) {
             const float4 r0 = B.bounceQ[2 * (size_t)i], r1 = B.bounceQ[2 * (size_t)i + 1];
             o = mk3(r0);
             d = mk3(r1);
             pathId = f2i(r1.w);
             outIdx = B.pathPix[pathId];
-            uint32_t nb = 0, nt = 0;
-            hit = traverseStrict<false, false>(S, o, d, r0.w, 0.0f, 0.0f, R, nb, nt);
+            hit = traverseStrict<false, COUNT>(S, o, d, r0.w, 0.0f, 0.0f, R, nb, nt);
             if (!hit) // reflected colour is black; unwind the levels above (src/main.cpp:288-294 then :263)
                 storeRGB(fb, outIdx, foldPath(B.pathState, B.cap, level, pathId, mk3(0.0f, 0.0f, 0.0f)));
         }
+        if (COUNT) accumulateTests(B.tests, 1, nb, nt);
         pushHitRecord(S, B, level, hit, R, o, d, outIdx, pathId);
     }
 }
 
 // ---- any-hit shadow rays: one thread per (hit, light).  pointInShadow, src/main.cpp:104-135 -------------------------------
+// COUNT = true runs the reference's full closest-hit query instead (that is what src/main.cpp:115 does and what the roofline
+// arithmetic charges a shadow ray with) and applies the predicate to its result: same answer, no early exit.
+template <bool COUNT>
 __global__ void __launch_bounds__(128) k_shadow(DevScene S, const FrameParams* __restrict__ Pp,
                                                 const float4* __restrict__ lights, WaveBuffers B, int level)
 {
     const int nL = Pp->nLights;
     const int n = B.counts[CGRT_CNT_HIT + level] * nL;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int h = i / nL, l = i - h * nL;
-        const float4 a = B.hitQ[3 * (size_t)h];
-        const V3 pointOn = mk3(a);
-        const V3 lightPos = mk3(__ldg(lights + 2 * l));
-        const V3 fromPosToLight = lightPos - pointOn;
-        const V3 dir = normalize3(fromPosToLight);
-        const float epsilon = 0.001f;
-        const V3 org = pointOn + epsilon * dir;
-        TraceResult R;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
         uint32_t nb = 0, nt = 0;
-        const bool shadowed =
-            traverseStrict<true, false>(S, org, dir, FLT_MAX, epsilon, length3(fromPosToLight), R, nb, nt);
-        B.lit[i] = shadowed ? 0 : 1;
+        if (i < n) {
+            const int h = i / nL, l = i - h * nL;
+            const float4 a = B.hitQ[3 * (size_t)h];
+            const V3 pointOn = mk3(a);
+            const V3 lightPos = mk3(__ldg(lights + 2 * l));
+            const V3 fromPosToLight = lightPos - pointOn;
+            const V3 dir = normalize3(fromPosToLight);
+            const float epsilon = 0.001f;
+            const V3 org = pointOn + epsilon * dir;
+            const float dist = length3(fromPosToLight);
+            TraceResult R;
+            bool shadowed;
+            if (COUNT) {
+                const bool hit = traverseStrict<false, true>(S, org, dir, FLT_MAX, 0.0f, 0.0f, R, nb, nt);
+                shadowed = hit && !(R.t + epsilon >= dist);
+            } else {
+                shadowed = traverseStrict<true, false>(S, org, dir, FLT_MAX, epsilon, dist, R, nb, nt);
+            }
+            B.lit[i] = shadowed ? 0 : 1;
+        }
+        if (COUNT) accumulateTests(B.tests, 2, nb, nt);
     }
 }
 
@@ -556,11 +583,27 @@ void launchGenerateRays(const FrameParams* dP, int nPixels, float4* rays, cudaSt
 
 // One frame of the wavefront. Every queue length lives in device memory (B.counts), so the sequence needs no host round trip:
 // the grids are sized for the worst case the host knows (nSlots) and the kernels loop over the device-side count.
+// `tr` (optional) records CUDA events around the kernels whose class is selected, for per-kernel device times.
+static inline void traceBegin(WaveTrace* tr, int cls, cudaStream_t st)
+{
+    if (tr && (tr->classMask >> cls & 1) && tr->n < tr->maxKernels) cudaEventRecord(tr->ev[2 * tr->n], st);
+}
+static inline void traceEnd(WaveTrace* tr, int cls, cudaStream_t st)
+{
+    if (tr) tr->launches[cls]++;
+    if (tr && (tr->classMask >> cls & 1) && tr->n < tr->maxKernels) {
+        cudaEventRecord(tr->ev[2 * tr->n + 1], st);
+        tr->cls[tr->n++] = cls;
+    }
+}
+
 int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
-                    const WaveBuffers& B, const int* dTileList, float* fb, int numSMs, cudaStream_t st)
+                    const WaveBuffers& B, const int* dTileList, float* fb, int numSMs, bool countTests, WaveTrace* tr,
+                    cudaStream_t st)
 {
     int launches = 0;
     cudaMemsetAsync(B.counts, 0, sizeof(int) * CGRT_CNT_TOTAL, st);
+    if (countTests) cudaMemsetAsync(B.tests, 0, sizeof(unsigned long long) * 6, st);
     if (hP.traceLimit <= 0) { // trace(0, ...) returns black for every pixel without casting a ray, src/main.cpp:267-272
         const size_t px = hP.world == 1 ? (size_t)hP.width * hP.height : (size_t)hP.nSlots;
         cudaMemsetAsync(fb, 0, px * 3 * sizeof(float), st);
@@ -568,20 +611,31 @@ int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams&
     }
     const int persistent = numSMs * 16; // 16 CTAs x 128 threads = 2048 threads/SM when registers allow
     const int gPrimary = gridFor((size_t)hP.nSlots, 128, 1 << 30);
-    k_primary<<<gPrimary, 128, 0, st>>>(S, dP, B, dTileList, fb);
+    traceBegin(tr, 0, st);
+    if (countTests) k_primary<true><<<gPrimary, 128, 0, st>>>(S, dP, B, dTileList, fb);
+    else k_primary<false><<<gPrimary, 128, 0, st>>>(S, dP, B, dTileList, fb);
+    traceEnd(tr, 0, st);
     launches++;
     const int gHit = gridFor((size_t)hP.nSlots, 128, persistent);
     const int gShadow = gridFor((size_t)hP.nSlots * (hP.nLights > 0 ? hP.nLights : 1), 128, persistent);
     for (int level = 0; level < hP.traceLimit; level++) {
         if (level > 0) {
-            k_bounce_closest<<<gHit, 128, 0, st>>>(S, B, level, fb);
+            traceBegin(tr, 1, st);
+            if (countTests) k_bounce_closest<true><<<gHit, 128, 0, st>>>(S, B, level, fb);
+            else k_bounce_closest<false><<<gHit, 128, 0, st>>>(S, B, level, fb);
+            traceEnd(tr, 1, st);
             launches++;
         }
         if (hP.nLights > 0) {
-            k_shadow<<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level);
+            traceBegin(tr, 2, st);
+            if (countTests) k_shadow<true><<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level);
+            else k_shadow<false><<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level);
+            traceEnd(tr, 2, st);
             launches++;
         }
+        traceBegin(tr, 3, st);
         k_shade<<<gHit, 128, 0, st>>>(S, dP, dLights, B, level, fb);
+        traceEnd(tr, 3, st);
         launches++;
     }
     return launches;

@@ -66,7 +66,18 @@ struct WaveBuffers {
     int* pathPix;      // [pathId] output index of the path's pixel
     float4* pathState; // [level][pathId] 2 x float4: directColor, ks of the shade() frame waiting for its reflection
     int* counts;       // CGRT_CNT_TOTAL queue lengths
+    unsigned long long* tests; // [class 0..2][box, tri] reference test counts (counting variants only)
     size_t cap;
+};
+
+// optional per-kernel event trace of one wavefront (classes: 0 primary, 1 bounce closest-hit, 2 shadow, 3 shade)
+struct WaveTrace {
+    cudaEvent_t* ev;   // 2 * maxKernels events
+    int maxKernels;
+    int classMask;
+    int n;             // traced kernels
+    int cls[3 * CGRT_MAX_LEVELS + 1];
+    int launches[4];
 };
 
 void launchSetupPlanes(const float4* v0, const float4* v1, const float4* v2, float4* pl, int n, cudaStream_t st);
@@ -83,7 +94,8 @@ void launchUnitPointInTriangle(const float* in, size_t n, uint8_t* inside, cudaS
 void launchUnitSphere(const float4* spheres, const float4* rays, size_t n, float* out, cudaStream_t st);
 void launchGenerateRays(const FrameParams* dP, int nPixels, float4* rays, cudaStream_t st);
 int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
-                    const WaveBuffers& B, const int* dTileList, float* fb, int numSMs, cudaStream_t st);
+                    const WaveBuffers& B, const int* dTileList, float* fb, int numSMs, bool countTests, WaveTrace* tr,
+                    cudaStream_t st);
 void launchAssemble(const float* gathered, size_t perRankFloats, const int* tileLists, const int* tileCounts, int maxTiles,
                     int world, int tileW, int tileH, int tilesX, int width, int height, float* frame, int numSMs,
                     cudaStream_t st);

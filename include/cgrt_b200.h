@@ -75,8 +75,12 @@ typedef struct cgrt_scene_desc {
 typedef struct cgrt_scene_options {
     int32_t device;        /* CUDA device ordinal this scene lives on */
     int32_t bvh_max_depth; /* reference literal 12 (src/bounding_volume_hierarchy.cpp:48); 0 = 12 */
-    int32_t reserved[6];
+    int32_t flags;         /* CGRT_SCENE_* */
+    int32_t reserved[5];
 } cgrt_scene_options;
+/* Build the BVH on the host and keep it for introspection only (cgrt_bvh_*): no CUDA call is made, so the host builder
+ * can be checked on machines without a GPU. Every query / render entry refuses such a scene with CGRT_ERR_NO_DEVICE. */
+#define CGRT_SCENE_HOST_ONLY 1
 
 /* PointLight, src/scene.h:42-45 */
 typedef struct cgrt_point_light {
@@ -96,13 +100,27 @@ typedef struct cgrt_render_params {
     int32_t trace_limit; /* recursion limit, reference literal 2 (src/main.cpp:267) */
     int32_t rank, world; /* interleaved screen-tile partition over the GPUs of one box; world=1 -> whole frame */
     int32_t tile_w, tile_h; /* 0 = default 8x8 */
-    int32_t reserved[5];
+    int32_t flags;          /* CGRT_RENDER_* */
+    int32_t reserved[4];
 } cgrt_render_params;
+
+/* kernel classes of the wavefront, in launch order within a level */
+enum { CGRT_K_PRIMARY = 0, CGRT_K_BOUNCE = 1, CGRT_K_SHADOW = 2, CGRT_K_SHADE = 3, CGRT_K_CLASSES = 4 };
+/* flags: bits 0..3 = record CUDA events around the kernels of that class (device time per class in the stats) */
+#define CGRT_RENDER_PROFILE(cls) (1 << (cls))
+#define CGRT_RENDER_PROFILE_ALL 0xF
+/* run the counting variants of the traversal kernels: stats.box_tests / tri_tests receive the number of ray/AABB and
+ * ray/triangle tests the REFERENCE traversal performs for the primary, bounce and shadow rays of the frame (shadow rays are
+ * charged the reference's full closest-hit work, src/main.cpp:115). Same image; slower; meant for the roofline arithmetic. */
+#define CGRT_RENDER_COUNT 0x100
 
 typedef struct cgrt_render_stats {
     uint64_t primary, primary_hit, shadow, bounce; /* logical rays, SURVEY.md §8(d) (shadow rays counted once) */
     uint64_t kernel_launches;                      /* kernels of this library launched by the call */
-    float device_ms;                               /* CUDA-event time of the wavefront on the library's stream */
+    uint64_t box_tests[3], tri_tests[3];           /* CGRT_RENDER_COUNT only: [primary, bounce, shadow] */
+    float device_ms;                               /* CUDA-event time of the whole wavefront on its stream */
+    float class_ms[4];                             /* CGRT_RENDER_PROFILE only: summed device time per kernel class */
+    uint32_t class_launches[4];                    /* kernels launched per class */
     float reserved[3];
 } cgrt_render_stats;
 
