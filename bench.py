@@ -305,6 +305,8 @@ def main():
             "config": {"workload": workload_name(d.n_triangles), "l2": "flushed between timed frames (256 MiB memset outside the event pair)",
                        "parallelism": f"tiles{world}" if world > 1 else "single", "tile": "8x8 interleaved, row skew 3",
                        "rays_per_frame": {"primary": n_primary, "shadow": n_shadow, "bounce": n_bounce},
+                       "kernel_ms_per_frame_rank0": dict(zip(capi.KERNEL_CLASS_NAMES, [round(v, 4) for v in st_prof["class_ms"]])),
+                       "kernel_launches_per_frame": dict(zip(capi.KERNEL_CLASS_NAMES, st_prof["class_launches"])),
                        "frame_roofline": {"algorithmic_bytes_per_frame": alg_bytes_frame, "bytes_per_ray": alg_bytes_frame / rays_frame,
                                           "achieved_GBps": alg_bytes_frame * args.steps / (total_ms * 1e-3) / 1e9,
                                           "frac_of_hbm_peak": alg_bytes_frame * args.steps / (total_ms * 1e-3) / 1e9 / (peak * world)}},

@@ -318,7 +318,10 @@ def test_c4_soup_properties(capi, oracle, gpu):
     again = rays.copy()
     again["t"] = h["t"]
     h2 = s.intersect(again)
-    assert (h2["tri"][hit] == -1).all() and same_bits(h2["t"], h["t"])
+    # nothing closer than the hit exists; the only re-acceptance the reference allows is its exact in-plane shortcut
+    # (dot(o,n) == D -> t = 0 even when ray.t is already 0, ray_tracing.cpp:43-47)
+    rehit = h2["tri"][hit] != -1
+    assert np.all(h["t"][hit][rehit] == 0.0) and rehit.mean() < 1e-4 and same_bits(h2["t"], h["t"])
     occ = s.intersect_any(rays, np.full(len(rays), np.inf, np.float32))
     assert np.array_equal(occ, hit)
     b = oracle.scene(flat).bvh()
