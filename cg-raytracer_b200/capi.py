@@ -187,7 +187,7 @@ class Scene:
     """Device-resident scene + BVH (cgrt_scene). `flat` needs the attributes of oracle.bindings.FlatScene /
     host loader output: vcount, tcount, vertices[.,6], triangles[.,3], materials[.,8], spheres[.,12]."""
 
-    def __init__(self, flat, lights=None, device=0, bvh_max_depth=12, host_only=False):
+    def __init__(self, flat, lights=None, device=0, bvh_max_depth=12, host_only=False, no_subtrees=False):
         self.lib = load_library()
         self.device = device
         self._keep = (np.ascontiguousarray(flat.vcount, np.int32), np.ascontiguousarray(flat.tcount, np.int32),
@@ -206,7 +206,7 @@ class Scene:
         o = SceneOptions()
         o.device = device
         o.bvh_max_depth = bvh_max_depth
-        o.flags = 1 if host_only else 0  # CGRT_SCENE_HOST_ONLY
+        o.flags = (1 if host_only else 0) | (2 if no_subtrees else 0)  # CGRT_SCENE_HOST_ONLY | CGRT_SCENE_NO_SUBTREES
         h = C.c_void_p()
         check(self.lib.cgrt_scene_create(C.byref(d), C.byref(o), C.byref(h)))
         self.h = h

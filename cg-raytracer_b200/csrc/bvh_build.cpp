@@ -12,7 +12,10 @@
 #include "bvh_build.h"
 
 #include <algorithm>
+#include <cfloat>
+#include <cmath>
 #include <cstddef>
+#include <limits>
 
 namespace cgrt {
 namespace {
@@ -204,6 +207,174 @@ void buildReferenceBVH(const std::vector<MeshView>& meshes, int maxDepth, BuiltB
         n.triCount = (int32_t)out.leafTris.size() - n.firstTri;
     }
     out.numLevels = maxLevel + 1; // numLevels() bvh.cpp:214-224
+}
+
+// =================================================================================================================
+// Culling sub-trees inside the reference leaves
+// =================================================================================================================
+// Soundness argument (what "conservative" means here). The reference accepts triangle k for a ray iff, in fp32 and in the
+// reference's evaluation order, the plane distance t passes its range checks and the point p = fl(o + d t) passes the three
+// edge tests dot(n, cross(e_i, p - v_i)) >= 0 (src/ray_tracing.cpp:23-72). Each edge function is evaluated with an absolute
+// error below ~2e-6 |e_i| |p - v_i|, so an accepted p lies inside the triangle grown by 2e-6 |p - v_i| per edge; for a
+// triangle whose smallest angle is at least 0.01 rad this keeps p within 1e-3 * diameter of the triangle, and p itself is
+// within 2^-22 * max|coordinate| of the exact ray. A sub-tree box is the union of its triangles' boxes grown by
+//      eps = 1e-3 * diameter(triangle) + 1e-6 * max|coordinate|
+// (rounded outwards), hence every point the reference can accept lies inside the box of every ancestor of its triangle and
+// the (tolerant) slab test of the traversal can never cull a triangle the reference would accept. Triangles that violate the
+// angle condition or contain non-finite coordinates get an unbounded box.
+namespace {
+
+struct TriBox {
+    float lo[3], hi[3], c[3];
+};
+
+inline float down(float x) { return std::nextafter(x, -std::numeric_limits<float>::infinity()); }
+inline float up(float x) { return std::nextafter(x, std::numeric_limits<float>::infinity()); }
+
+TriBox conservativeBox(const float* p0, const float* p1, const float* p2)
+{
+    TriBox tb;
+    bool finite = true;
+    double q[3][3];
+    for (int k = 0; k < 3; k++) {
+        q[0][k] = p0[k]; q[1][k] = p1[k]; q[2][k] = p2[k];
+        finite = finite && std::isfinite(p0[k]) && std::isfinite(p1[k]) && std::isfinite(p2[k]);
+    }
+    bool bounded = finite;
+    double diam = 0.0, maxAbs = 0.0;
+    if (finite) {
+        double e[3][3], len[3];
+        for (int i = 0; i < 3; i++) {
+            len[i] = 0.0;
+            for (int k = 0; k < 3; k++) {
+                e[i][k] = q[(i + 1) % 3][k] - q[i][k];
+                len[i] += e[i][k] * e[i][k];
+                maxAbs = std::max(maxAbs, std::fabs(q[i][k]));
+            }
+            len[i] = std::sqrt(len[i]);
+            diam = std::max(diam, len[i]);
+        }
+        // smallest angle via the largest edge: sin(angle) = 2*area / (a*b)
+        const double cx = e[0][1] * e[2][2] - e[0][2] * e[2][1], cy = e[0][2] * e[2][0] - e[0][0] * e[2][2],
+                     cz = e[0][0] * e[2][1] - e[0][1] * e[2][0];
+        const double area2 = std::sqrt(cx * cx + cy * cy + cz * cz);
+        double minSin = 1.0;
+        for (int i = 0; i < 3; i++) {
+            const double prod = len[i] * len[(i + 2) % 3]; // the two edges meeting at vertex i
+            if (!(prod > 0.0)) { minSin = 0.0; break; }
+            minSin = std::min(minSin, area2 / prod);
+        }
+        if (!(minSin >= 0.01) || !(diam < 1e30)) bounded = false; // slivers / degenerate / huge: always tested
+    }
+    for (int k = 0; k < 3; k++) {
+        if (!bounded) {
+            tb.lo[k] = -FLT_MAX;
+            tb.hi[k] = FLT_MAX;
+            tb.c[k] = finite ? (float)((q[0][k] + q[1][k] + q[2][k]) / 3.0) : 0.0f;
+            continue;
+        }
+        const double eps = 1e-3 * diam + 1e-6 * maxAbs;
+        const double lo = std::min(q[0][k], std::min(q[1][k], q[2][k])) - eps;
+        const double hi = std::max(q[0][k], std::max(q[1][k], q[2][k])) + eps;
+        tb.lo[k] = down((float)lo);
+        tb.hi[k] = up((float)hi);
+        tb.c[k] = (float)((q[0][k] + q[1][k] + q[2][k]) / 3.0);
+    }
+    return tb;
+}
+
+struct SubBuilder {
+    const std::vector<TriBox>& boxes; // per position (leaf order at entry)
+    std::vector<int32_t>& order;      // positions being permuted (values index `boxes`)
+    std::vector<SubNode>& nodes;
+    int subLeafSize;
+
+    void bounds(int begin, int end, float lo[3], float hi[3]) const
+    {
+        for (int k = 0; k < 3; k++) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
+        for (int i = begin; i < end; i++) {
+            const TriBox& b = boxes[order[i]];
+            for (int k = 0; k < 3; k++) {
+                lo[k] = std::min(lo[k], b.lo[k]);
+                hi[k] = std::max(hi[k], b.hi[k]);
+            }
+        }
+    }
+
+    // builds the node for [begin,end) into nodes[self]; children are allocated adjacently
+    void build(int self, int begin, int end, int base)
+    {
+        SubNode n;
+        bounds(begin, end, n.lo, n.hi);
+        const int count = end - begin;
+        if (count <= subLeafSize) {
+            n.a = base + begin;
+            n.b = count;
+            nodes[self] = n;
+            return;
+        }
+        float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (int i = begin; i < end; i++)
+            for (int k = 0; k < 3; k++) {
+                clo[k] = std::min(clo[k], boxes[order[i]].c[k]);
+                chi[k] = std::max(chi[k], boxes[order[i]].c[k]);
+            }
+        int axis = 0;
+        if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+        if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+        const int mid = begin + count / 2;
+        std::nth_element(order.begin() + begin, order.begin() + mid, order.begin() + end, [&](int32_t x, int32_t y) {
+            const float cx = boxes[x].c[axis], cy = boxes[y].c[axis];
+            return cx < cy || (cx == cy && x < y);
+        });
+        const int left = (int)nodes.size();
+        nodes.push_back(SubNode());
+        nodes.push_back(SubNode());
+        n.a = left;
+        n.b = 0;
+        nodes[self] = n;
+        build(left, begin, mid, base);
+        build(left + 1, mid, end, base);
+    }
+};
+
+} // namespace
+
+void buildLeafSubTrees(const std::vector<MeshView>& meshes, BuiltBVH& bvh, int minLeafForSubTree, int subLeafSize)
+{
+    const size_t T = bvh.leafTris.size();
+    bvh.leafTrisReferenceOrder = bvh.leafTris;
+    bvh.leafRank.assign(T, 0);
+    bvh.subNodes.clear();
+    bvh.subRoot.assign(bvh.nodes.size(), -1);
+    std::vector<LeafTri> permuted = bvh.leafTris;
+    for (size_t ni = 0; ni < bvh.nodes.size(); ni++) {
+        const HostNode& n = bvh.nodes[ni];
+        if (!n.isLeaf) continue;
+        const int first = n.firstTri, count = n.triCount;
+        for (int i = 0; i < count; i++) bvh.leafRank[first + i] = i;
+        if (count < minLeafForSubTree) continue;
+        std::vector<TriBox> boxes(count);
+        for (int i = 0; i < count; i++) {
+            const LeafTri lt = bvh.leafTris[first + i];
+            const MeshView& mv = meshes[lt.mesh];
+            const uint32_t* tri = mv.triangles + 3 * (size_t)lt.tri;
+            boxes[i] = conservativeBox(mv.vertices + 6 * (size_t)tri[0], mv.vertices + 6 * (size_t)tri[1],
+                                       mv.vertices + 6 * (size_t)tri[2]);
+        }
+        std::vector<int32_t> order(count);
+        for (int i = 0; i < count; i++) order[i] = i;
+        const int root = (int)bvh.subNodes.size();
+        bvh.subNodes.push_back(SubNode());
+        SubBuilder sb{boxes, order, bvh.subNodes, subLeafSize};
+        sb.build(root, 0, count, first);
+        bvh.subRoot[ni] = root;
+        for (int i = 0; i < count; i++) {
+            permuted[first + i] = bvh.leafTris[first + order[i]];
+            bvh.leafRank[first + i] = order[i];
+        }
+    }
+    bvh.leafTris.swap(permuted);
 }
 
 } // namespace cgrt

@@ -28,13 +28,32 @@ struct LeafTri {
     int32_t tri; // mesh-local triangle index
 };
 
+// Node of the culling sub-trees that refine the (large) leaves of the reference tree. Boxes are pre-expanded so that
+// culling is conservative with respect to the reference's floating-point accept test (see buildLeafSubTrees).
+struct SubNode {
+    float lo[3], hi[3];
+    int32_t a; // inner: index of the left child in BuiltBVH::subNodes (right = a + 1); leaf: first position in leafTris
+    int32_t b; // inner: 0; leaf: triangle count (> 0)
+};
+
 struct BuiltBVH {
     std::vector<HostNode> nodes;
-    std::vector<LeafTri> leafTris;
+    std::vector<LeafTri> leafTris;   // after buildLeafSubTrees: permuted inside each reference leaf (sub-tree order)
+    std::vector<int32_t> leafRank;   // per position: rank of that triangle in the reference's own leaf order
+    std::vector<LeafTri> leafTrisReferenceOrder; // the reference's visiting order (intersectLeaf), kept for introspection
+    std::vector<SubNode> subNodes;
+    std::vector<int32_t> subRoot;    // per reference node: root of its sub-tree in subNodes, -1 = scan the leaf
     int numLevels = 0;
 };
 
 // maxDepth: the reference literal is 12 (bvh.cpp:48); leaves are nodes at level maxDepth-1 or single-mesh/single-triangle nodes.
 void buildReferenceBVH(const std::vector<MeshView>& meshes, int maxDepth, BuiltBVH& out);
+
+// Refine every reference leaf with more than `minLeafForSubTree` triangles by a binary culling tree (median split of the
+// centroids along the longest axis, `subLeafSize` triangles per sub-leaf). The reference tree itself is untouched: the
+// traversal still visits reference nodes in the reference's order with the reference's exact box arithmetic; inside a
+// reference leaf the sub-tree only decides which triangles need the exact test. Triangles whose accept region cannot be
+// bounded tightly (non-finite coordinates, minimum angle below ~0.01 rad) get an unbounded box, i.e. they are always tested.
+void buildLeafSubTrees(const std::vector<MeshView>& meshes, BuiltBVH& bvh, int minLeafForSubTree = 8, int subLeafSize = 2);
 
 } // namespace cgrt

@@ -174,8 +174,8 @@ struct cgrt_scene {
     int64_t nTris = 0;
     int nMeshes = 0;
 
-    DevBuf<float4> nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres;
-    DevBuf<int> origToLeaf;
+    DevBuf<float4> nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, subNodes;
+    DevBuf<int> origToLeaf, subRoot;
     DevScene dev{};
 
     std::vector<cgrt_point_light> lights;
@@ -226,7 +226,7 @@ static void destroyScene(cgrt_scene* s)
     cudaSetDevice(s->device);
     s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
     s->triN0.release(); s->triN1.release(); s->triN2.release(); s->mats.release(); s->spheres.release();
-    s->origToLeaf.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
+    s->origToLeaf.release(); s->subNodes.release(); s->subRoot.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->frame.release();
     s->tests.release();
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
@@ -318,8 +318,16 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     buildReferenceBVH(views, maxDepth, s->bvh);
     const size_t T = s->bvh.leafTris.size();
     const size_t NN = s->bvh.nodes.size();
-    s->leafGlobalId.resize(T);
+    s->leafGlobalId.resize(T); // the reference's own leaf order (introspection); device arrays may be permuted inside leaves
     for (size_t i = 0; i < T; i++) s->leafGlobalId[i] = views[s->bvh.leafTris[i].mesh].triOffset + s->bvh.leafTris[i].tri;
+    const bool subTrees = !(opt && (opt->flags & CGRT_SCENE_NO_SUBTREES));
+    if (subTrees) buildLeafSubTrees(views, s->bvh);
+    else {
+        s->bvh.leafRank.assign(T, 0);
+        for (const HostNode& n : s->bvh.nodes)
+            if (n.isLeaf)
+                for (int i = 0; i < n.triCount; i++) s->bvh.leafRank[n.firstTri + i] = i;
+    }
     if (hostOnly) { // BVH introspection only (builder tests on machines without a GPU); every query entry refuses it
         *out = s;
         return CGRT_OK;
@@ -341,18 +349,17 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     std::vector<float4> hv[3], hn[3];
     for (int k = 0; k < 3; k++) { hv[k].resize(T); hn[k].resize(T); }
     std::vector<int> hOrigToLeaf((size_t)gid, 0);
-    s->leafGlobalId.resize(T);
     for (size_t i = 0; i < T; i++) {
         const LeafTri lt = s->bvh.leafTris[i];
         const MeshView& mv = views[lt.mesh];
         const int32_t g = mv.triOffset + lt.tri;
-        s->leafGlobalId[i] = g;
         hOrigToLeaf[g] = (int)i;
         for (int k = 0; k < 3; k++) {
             const float* vtx = mv.vertices + 6 * (size_t)mv.triangles[3 * (size_t)lt.tri + k];
             float w = 0.0f;
             if (k == 0) std::memcpy(&w, &g, 4);
             if (k == 1) std::memcpy(&w, &lt.mesh, 4);
+            if (k == 2) std::memcpy(&w, &s->bvh.leafRank[i], 4);
             hv[k][i] = make_float4(vtx[0], vtx[1], vtx[2], w);
             hn[k][i] = make_float4(vtx[3], vtx[4], vtx[5], 0.0f);
         }
@@ -378,6 +385,18 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     UP(triN0, hn[0]); UP(triN1, hn[1]); UP(triN2, hn[2]);
     UP(mats, hMats);
     UP(origToLeaf, hOrigToLeaf);
+    std::vector<float4> hSub(s->bvh.subNodes.size() * 2);
+    for (size_t i = 0; i < s->bvh.subNodes.size(); i++) {
+        const SubNode& n = s->bvh.subNodes[i];
+        float fa, fb;
+        std::memcpy(&fa, &n.a, 4);
+        std::memcpy(&fb, &n.b, 4);
+        hSub[2 * i] = make_float4(n.lo[0], n.lo[1], n.lo[2], fa);
+        hSub[2 * i + 1] = make_float4(n.hi[0], n.hi[1], n.hi[2], fb);
+    }
+    if (s->bvh.subRoot.size() != NN) s->bvh.subRoot.assign(NN, -1);
+    UP(subNodes, hSub);
+    UP(subRoot, s->bvh.subRoot);
 #undef UP
     rc = s->triPl.ensure(T);
     if (rc) { destroyScene(s); return rc; }
@@ -398,6 +417,8 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     s->dev.triN0 = s->triN0.p; s->dev.triN1 = s->triN1.p; s->dev.triN2 = s->triN2.p;
     s->dev.mats = s->mats.p;
     s->dev.origToLeaf = s->origToLeaf.p;
+    s->dev.subNodes = s->bvh.subNodes.empty() ? nullptr : s->subNodes.p;
+    s->dev.subRoot = s->subRoot.p;
     s->dev.nNodes = (int)NN;
     s->dev.nTris = (int)T;
     s->dev.nMeshes = d->n_meshes;

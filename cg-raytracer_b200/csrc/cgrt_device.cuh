@@ -1,18 +1,140 @@
-// Device-side scene layout and the strict (reference-order) BVH traversal shared by every kernel.
+// Device-side BVH traversal shared by every kernel: the reference's exact visiting order over the reference tree, with the
+// (large) reference leaves refined by conservative culling sub-trees. Results are identical to the reference's sequential
+// leaf scan by construction; see the comments on leaf evaluation below.
 #pragma once
 #include "rt_math.cuh"
 #include "cgrt_kernels.h"
-
 
 RT_DEV int f2i(float f) { return __float_as_int(f); }
 RT_DEV float i2f(int i) { return __int_as_float(i); }
 
 struct TraceResult {
     float t;      // ray.t after the query
-    int tri;      // leaf-order index of the last accepted triangle, -1 none
+    int tri;      // position (leaf-ordered arrays) of the last accepted triangle, -1 none
     int sphere;   // index of the last accepted sphere (closer than every triangle), -1 none
     V3 sphereN;   // its normal
 };
+
+// ---- leaf evaluation ----------------------------------------------------------------------------------------------------------
+// intersectLeaf (src/bounding_volume_hierarchy.cpp:535-553) scans the leaf's triangles in order and accepts a triangle iff
+// its plane distance tt is >= 0 and < the CURRENT ray.t and the hit point is inside (src/ray_tracing.cpp:40-114). The state
+// after the scan is therefore: among the triangles that are acceptable against the ray.t at leaf ENTRY, the one with the
+// smallest tt, ties broken by the earliest position in the leaf ("rank"). That characterisation does not depend on the order
+// in which the triangles are examined, which is what lets the sub-tree skip triangles that cannot be accepted.
+// One quirk: when the origin lies exactly in the triangle's plane (dot(o,n) == D) the reference takes t = 0 WITHOUT comparing
+// against ray.t (:43-47), so among such "shortcut" candidates the LAST one in leaf order wins, and it beats every other.
+struct LeafBest {
+    float t;      // best distance so far (initially ray.t at leaf entry)
+    int pos;      // position of the best triangle, -1 = none accepted in this leaf yet
+    int rank;     // its rank in the reference's leaf order
+    bool shortcut;
+};
+
+// Exact accept arithmetic for one triangle (same expression trees as planeTest + pointInTriangleDev), folded into `best`.
+// Returns true iff the triangle became the new best.
+RT_DEV bool leafCandidate(const DevScene& S, int i, const V3& o, const V3& d, LeafBest& best)
+{
+    const float4 pl = __ldg(S.triPl + i);
+    const V3 n = mk3(pl);
+    const float on = dot3(o, n);
+    float tt;
+    bool shortcut = false;
+    if (on == pl.w) {
+        tt = 0.0f;
+        shortcut = true;
+    } else {
+        const float denominator = dot3(d, n);
+        if (denominator == 0) return false;
+        tt = (pl.w - on) / denominator;
+        if (tt < 0) return false;
+        // cannot win: farther than the best, or a shortcut candidate already holds the leaf, or equal to ray.t at leaf
+        // entry (rejected by the reference's `t >= ray.t`)
+        if (!(tt <= best.t)) return false;
+        if (best.shortcut) return false;
+        if (tt == best.t && best.pos < 0) return false;
+    }
+    const float4 v0 = __ldg(S.triV0 + i), v1 = __ldg(S.triV1 + i), v2 = __ldg(S.triV2 + i);
+    const int rank = f2i(v2.w);
+    if (shortcut) {
+        if (best.shortcut && rank < best.rank) return false; // the last shortcut candidate in leaf order wins
+    } else if (tt == best.t && rank > best.rank) {
+        return false; // equally close: the reference keeps the one it reached first
+    }
+    const V3 p = o + d * tt;
+    if (!pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), n, p)) return false;
+    best.t = tt;
+    best.pos = i;
+    best.rank = rank;
+    best.shortcut = shortcut;
+    return true;
+}
+
+// Tolerant slab test against a pre-expanded sub-tree box with the per-ray reciprocal direction. Never reports a miss for a box
+// that contains a point the reference could accept at a distance <= bt (bvh_build.cpp: soundness argument).
+RT_DEV bool slabLoose(const float4& lo, const float4& hi, const V3& o, const V3& inv, float bt, float& tNear)
+{
+    const float t0x = (lo.x - o.x) * inv.x, t1x = (hi.x - o.x) * inv.x;
+    const float t0y = (lo.y - o.y) * inv.y, t1y = (hi.y - o.y) * inv.y;
+    const float t0z = (lo.z - o.z) * inv.z, t1z = (hi.z - o.z) * inv.z;
+    const float tIn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+    const float tOut = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    tNear = tIn;
+    const float slack = 1.000001f;
+    return !(tOut < 0.0f || tIn > tOut * slack || tIn > bt * slack);
+}
+
+#define CGRT_SUBSTACK 40
+
+// Evaluate one reference leaf through its culling sub-tree. Returns true iff ANY && the shadow predicate fired.
+template <bool ANY>
+RT_DEV bool leafThroughSubTree(const DevScene& S, int root, const V3& o, const V3& d, const V3& inv, float eps, float maxDist,
+                               LeafBest& best)
+{
+    int stN[CGRT_SUBSTACK];
+    float stT[CGRT_SUBSTACK];
+    int sp = 0;
+    int node = root;
+    while (true) {
+        const float4 q0 = __ldg(S.subNodes + 2 * node), q1 = __ldg(S.subNodes + 2 * node + 1);
+        const int a = f2i(q0.w), b = f2i(q1.w);
+        bool descend = false;
+        if (b != 0) {
+            for (int i = a; i < a + b; i++) {
+                if (leafCandidate(S, i, o, d, best)) {
+                    if (ANY && !(best.t + eps >= maxDist)) return true;
+                }
+            }
+        } else {
+            const float4 l0 = __ldg(S.subNodes + 2 * a), l1 = __ldg(S.subNodes + 2 * a + 1);
+            const float4 r0 = __ldg(S.subNodes + 2 * a + 2), r1 = __ldg(S.subNodes + 2 * a + 3);
+            float tL, tR;
+            const bool hL = slabLoose(l0, l1, o, inv, best.t, tL);
+            const bool hR = slabLoose(r0, r1, o, inv, best.t, tR);
+            if (hL && hR && sp < CGRT_SUBSTACK) {
+                const bool leftFirst = tL <= tR;
+                stN[sp] = leftFirst ? a + 1 : a;
+                stT[sp] = leftFirst ? tR : tL;
+                sp++;
+                node = leftFirst ? a : a + 1;
+                descend = true;
+            } else if (hL || hR) {
+                node = hL ? a : a + 1;
+                descend = true;
+            }
+        }
+        if (descend) continue;
+        bool found = false;
+        while (sp > 0) {
+            sp--;
+            if (stT[sp] > best.t * 1.000001f) continue;
+            node = stN[sp];
+            found = true;
+            break;
+        }
+        if (!found) break;
+    }
+    return false;
+}
 
 // Closest-hit traversal in the reference's exact visiting order:
 //   intersect            src/bounding_volume_hierarchy.cpp:850-881
@@ -20,11 +142,12 @@ struct TraceResult {
 //   intersectNonLeaf     :715-736     slab-test BOTH children against the current ray.t (tLeft/tRight, -1 = miss)
 //   intersectDeeper      :679-701     classify by startsInBox
 //   intersectChildrenHierarchically :572-595, intersectRayThatStartsOutsideBoxes :611-635 (with the intended `return`s)
-//   intersectLeaf        :535-553
+//   intersectLeaf        :535-553     (through leafCandidate, see above)
 // The recursion is unrolled onto an explicit stack of (node, tSecond): the pending sibling is skipped at pop time iff
 // ray.t < tSecond, which equals the reference's `hitFirst && ray.t < tSecond` because tSecond < ray.t held when it was pushed.
 // ANY = true adds an early exit as soon as an accepted hit satisfies the shadow predicate !(t + eps >= maxDist)
 // (pointInShadow, src/main.cpp:104-135); later accepted hits can only be closer, so the answer equals the closest-hit one.
+// COUNT = true scans every leaf sequentially (no sub-tree) and counts the reference's box / triangle tests.
 template <bool ANY, bool COUNT>
 RT_DEV bool traverseStrict(const DevScene& S, const V3& o, const V3& d, float tIn, float eps, float maxDist, TraceResult& R,
                            uint32_t& nBox, uint32_t& nTri)
@@ -41,40 +164,65 @@ RT_DEV bool traverseStrict(const DevScene& S, const V3& o, const V3& d, float tI
             enter = slabTest(mk3(q0), mk3(q1), o, d, t, tmp);
         }
         if (enter) {
+            // per-ray data of the tolerant sub-tree slab test; rays with extreme direction components scan leaves instead
+            V3 inv = mk3(0.0f, 0.0f, 0.0f);
+            bool useSub = !COUNT && S.subNodes != nullptr;
+            if (useSub) {
+                const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+                const bool okx = (ax == 0.0f) || (ax >= 1e-20f && ax <= 1e20f);
+                const bool oky = (ay == 0.0f) || (ay >= 1e-20f && ay <= 1e20f);
+                const bool okz = (az == 0.0f) || (az >= 1e-20f && az <= 1e20f);
+                const bool fin = fabsf(o.x) <= 1e30f && fabsf(o.y) <= 1e30f && fabsf(o.z) <= 1e30f; // false for NaN
+                useSub = okx && oky && okz && fin;
+                inv.x = ax == 0.0f ? 1e30f : 1.0f / d.x;
+                inv.y = ay == 0.0f ? 1e30f : 1.0f / d.y;
+                inv.z = az == 0.0f ? 1e30f : 1.0f / d.z;
+            }
             int stN[CGRT_STACK];
             float stT[CGRT_STACK];
             int sp = 0;
+            int cur = 0;
             uint32_t a = (uint32_t)f2i(q0.w), b = (uint32_t)f2i(q1.w);
             while (true) {
                 if (b != 0u) {
-                    // ---- intersectLeaf: every triangle in leaf order, accept iff plane hit closer than ray.t and inside
-                    const uint32_t end = a + b;
-                    for (uint32_t i = a; i < end; i++) {
-                        if (COUNT) nTri++;
-                        const float4 pl = __ldg(S.triPl + i);
-                        float tt;
-                        if (planeTest(mk3(pl), pl.w, o, d, t, tt)) {
-                            const float4 v0 = __ldg(S.triV0 + i), v1 = __ldg(S.triV1 + i), v2 = __ldg(S.triV2 + i);
-                            const V3 p = o + d * tt;
-                            if (pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), mk3(pl), p)) {
-                                t = tt;
-                                hitTri = (int)i;
-                                if (ANY && !(tt + eps >= maxDist)) {
-                                    R.t = t;
-                                    R.tri = hitTri;
+                    // ---- intersectLeaf
+                    LeafBest best;
+                    best.t = t;
+                    best.pos = -1;
+                    best.rank = -1;
+                    best.shortcut = false;
+                    const int sr = useSub ? __ldg(S.subRoot + cur) : -1;
+                    if (COUNT) nTri += b;
+                    if (sr >= 0) {
+                        if (leafThroughSubTree<ANY>(S, sr, o, d, inv, eps, maxDist, best)) {
+                            R.t = best.t;
+                            R.tri = best.pos;
+                            return true;
+                        }
+                    } else {
+                        const uint32_t end = a + b;
+                        for (uint32_t i = a; i < end; i++) {
+                            if (leafCandidate(S, (int)i, o, d, best)) {
+                                if (ANY && !(best.t + eps >= maxDist)) {
+                                    R.t = best.t;
+                                    R.tri = best.pos;
                                     return true;
                                 }
                             }
                         }
+                    }
+                    if (best.pos >= 0) {
+                        t = best.t;
+                        hitTri = best.pos;
                     }
                     // ---- return to the nearest pending sibling that is not pruned
                     bool found = false;
                     while (sp > 0) {
                         sp--;
                         if (t < stT[sp]) continue;
-                        const int n = stN[sp];
-                        q0 = __ldg(S.nodes + 2 * n);
-                        q1 = __ldg(S.nodes + 2 * n + 1);
+                        cur = stN[sp];
+                        q0 = __ldg(S.nodes + 2 * cur);
+                        q1 = __ldg(S.nodes + 2 * cur + 1);
                         a = (uint32_t)f2i(q0.w);
                         b = (uint32_t)f2i(q1.w);
                         found = true;
@@ -120,6 +268,7 @@ RT_DEV bool traverseStrict(const DevScene& S, const V3& o, const V3& d, float tI
                         sp++;
                     }
                     if (first >= 0) {
+                        cur = first;
                         if (first == L) { a = (uint32_t)f2i(l0.w); b = (uint32_t)f2i(l1.w); }
                         else { a = (uint32_t)f2i(r0.w); b = (uint32_t)f2i(r1.w); }
                     } else {
@@ -127,9 +276,9 @@ RT_DEV bool traverseStrict(const DevScene& S, const V3& o, const V3& d, float tI
                         while (sp > 0) {
                             sp--;
                             if (t < stT[sp]) continue;
-                            const int n = stN[sp];
-                            q0 = __ldg(S.nodes + 2 * n);
-                            q1 = __ldg(S.nodes + 2 * n + 1);
+                            cur = stN[sp];
+                            q0 = __ldg(S.nodes + 2 * cur);
+                            q1 = __ldg(S.nodes + 2 * cur + 1);
                             a = (uint32_t)f2i(q0.w);
                             b = (uint32_t)f2i(q1.w);
                             found = true;

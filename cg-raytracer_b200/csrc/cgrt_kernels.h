@@ -11,7 +11,11 @@
 //               leaf      : a = first triangle (leaf order), b = triangle count (> 0)
 // triPl     : float4 per triangle (leaf order): plane normal.xyz, D     (trianglePlane, src/ray_tracing.cpp:74-82, precomputed
 //             on the device with the same expression tree -> same bits as the reference's per-test recomputation)
-// triV0/1/2 : float4 per triangle: position.xyz ; triV0.w = global triangle id (bit-cast), triV1.w = mesh/material id
+// triV0/1/2 : float4 per triangle: position.xyz ; triV0.w = global triangle id (bit-cast), triV1.w = mesh/material id,
+//             triV2.w = rank of the triangle in the reference's own leaf order (tie-break, see cgrt_device.cuh)
+//             Inside a reference leaf the triangles are stored in sub-tree order (bvh_build.cpp buildLeafSubTrees).
+// subNodes  : 2 x float4 per node of the culling sub-trees that refine the reference leaves (same packing as `nodes`,
+//             boxes pre-expanded); subRoot[node] = root of the sub-tree of reference leaf `node`, -1 = scan the leaf
 // triN0/1/2 : float4 per triangle: vertex normal.xyz (read only for the final hit)
 // mats      : 2 x float4 per mesh:  [kd.xyz | shininess] [ks.xyz | transparency]        (src/mesh.h:17-23)
 // spheres   : 3 x float4 per sphere: [center | radius] [kd | shininess] [ks | transparency]  (src/scene.h:36-40)
@@ -26,6 +30,8 @@ struct DevScene {
     const float4* triN2;
     const float4* mats;
     const float4* spheres;
+    const float4* subNodes;
+    const int* subRoot;
     const int* origToLeaf; // global triangle id -> leaf-order index (brute-force path only)
     int nNodes;
     int nTris;

@@ -81,6 +81,9 @@ typedef struct cgrt_scene_options {
 /* Build the BVH on the host and keep it for introspection only (cgrt_bvh_*): no CUDA call is made, so the host builder
  * can be checked on machines without a GPU. Every query / render entry refuses such a scene with CGRT_ERR_NO_DEVICE. */
 #define CGRT_SCENE_HOST_ONLY 1
+/* Do not refine the reference leaves with culling sub-trees: every visited leaf is scanned triangle by triangle exactly as
+ * intersectLeaf does (A/B switch for tests and profiling; results are identical either way). */
+#define CGRT_SCENE_NO_SUBTREES 2
 
 /* PointLight, src/scene.h:42-45 */
 typedef struct cgrt_point_light {
