@@ -84,56 +84,200 @@ RT_DEV bool slabLoose(const float4& lo, const float4& hi, const V3& o, const V3&
 }
 
 #define CGRT_SUBSTACK 40
+#define CGRT_SUBFLAG 0x40000000 // stack / current-node ids with this bit set refer to S.subNodes
 
-// Evaluate one reference leaf through its culling sub-tree. Returns true iff ANY && the shadow predicate fired.
+// ---- the production traversal: one node per loop iteration, reference nodes and sub-tree nodes on ONE stack -----------------
+// Same visiting order, pruning and accept arithmetic as traverseStrict below (which documents the mapping to the reference's
+// functions); the difference is purely structural. Every iteration of the single loop handles exactly one node - a reference
+// inner node (exact ordered logic), a reference leaf without sub-tree (sequential scan), a sub-tree inner node (tolerant
+// slab tests) or a sub-tree leaf (exact triangle tests) - so that the lanes of a warp advance in lock-step instead of
+// waiting for each other's nested loops. Stack entries carry a key: for a reference sibling the entry distance tSecond
+// (skipped iff ray.t < tSecond, intersectChildrenHierarchically), for a sub-tree node its tolerant entry distance (skipped
+// iff it lies beyond the leaf's best distance). A reference leaf's result is committed when its sub-tree entries are gone.
 template <bool ANY>
-RT_DEV bool leafThroughSubTree(const DevScene& S, int root, const V3& o, const V3& d, const V3& inv, float eps, float maxDist,
-                               LeafBest& best)
+RT_DEV bool traverseFast(const DevScene& S, const V3& o, const V3& d, float tIn, float eps, float maxDist, TraceResult& R)
 {
-    int stN[CGRT_SUBSTACK];
-    float stT[CGRT_SUBSTACK];
-    int sp = 0;
-    int node = root;
-    while (true) {
-        const float4 q0 = __ldg(S.subNodes + 2 * node), q1 = __ldg(S.subNodes + 2 * node + 1);
-        const int a = f2i(q0.w), b = f2i(q1.w);
-        bool descend = false;
-        if (b != 0) {
-            for (int i = a; i < a + b; i++) {
-                if (leafCandidate(S, i, o, d, best)) {
-                    if (ANY && !(best.t + eps >= maxDist)) return true;
+    float t = tIn;
+    int hitTri = -1;
+    R.sphere = -1;
+    if (S.nNodes > 0) {
+        const float4 rq0 = __ldg(S.nodes + 0), rq1 = __ldg(S.nodes + 1);
+        bool enter = startsInBox(o, mk3(rq0), mk3(rq1));
+        if (!enter) {
+            float tmp;
+            enter = slabTest(mk3(rq0), mk3(rq1), o, d, t, tmp);
+        }
+        if (enter) {
+            // per-ray data of the tolerant sub-tree slab test; rays with extreme direction components scan leaves instead
+            const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+            const bool okx = (ax == 0.0f) || (ax >= 1e-20f && ax <= 1e20f);
+            const bool oky = (ay == 0.0f) || (ay >= 1e-20f && ay <= 1e20f);
+            const bool okz = (az == 0.0f) || (az >= 1e-20f && az <= 1e20f);
+            const bool fin = fabsf(o.x) <= 1e30f && fabsf(o.y) <= 1e30f && fabsf(o.z) <= 1e30f; // false for NaN
+            const bool useSub = S.subNodes != nullptr && okx && oky && okz && fin;
+            V3 inv;
+            inv.x = ax == 0.0f ? 1e30f : 1.0f / d.x;
+            inv.y = ay == 0.0f ? 1e30f : 1.0f / d.y;
+            inv.z = az == 0.0f ? 1e30f : 1.0f / d.z;
+
+            int stN[CGRT_STACK + CGRT_SUBSTACK];
+            float stT[CGRT_STACK + CGRT_SUBSTACK];
+            int sp = 0;
+            int node = 0;
+            bool inLeaf = false;
+            int subBase = 0;
+            LeafBest best;
+            best.t = t; best.pos = -1; best.rank = -1; best.shortcut = false;
+            const float slack = 1.000001f;
+            bool done = false;
+            while (!done) {
+                bool needPop = false;
+                if (!(node & CGRT_SUBFLAG)) {
+                    const float4 q0 = __ldg(S.nodes + 2 * node), q1 = __ldg(S.nodes + 2 * node + 1);
+                    const uint32_t a = (uint32_t)f2i(q0.w), b = (uint32_t)f2i(q1.w);
+                    if (b != 0u) {
+                        // ---- reference leaf
+                        best.t = t; best.pos = -1; best.rank = -1; best.shortcut = false;
+                        const int sr = useSub ? __ldg(S.subRoot + node) : -1;
+                        if (sr >= 0) {
+                            inLeaf = true;
+                            subBase = sp;
+                            node = sr | CGRT_SUBFLAG;
+                        } else {
+                            const uint32_t end = a + b;
+                            for (uint32_t i = a; i < end; i++) {
+                                if (leafCandidate(S, (int)i, o, d, best)) {
+                                    if (ANY && !(best.t + eps >= maxDist)) {
+                                        R.t = best.t;
+                                        R.tri = best.pos;
+                                        return true;
+                                    }
+                                }
+                            }
+                            if (best.pos >= 0) { t = best.t; hitTri = best.pos; }
+                            needPop = true;
+                        }
+                    } else {
+                        // ---- reference inner node: intersectNonLeaf + intersectDeeper, exact arithmetic
+                        const int L = (int)a, Rn = (int)a + 1;
+                        const float4 l0 = __ldg(S.nodes + 2 * L), l1 = __ldg(S.nodes + 2 * L + 1);
+                        const float4 r0 = __ldg(S.nodes + 2 * L + 2), r1 = __ldg(S.nodes + 2 * L + 3);
+                        float tL = -1.0f, tR = -1.0f, tmp;
+                        if (slabTest(mk3(l0), mk3(l1), o, d, t, tmp)) tL = tmp;
+                        if (slabTest(mk3(r0), mk3(r1), o, d, t, tmp)) tR = tmp;
+                        const bool inL = startsInBox(o, mk3(l0), mk3(l1));
+                        const bool inR = startsInBox(o, mk3(r0), mk3(r1));
+                        int first = -1, second = -1;
+                        float tS = -1.0f;
+                        if (inL && inR) {
+                            first = L; second = Rn; tS = -1.0f;
+                        } else if (inL) {
+                            first = L;
+                            if (!(tR < 0)) { second = Rn; tS = tR; }
+                        } else if (inR) {
+                            first = Rn;
+                            if (!(tL < 0)) { second = L; tS = tL; }
+                        } else {
+                            if (tL < 0 && tR < 0) {
+                            } else if (tL < 0) {
+                                first = Rn;
+                            } else if (tR < 0) {
+                                first = L;
+                            } else if (tL < tR) {
+                                first = L; second = Rn; tS = tR;
+                            } else {
+                                first = Rn; second = L; tS = tL;
+                            }
+                        }
+                        if (second >= 0) {
+                            stN[sp] = second;
+                            stT[sp] = tS;
+                            sp++;
+                        }
+                        if (first >= 0) node = first;
+                        else needPop = true;
+                    }
+                } else {
+                    const int sn = node & ~CGRT_SUBFLAG;
+                    const float4 q0 = __ldg(S.subNodes + 2 * sn), q1 = __ldg(S.subNodes + 2 * sn + 1);
+                    const int a = f2i(q0.w), b = f2i(q1.w);
+                    if (b != 0) {
+                        // ---- sub-tree leaf: exact tests of the few triangles that survived the culling
+                        for (int i = a; i < a + b; i++) {
+                            if (leafCandidate(S, i, o, d, best)) {
+                                if (ANY && !(best.t + eps >= maxDist)) {
+                                    R.t = best.t;
+                                    R.tri = best.pos;
+                                    return true;
+                                }
+                            }
+                        }
+                        needPop = true;
+                    } else {
+                        // ---- sub-tree inner node: tolerant slab tests, nearer child first
+                        const float4 l0 = __ldg(S.subNodes + 2 * a), l1 = __ldg(S.subNodes + 2 * a + 1);
+                        const float4 r0 = __ldg(S.subNodes + 2 * a + 2), r1 = __ldg(S.subNodes + 2 * a + 3);
+                        float tL, tR;
+                        const bool hL = slabLoose(l0, l1, o, inv, best.t, tL);
+                        const bool hR = slabLoose(r0, r1, o, inv, best.t, tR);
+                        if (hL && hR) {
+                            const bool leftFirst = tL <= tR;
+                            stN[sp] = (leftFirst ? a + 1 : a) | CGRT_SUBFLAG;
+                            stT[sp] = leftFirst ? tR : tL;
+                            sp++;
+                            node = (leftFirst ? a : a + 1) | CGRT_SUBFLAG;
+                        } else if (hL || hR) {
+                            node = (hL ? a : a + 1) | CGRT_SUBFLAG;
+                        } else {
+                            needPop = true;
+                        }
+                    }
+                }
+                if (needPop) {
+                    while (true) {
+                        if (inLeaf && sp == subBase) { // the reference leaf's sub-tree is exhausted: commit its result
+                            if (best.pos >= 0) { t = best.t; hitTri = best.pos; }
+                            inLeaf = false;
+                        }
+                        if (sp == 0) {
+                            done = true;
+                            break;
+                        }
+                        sp--;
+                        const int n = stN[sp];
+                        const float key = stT[sp];
+                        if (n & CGRT_SUBFLAG) {
+                            if (key > best.t * slack) continue;
+                        } else {
+                            if (t < key) continue;
+                        }
+                        node = n;
+                        break;
+                    }
                 }
             }
-        } else {
-            const float4 l0 = __ldg(S.subNodes + 2 * a), l1 = __ldg(S.subNodes + 2 * a + 1);
-            const float4 r0 = __ldg(S.subNodes + 2 * a + 2), r1 = __ldg(S.subNodes + 2 * a + 3);
-            float tL, tR;
-            const bool hL = slabLoose(l0, l1, o, inv, best.t, tL);
-            const bool hR = slabLoose(r0, r1, o, inv, best.t, tR);
-            if (hL && hR && sp < CGRT_SUBSTACK) {
-                const bool leftFirst = tL <= tR;
-                stN[sp] = leftFirst ? a + 1 : a;
-                stT[sp] = leftFirst ? tR : tL;
-                sp++;
-                node = leftFirst ? a : a + 1;
-                descend = true;
-            } else if (hL || hR) {
-                node = hL ? a : a + 1;
-                descend = true;
+        }
+    }
+    // ---- sphere loop, src/bounding_volume_hierarchy.cpp:878-879
+    for (int s = 0; s < S.nSpheres; s++) {
+        const float4 c = __ldg(S.spheres + 3 * s);
+        float ts;
+        V3 nn;
+        if (sphereTest(mk3(c), c.w, o, d, t, ts, nn)) {
+            t = ts;
+            R.sphere = s;
+            R.sphereN = nn;
+            if (ANY && !(ts + eps >= maxDist)) {
+                R.t = t;
+                R.tri = hitTri;
+                return true;
             }
         }
-        if (descend) continue;
-        bool found = false;
-        while (sp > 0) {
-            sp--;
-            if (stT[sp] > best.t * 1.000001f) continue;
-            node = stN[sp];
-            found = true;
-            break;
-        }
-        if (!found) break;
     }
-    return false;
+    R.t = t;
+    R.tri = hitTri;
+    if (ANY) return false;
+    return hitTri >= 0 || R.sphere >= 0;
 }
 
 // Closest-hit traversal in the reference's exact visiting order:
@@ -147,7 +291,8 @@ RT_DEV bool leafThroughSubTree(const DevScene& S, int root, const V3& o, const V
 // ray.t < tSecond, which equals the reference's `hitFirst && ray.t < tSecond` because tSecond < ray.t held when it was pushed.
 // ANY = true adds an early exit as soon as an accepted hit satisfies the shadow predicate !(t + eps >= maxDist)
 // (pointInShadow, src/main.cpp:104-135); later accepted hits can only be closer, so the answer equals the closest-hit one.
-// COUNT = true scans every leaf sequentially (no sub-tree) and counts the reference's box / triangle tests.
+// This variant scans every leaf sequentially (no sub-tree) and, with COUNT = true, counts the reference's box / triangle tests;
+// the kernels use it for the counting passes, traverseFast above for production.
 template <bool ANY, bool COUNT>
 RT_DEV bool traverseStrict(const DevScene& S, const V3& o, const V3& d, float tIn, float eps, float maxDist, TraceResult& R,
                            uint32_t& nBox, uint32_t& nTri)
@@ -164,20 +309,6 @@ RT_DEV bool traverseStrict(const DevScene& S, const V3& o, const V3& d, float tI
             enter = slabTest(mk3(q0), mk3(q1), o, d, t, tmp);
         }
         if (enter) {
-            // per-ray data of the tolerant sub-tree slab test; rays with extreme direction components scan leaves instead
-            V3 inv = mk3(0.0f, 0.0f, 0.0f);
-            bool useSub = !COUNT && S.subNodes != nullptr;
-            if (useSub) {
-                const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-                const bool okx = (ax == 0.0f) || (ax >= 1e-20f && ax <= 1e20f);
-                const bool oky = (ay == 0.0f) || (ay >= 1e-20f && ay <= 1e20f);
-                const bool okz = (az == 0.0f) || (az >= 1e-20f && az <= 1e20f);
-                const bool fin = fabsf(o.x) <= 1e30f && fabsf(o.y) <= 1e30f && fabsf(o.z) <= 1e30f; // false for NaN
-                useSub = okx && oky && okz && fin;
-                inv.x = ax == 0.0f ? 1e30f : 1.0f / d.x;
-                inv.y = ay == 0.0f ? 1e30f : 1.0f / d.y;
-                inv.z = az == 0.0f ? 1e30f : 1.0f / d.z;
-            }
             int stN[CGRT_STACK];
             float stT[CGRT_STACK];
             int sp = 0;
@@ -191,15 +322,8 @@ RT_DEV bool traverseStrict(const DevScene& S, const V3& o, const V3& d, float tI
                     best.pos = -1;
                     best.rank = -1;
                     best.shortcut = false;
-                    const int sr = useSub ? __ldg(S.subRoot + cur) : -1;
                     if (COUNT) nTri += b;
-                    if (sr >= 0) {
-                        if (leafThroughSubTree<ANY>(S, sr, o, d, inv, eps, maxDist, best)) {
-                            R.t = best.t;
-                            R.tri = best.pos;
-                            return true;
-                        }
-                    } else {
+                    {
                         const uint32_t end = a + b;
                         for (uint32_t i = a; i < end; i++) {
                             if (leafCandidate(S, (int)i, o, d, best)) {

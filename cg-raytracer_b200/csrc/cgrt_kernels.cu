@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(128) k_closest_batch(DevScene S, const float4*
         const V3 o = mk3(r0), d = mk3(r1);
         TraceResult R;
         uint32_t nBox = 0, nTri = 0;
-        const bool hit = traverseStrict<false, COUNT>(S, o, d, r0.w, 0.0f, 0.0f, R, nBox, nTri);
+        const bool hit = COUNT ? traverseStrict<false, true>(S, o, d, r0.w, 0.0f, 0.0f, R, nBox, nTri)
+                               : traverseFast<false>(S, o, d, r0.w, 0.0f, 0.0f, R);
         writeHit(S, o, d, r0.w, hit, R, hits + 2 * i);
         if (COUNT) {
             counts[2 * i] = nBox;
@@ -73,8 +74,7 @@ __global__ void __launch_bounds__(128) k_any_batch(DevScene S, const float4* __r
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float4 r0 = __ldg(rays + 2 * i), r1 = __ldg(rays + 2 * i + 1);
         TraceResult R;
-        uint32_t nBox = 0, nTri = 0;
-        const bool sh = traverseStrict<true, false>(S, mk3(r0), mk3(r1), r0.w, eps, __ldg(maxDist + i), R, nBox, nTri);
+        const bool sh = traverseFast<true>(S, mk3(r0), mk3(r1), r0.w, eps, __ldg(maxDist + i), R);
         occluded[i] = sh ? 1 : 0;
     }
 }
@@ -312,7 +312,8 @@ __global__ void __launch_bounds__(128) k_primary(DevScene S, const FrameParams* 
         uint32_t nb = 0, nt = 0;
         if (valid) {
             d = primaryDirection(P, x, y);
-            hit = traverseStrict<false, COUNT>(S, o, d, FLT_MAX, 0.0f, 0.0f, R, nb, nt);
+            hit = COUNT ? traverseStrict<false, true>(S, o, d, FLT_MAX, 0.0f, 0.0f, R, nb, nt)
+                        : traverseFast<false>(S, o, d, FLT_MAX, 0.0f, 0.0f, R);
             if (!hit) storeRGB(fb, outIdx, mk3(0.0f, 0.0f, 0.0f)); // trace(): miss -> black, src/main.cpp:288-294
         } else if (slot < n && P.world > 1) {
             storeRGB(fb, slot, mk3(0.0f, 0.0f, 0.0f)); // padding pixels of edge tiles in the tile-major buffer
@@ -341,7 +342,8 @@ __global__ void __launch_bounds__(128) k_bounce_closest(DevScene S, WaveBuffers 
             d = mk3(r1);
             pathId = f2i(r1.w);
             outIdx = B.pathPix[pathId];
-            hit = traverseStrict<false, COUNT>(S, o, d, r0.w, 0.0f, 0.0f, R, nb, nt);
+            hit = COUNT ? traverseStrict<false, true>(S, o, d, r0.w, 0.0f, 0.0f, R, nb, nt)
+                        : traverseFast<false>(S, o, d, r0.w, 0.0f, 0.0f, R);
             if (!hit) // reflected colour is black; unwind the levels above (src/main.cpp:288-294 then :263)
                 storeRGB(fb, outIdx, foldPath(B.pathState, B.cap, level, pathId, mk3(0.0f, 0.0f, 0.0f)));
         }
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(128) k_shadow(DevScene S, const FrameParams* _
                 const bool hit = traverseStrict<false, true>(S, org, dir, FLT_MAX, 0.0f, 0.0f, R, nb, nt);
                 shadowed = hit && !(R.t + epsilon >= dist);
             } else {
-                shadowed = traverseStrict<true, false>(S, org, dir, FLT_MAX, epsilon, dist, R, nb, nt);
+                shadowed = traverseFast<true>(S, org, dir, FLT_MAX, epsilon, dist, R);
             }
             B.lit[i] = shadowed ? 0 : 1;
         }
