@@ -86,198 +86,271 @@ RT_DEV bool slabLoose(const float4& lo, const float4& hi, const V3& o, const V3&
 #define CGRT_SUBSTACK 40
 #define CGRT_SUBFLAG 0x40000000 // stack / current-node ids with this bit set refer to S.subNodes
 
-// ---- the production traversal: one node per loop iteration, reference nodes and sub-tree nodes on ONE stack -----------------
+// ---- the production traversal: one node per step, reference nodes and sub-tree nodes on ONE stack, resumable --------------
 // Same visiting order, pruning and accept arithmetic as traverseStrict below (which documents the mapping to the reference's
-// functions); the difference is purely structural. Every iteration of the single loop handles exactly one node - a reference
-// inner node (exact ordered logic), a reference leaf without sub-tree (sequential scan), a sub-tree inner node (tolerant
-// slab tests) or a sub-tree leaf (exact triangle tests) - so that the lanes of a warp advance in lock-step instead of
-// waiting for each other's nested loops. Stack entries carry a key: for a reference sibling the entry distance tSecond
-// (skipped iff ray.t < tSecond, intersectChildrenHierarchically), for a sub-tree node its tolerant entry distance (skipped
-// iff it lies beyond the leaf's best distance). A reference leaf's result is committed when its sub-tree entries are gone.
-template <bool ANY>
-RT_DEV bool traverseFast(const DevScene& S, const V3& o, const V3& d, float tIn, float eps, float maxDist, TraceResult& R)
-{
-    float t = tIn;
-    int hitTri = -1;
-    R.sphere = -1;
-    if (S.nNodes > 0) {
-        const float4 rq0 = __ldg(S.nodes + 0), rq1 = __ldg(S.nodes + 1);
-        bool enter = startsInBox(o, mk3(rq0), mk3(rq1));
-        if (!enter) {
-            float tmp;
-            enter = slabTest(mk3(rq0), mk3(rq1), o, d, t, tmp);
-        }
-        if (enter) {
-            // per-ray data of the tolerant sub-tree slab test; rays with extreme direction components scan leaves instead
-            const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-            const bool okx = (ax == 0.0f) || (ax >= 1e-20f && ax <= 1e20f);
-            const bool oky = (ay == 0.0f) || (ay >= 1e-20f && ay <= 1e20f);
-            const bool okz = (az == 0.0f) || (az >= 1e-20f && az <= 1e20f);
-            const bool fin = fabsf(o.x) <= 1e30f && fabsf(o.y) <= 1e30f && fabsf(o.z) <= 1e30f; // false for NaN
-            const bool useSub = S.subNodes != nullptr && okx && oky && okz && fin;
-            V3 inv;
-            inv.x = ax == 0.0f ? 1e30f : 1.0f / d.x;
-            inv.y = ay == 0.0f ? 1e30f : 1.0f / d.y;
-            inv.z = az == 0.0f ? 1e30f : 1.0f / d.z;
+// functions); the difference is purely structural. Every step handles exactly one node - a reference inner node (exact
+// ordered logic), a reference leaf without sub-tree (sequential scan), a sub-tree inner node (tolerant slab tests) or a
+// sub-tree leaf (exact triangle tests) - so that the lanes of a warp advance in lock-step instead of waiting for each other's
+// nested loops, and so that a lane whose ray is finished can be handed a new ray between steps (persistent warps,
+// cgrt_kernels.cu). Stack entries carry a key: for a reference sibling the entry distance tSecond (skipped iff
+// ray.t < tSecond, intersectChildrenHierarchically), for a sub-tree node its tolerant entry distance (skipped iff it lies
+// beyond the leaf's best distance). A reference leaf's result is committed when its sub-tree entries are gone.
+struct Trav {
+    V3 o, d, inv;
+    float t;
+    int hitTri;
+    int sp, node, subBase;
+    bool useSub, inLeaf;
+    LeafBest best;
+};
+// the traversal stack lives outside the struct so that the scalars above stay in registers
+struct TravStack {
+    int n[CGRT_STACK + CGRT_SUBSTACK];
+    float t[CGRT_STACK + CGRT_SUBSTACK];
+};
 
-            int stN[CGRT_STACK + CGRT_SUBSTACK];
-            float stT[CGRT_STACK + CGRT_SUBSTACK];
-            int sp = 0;
-            int node = 0;
-            bool inLeaf = false;
-            int subBase = 0;
-            LeafBest best;
-            best.t = t; best.pos = -1; best.rank = -1; best.shortcut = false;
-            const float slack = 1.000001f;
-            bool done = false;
-            while (!done) {
-                bool needPop = false;
-                if (!(node & CGRT_SUBFLAG)) {
-                    const float4 q0 = __ldg(S.nodes + 2 * node), q1 = __ldg(S.nodes + 2 * node + 1);
-                    const uint32_t a = (uint32_t)f2i(q0.w), b = (uint32_t)f2i(q1.w);
-                    if (b != 0u) {
-                        // ---- reference leaf
-                        best.t = t; best.pos = -1; best.rank = -1; best.shortcut = false;
-                        const int sr = useSub ? __ldg(S.subRoot + node) : -1;
-                        if (sr >= 0) {
-                            inLeaf = true;
-                            subBase = sp;
-                            node = sr | CGRT_SUBFLAG;
-                        } else {
-                            const uint32_t end = a + b;
-                            for (uint32_t i = a; i < end; i++) {
-                                if (leafCandidate(S, (int)i, o, d, best)) {
-                                    if (ANY && !(best.t + eps >= maxDist)) {
-                                        R.t = best.t;
-                                        R.tri = best.pos;
-                                        return true;
-                                    }
-                                }
-                            }
-                            if (best.pos >= 0) { t = best.t; hitTri = best.pos; }
-                            needPop = true;
-                        }
-                    } else {
-                        // ---- reference inner node: intersectNonLeaf + intersectDeeper, exact arithmetic
-                        const int L = (int)a, Rn = (int)a + 1;
-                        const float4 l0 = __ldg(S.nodes + 2 * L), l1 = __ldg(S.nodes + 2 * L + 1);
-                        const float4 r0 = __ldg(S.nodes + 2 * L + 2), r1 = __ldg(S.nodes + 2 * L + 3);
-                        float tL = -1.0f, tR = -1.0f, tmp;
-                        if (slabTest(mk3(l0), mk3(l1), o, d, t, tmp)) tL = tmp;
-                        if (slabTest(mk3(r0), mk3(r1), o, d, t, tmp)) tR = tmp;
-                        const bool inL = startsInBox(o, mk3(l0), mk3(l1));
-                        const bool inR = startsInBox(o, mk3(r0), mk3(r1));
-                        int first = -1, second = -1;
-                        float tS = -1.0f;
-                        if (inL && inR) {
-                            first = L; second = Rn; tS = -1.0f;
-                        } else if (inL) {
-                            first = L;
-                            if (!(tR < 0)) { second = Rn; tS = tR; }
-                        } else if (inR) {
-                            first = Rn;
-                            if (!(tL < 0)) { second = L; tS = tL; }
-                        } else {
-                            if (tL < 0 && tR < 0) {
-                            } else if (tL < 0) {
-                                first = Rn;
-                            } else if (tR < 0) {
-                                first = L;
-                            } else if (tL < tR) {
-                                first = L; second = Rn; tS = tR;
-                            } else {
-                                first = Rn; second = L; tS = tL;
-                            }
-                        }
-                        if (second >= 0) {
-                            stN[sp] = second;
-                            stT[sp] = tS;
-                            sp++;
-                        }
-                        if (first >= 0) node = first;
-                        else needPop = true;
-                    }
-                } else {
-                    const int sn = node & ~CGRT_SUBFLAG;
-                    const float4 q0 = __ldg(S.subNodes + 2 * sn), q1 = __ldg(S.subNodes + 2 * sn + 1);
-                    const int a = f2i(q0.w), b = f2i(q1.w);
-                    if (b != 0) {
-                        // ---- sub-tree leaf: exact tests of the few triangles that survived the culling
-                        for (int i = a; i < a + b; i++) {
-                            if (leafCandidate(S, i, o, d, best)) {
-                                if (ANY && !(best.t + eps >= maxDist)) {
-                                    R.t = best.t;
-                                    R.tri = best.pos;
-                                    return true;
-                                }
-                            }
-                        }
-                        needPop = true;
-                    } else {
-                        // ---- sub-tree inner node: tolerant slab tests, nearer child first
-                        const float4 l0 = __ldg(S.subNodes + 2 * a), l1 = __ldg(S.subNodes + 2 * a + 1);
-                        const float4 r0 = __ldg(S.subNodes + 2 * a + 2), r1 = __ldg(S.subNodes + 2 * a + 3);
-                        float tL, tR;
-                        const bool hL = slabLoose(l0, l1, o, inv, best.t, tL);
-                        const bool hR = slabLoose(r0, r1, o, inv, best.t, tR);
-                        if (hL && hR) {
-                            const bool leftFirst = tL <= tR;
-                            stN[sp] = (leftFirst ? a + 1 : a) | CGRT_SUBFLAG;
-                            stT[sp] = leftFirst ? tR : tL;
-                            sp++;
-                            node = (leftFirst ? a : a + 1) | CGRT_SUBFLAG;
-                        } else if (hL || hR) {
-                            node = (hL ? a : a + 1) | CGRT_SUBFLAG;
-                        } else {
-                            needPop = true;
-                        }
-                    }
-                }
-                if (needPop) {
-                    while (true) {
-                        if (inLeaf && sp == subBase) { // the reference leaf's sub-tree is exhausted: commit its result
-                            if (best.pos >= 0) { t = best.t; hitTri = best.pos; }
-                            inLeaf = false;
-                        }
-                        if (sp == 0) {
-                            done = true;
-                            break;
-                        }
-                        sp--;
-                        const int n = stN[sp];
-                        const float key = stT[sp];
-                        if (n & CGRT_SUBFLAG) {
-                            if (key > best.t * slack) continue;
-                        } else {
-                            if (t < key) continue;
-                        }
-                        node = n;
-                        break;
-                    }
-                }
+enum { TRAV_CONTINUE = 0, TRAV_DONE = 1, TRAV_FIRED = 2 };
+
+// intersectDataStructure (bvh.cpp:831-844): returns true iff the tree has to be traversed for this ray.
+RT_DEV bool travBegin(const DevScene& S, Trav& T, const V3& o, const V3& d, float tIn)
+{
+    T.o = o;
+    T.d = d;
+    T.t = tIn;
+    T.hitTri = -1;
+    T.sp = 0;
+    T.node = 0;
+    T.subBase = 0;
+    T.inLeaf = false;
+    T.best.t = tIn; T.best.pos = -1; T.best.rank = -1; T.best.shortcut = false;
+    if (S.nNodes <= 0) return false;
+    const float4 rq0 = __ldg(S.nodes + 0), rq1 = __ldg(S.nodes + 1);
+    bool enter = startsInBox(o, mk3(rq0), mk3(rq1));
+    if (!enter) {
+        float tmp;
+        enter = slabTest(mk3(rq0), mk3(rq1), o, d, tIn, tmp);
+    }
+    if (!enter) return false;
+    // per-ray data of the tolerant sub-tree slab test; rays with extreme direction components scan leaves instead
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    const bool okx = (ax == 0.0f) || (ax >= 1e-20f && ax <= 1e20f);
+    const bool oky = (ay == 0.0f) || (ay >= 1e-20f && ay <= 1e20f);
+    const bool okz = (az == 0.0f) || (az >= 1e-20f && az <= 1e20f);
+    const bool fin = fabsf(o.x) <= 1e30f && fabsf(o.y) <= 1e30f && fabsf(o.z) <= 1e30f; // false for NaN
+    T.useSub = S.subNodes != nullptr && okx && oky && okz && fin;
+    T.inv.x = ax == 0.0f ? 1e30f : 1.0f / d.x;
+    T.inv.y = ay == 0.0f ? 1e30f : 1.0f / d.y;
+    T.inv.z = az == 0.0f ? 1e30f : 1.0f / d.z;
+    return true;
+}
+
+// Node classes of the state machine. The current node id encodes its class: reference nodes are plain indices into
+// S.nodes; CGRT_SUBFLAG marks a sub-tree inner node (index into S.subNodes); CGRT_SUBFLAG|CGRT_LEAFFLAG marks a sub-tree
+// leaf and carries its triangle range directly (bit 28 = count-1, bits 0..27 = first position), so a sub-tree leaf costs
+// no node fetch.
+#define CGRT_LEAFFLAG 0x20000000
+#define CGRT_LEAFCNT_SHIFT 28
+#define CGRT_POS_MASK 0x0fffffff
+enum { CLS_REF = 0, CLS_SUBINNER = 1, CLS_SUBLEAF = 2, CLS_NONE = 3 };
+RT_DEV int travClass(int node)
+{
+    return !(node & CGRT_SUBFLAG) ? CLS_REF : ((node & CGRT_LEAFFLAG) ? CLS_SUBLEAF : CLS_SUBINNER);
+}
+RT_DEV int subChildId(int index, const float4& lo, const float4& hi)
+{
+    const int b = f2i(hi.w);
+    if (b == 0) return index | CGRT_SUBFLAG;
+    return CGRT_SUBFLAG | CGRT_LEAFFLAG | ((b - 1) << CGRT_LEAFCNT_SHIFT) | f2i(lo.w);
+}
+
+// pop: next pending node that is not pruned, committing the reference leaf when its sub-tree entries are gone
+RT_DEV int travPop(Trav& T, TravStack& K)
+{
+    const float slack = 1.000001f;
+    while (true) {
+        if (T.inLeaf && T.sp == T.subBase) {
+            if (T.best.pos >= 0) { T.t = T.best.t; T.hitTri = T.best.pos; }
+            T.inLeaf = false;
+        }
+        if (T.sp == 0) return TRAV_DONE;
+        T.sp--;
+        const int n = K.n[T.sp];
+        const float key = K.t[T.sp];
+        if (n & CGRT_SUBFLAG) {
+            if (key > T.best.t * slack) continue;
+        } else {
+            if (T.t < key) continue;
+        }
+        T.node = n;
+        return TRAV_CONTINUE;
+    }
+}
+
+// one step on a reference node
+template <bool ANY>
+RT_DEV int travStepRef(const DevScene& S, Trav& T, TravStack& K, float eps, float maxDist)
+{
+    const V3 o = T.o, d = T.d;
+    const int node = T.node;
+    const float4 q0 = __ldg(S.nodes + 2 * node), q1 = __ldg(S.nodes + 2 * node + 1);
+    const uint32_t a = (uint32_t)f2i(q0.w), b = (uint32_t)f2i(q1.w);
+    if (b != 0u) {
+        // ---- reference leaf
+        T.best.t = T.t; T.best.pos = -1; T.best.rank = -1; T.best.shortcut = false;
+        const int sr = T.useSub ? __ldg(S.subRoot + node) : -1;
+        if (sr >= 0) {
+            T.inLeaf = true;
+            T.subBase = T.sp;
+            T.node = sr | CGRT_SUBFLAG; // the root of a sub-tree is always an inner node (leaves below 8 triangles have none)
+            return TRAV_CONTINUE;
+        }
+        const uint32_t end = a + b;
+        for (uint32_t i = a; i < end; i++) {
+            if (leafCandidate(S, (int)i, o, d, T.best)) {
+                if (ANY && !(T.best.t + eps >= maxDist)) return TRAV_FIRED;
             }
         }
+        if (T.best.pos >= 0) { T.t = T.best.t; T.hitTri = T.best.pos; }
+        return travPop(T, K);
     }
-    // ---- sphere loop, src/bounding_volume_hierarchy.cpp:878-879
+    // ---- reference inner node: intersectNonLeaf + intersectDeeper, exact arithmetic
+    const int L = (int)a, Rn = (int)a + 1;
+    const float4 l0 = __ldg(S.nodes + 2 * L), l1 = __ldg(S.nodes + 2 * L + 1);
+    const float4 r0 = __ldg(S.nodes + 2 * L + 2), r1 = __ldg(S.nodes + 2 * L + 3);
+    float tL = -1.0f, tR = -1.0f, tmp;
+    if (slabTest(mk3(l0), mk3(l1), o, d, T.t, tmp)) tL = tmp;
+    if (slabTest(mk3(r0), mk3(r1), o, d, T.t, tmp)) tR = tmp;
+    const bool inL = startsInBox(o, mk3(l0), mk3(l1));
+    const bool inR = startsInBox(o, mk3(r0), mk3(r1));
+    int first = -1, second = -1;
+    float tS = -1.0f;
+    if (inL && inR) { // both visited unconditionally, left operand of `|` first (g++ order)
+        first = L; second = Rn; tS = -1.0f;
+    } else if (inL) {
+        first = L;
+        if (!(tR < 0)) { second = Rn; tS = tR; }
+    } else if (inR) {
+        first = Rn;
+        if (!(tL < 0)) { second = L; tS = tL; }
+    } else {
+        if (tL < 0 && tR < 0) {
+        } else if (tL < 0) {
+            first = Rn;
+        } else if (tR < 0) {
+            first = L;
+        } else if (tL < tR) {
+            first = L; second = Rn; tS = tR;
+        } else {
+            first = Rn; second = L; tS = tL;
+        }
+    }
+    if (second >= 0) {
+        K.n[T.sp] = second;
+        K.t[T.sp] = tS;
+        T.sp++;
+    }
+    if (first >= 0) {
+        T.node = first;
+        return TRAV_CONTINUE;
+    }
+    return travPop(T, K);
+}
+
+// one step on a sub-tree inner node: tolerant slab tests, nearer child first
+RT_DEV int travStepSubInner(const DevScene& S, Trav& T, TravStack& K)
+{
+    const int sn = T.node & CGRT_POS_MASK;
+    const int a = f2i(__ldg(S.subNodes + 2 * sn).w);
+    const float4 l0 = __ldg(S.subNodes + 2 * a), l1 = __ldg(S.subNodes + 2 * a + 1);
+    const float4 r0 = __ldg(S.subNodes + 2 * a + 2), r1 = __ldg(S.subNodes + 2 * a + 3);
+    float tL, tR;
+    const bool hL = slabLoose(l0, l1, T.o, T.inv, T.best.t, tL);
+    const bool hR = slabLoose(r0, r1, T.o, T.inv, T.best.t, tR);
+    const int idL = subChildId(a, l0, l1), idR = subChildId(a + 1, r0, r1);
+    if (hL && hR) {
+        const bool leftFirst = tL <= tR;
+        K.n[T.sp] = leftFirst ? idR : idL;
+        K.t[T.sp] = leftFirst ? tR : tL;
+        T.sp++;
+        T.node = leftFirst ? idL : idR;
+        return TRAV_CONTINUE;
+    }
+    if (hL || hR) {
+        T.node = hL ? idL : idR;
+        return TRAV_CONTINUE;
+    }
+    return travPop(T, K);
+}
+
+// one step on a sub-tree leaf: exact tests of the few triangles that survived the culling
+template <bool ANY>
+RT_DEV int travStepSubLeaf(const DevScene& S, Trav& T, TravStack& K, float eps, float maxDist)
+{
+    const int first = T.node & CGRT_POS_MASK;
+    const int count = ((T.node >> CGRT_LEAFCNT_SHIFT) & 1) + 1;
+    for (int i = first; i < first + count; i++) {
+        if (leafCandidate(S, i, T.o, T.d, T.best)) {
+            if (ANY && !(T.best.t + eps >= maxDist)) return TRAV_FIRED;
+        }
+    }
+    return travPop(T, K);
+}
+
+template <bool ANY>
+RT_DEV int travStep(const DevScene& S, Trav& T, TravStack& K, float eps, float maxDist)
+{
+    const int cls = travClass(T.node);
+    if (cls == CLS_REF) return travStepRef<ANY>(S, T, K, eps, maxDist);
+    if (cls == CLS_SUBINNER) return travStepSubInner(S, T, K);
+    return travStepSubLeaf<ANY>(S, T, K, eps, maxDist);
+}
+
+// After the tree: the sphere loop of BoundingVolumeHierarchy::intersect (bvh.cpp:878-879) and the result record.
+// `state` is TRAV_FIRED when the any-hit predicate already fired inside the tree. Returns hit (closest) / shadowed (ANY).
+template <bool ANY>
+RT_DEV bool travFinish(const DevScene& S, Trav& T, int state, float eps, float maxDist, TraceResult& R)
+{
+    R.sphere = -1;
+    if (ANY && state == TRAV_FIRED) {
+        R.t = T.best.t;
+        R.tri = T.best.pos;
+        return true;
+    }
+    float t = T.t;
     for (int s = 0; s < S.nSpheres; s++) {
         const float4 c = __ldg(S.spheres + 3 * s);
         float ts;
         V3 nn;
-        if (sphereTest(mk3(c), c.w, o, d, t, ts, nn)) {
+        if (sphereTest(mk3(c), c.w, T.o, T.d, t, ts, nn)) {
             t = ts;
             R.sphere = s;
             R.sphereN = nn;
             if (ANY && !(ts + eps >= maxDist)) {
                 R.t = t;
-                R.tri = hitTri;
+                R.tri = T.hitTri;
                 return true;
             }
         }
     }
     R.t = t;
-    R.tri = hitTri;
+    R.tri = T.hitTri;
     if (ANY) return false;
-    return hitTri >= 0 || R.sphere >= 0;
+    return T.hitTri >= 0 || R.sphere >= 0;
+}
+
+// one ray, start to finish (batch entry points that do not use persistent warps)
+template <bool ANY>
+RT_DEV bool traverseFast(const DevScene& S, const V3& o, const V3& d, float tIn, float eps, float maxDist, TraceResult& R)
+{
+    Trav T;
+    TravStack K;
+    int state = TRAV_DONE;
+    if (travBegin(S, T, o, d, tIn)) {
+        do {
+            state = travStep<ANY>(S, T, K, eps, maxDist);
+        } while (state == TRAV_CONTINUE);
+    }
+    return travFinish<ANY>(S, T, state, eps, maxDist, R);
 }
 
 // Closest-hit traversal in the reference's exact visiting order:

@@ -388,6 +388,200 @@ __global__ void __launch_bounds__(128) k_shadow(DevScene S, const FrameParams* _
     }
 }
 
+// =================================================================================================================
+// Persistent warps: the production form of the three traversal kernels.
+// Every lane owns a resumable traversal (Trav). Between bursts of steps, lanes whose ray is finished hand in their result
+// (collectively, so that queue pushes stay warp-aggregated) and are given the next ray from a global work counter, so a warp
+// keeps its lanes busy instead of idling until its slowest ray is done; rays that miss the root box (most primary rays)
+// cost one converged refill round. A Policy supplies the rays and consumes the results:
+//     bool load(int idx, V3& o, V3& d, float& tIn, float& eps, float& maxDist)   false = nothing to trace for this index
+//     void retire(bool fin, int idx, bool traced, bool result, const TraceResult& R, const Trav& T, float tIn)   (all lanes)
+// =================================================================================================================
+#define CGRT_STEPS_PER_ROUND 6
+#define CGRT_REFILL_MIN_IDLE 6
+// vote weights ~ 1 / (instructions of one step of the class): exact reference node ~260, tolerant sub-tree node ~60,
+// sub-tree leaf (<= 2 exact triangle tests) ~120
+#define CGRT_W_REF 4
+#define CGRT_W_SUBINNER 16
+#define CGRT_W_SUBLEAF 8
+
+template <bool ANY, class Policy>
+RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCounter)
+{
+    Trav T;
+    TravStack K;
+    int idx = -1;               // work item owned by this lane, -1 = idle
+    int state = TRAV_DONE;
+    bool traced = false;        // the item produced a ray (load() returned true)
+    float tIn = 0.0f, eps = 0.0f, maxDist = 0.0f;
+    bool exhausted = false;     // warp-uniform: the work counter has run past n
+    const int lane = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    while (true) {
+        // ---- refill
+        const unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
+        const int nIdle = __popc(idle);
+        if (!exhausted && (nIdle >= CGRT_REFILL_MIN_IDLE || idle == 0xffffffffu)) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(workCounter, nIdle);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + nIdle >= n) exhausted = true;
+            if (idx < 0) {
+                const int mine = base + __popc(idle & ltMask);
+                if (mine < n) {
+                    idx = mine;
+                    V3 o, d;
+                    traced = P.load(idx, o, d, tIn, eps, maxDist);
+                    state = TRAV_DONE;
+                    if (traced) {
+                        if (travBegin(S, T, o, d, tIn)) state = TRAV_CONTINUE;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, idx >= 0) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- a burst of steps
+        // Each iteration executes ONE node class, chosen by a warp vote that maximises lanes-advanced per instruction
+        // (weights ~ 1 / cost of the class's step); lanes waiting in another class keep their state. This trades a little
+        // latency for not paying all three code paths on every iteration.
+#pragma unroll 1
+        for (int it = 0; it < CGRT_STEPS_PER_ROUND; it++) {
+            const bool run = idx >= 0 && state == TRAV_CONTINUE;
+            const int cls = run ? travClass(T.node) : CLS_NONE;
+            const int s0 = __popc(__ballot_sync(0xffffffffu, cls == CLS_REF)) * CGRT_W_REF;
+            const int s1 = __popc(__ballot_sync(0xffffffffu, cls == CLS_SUBINNER)) * CGRT_W_SUBINNER;
+            const int s2 = __popc(__ballot_sync(0xffffffffu, cls == CLS_SUBLEAF)) * CGRT_W_SUBLEAF;
+            if ((s0 | s1 | s2) == 0) break;
+            if (s0 >= s1 && s0 >= s2) {
+                if (cls == CLS_REF) state = travStepRef<ANY>(S, T, K, eps, maxDist);
+            } else if (s1 >= s2) {
+                if (cls == CLS_SUBINNER) state = travStepSubInner(S, T, K);
+            } else {
+                if (cls == CLS_SUBLEAF) state = travStepSubLeaf<ANY>(S, T, K, eps, maxDist);
+            }
+        }
+        // ---- retire finished lanes (collective)
+        const bool fin = idx >= 0 && state != TRAV_CONTINUE;
+        TraceResult R;
+        R.sphere = -1; R.tri = -1; R.t = tIn;
+        bool result = false;
+        if (fin && traced) result = travFinish<ANY>(S, T, state, eps, maxDist, R);
+        P.retire(fin, idx, traced, result, R, T, tIn);
+        if (fin) idx = -1;
+    }
+}
+
+struct PrimaryPolicy {
+    const DevScene& S;
+    const FrameParams& P;
+    const WaveBuffers& B;
+    const int* tileList;
+    float* fb;
+    int outIdx; // per lane: output index of the item being traced
+    RT_DEV bool load(int slot, V3& o, V3& d, float& tIn, float& eps, float& maxDist)
+    {
+        int x, y;
+        outIdx = -1;
+        if (!slotToPixel(P, tileList, slot, x, y, outIdx)) {
+            outIdx = -1;
+            return false;
+        }
+        o = mk3(P.camX, P.camY, P.camZ);
+        d = primaryDirection(P, x, y);
+        tIn = FLT_MAX;
+        eps = 0.0f;
+        maxDist = 0.0f;
+        return true;
+    }
+    RT_DEV void retire(bool fin, int slot, bool traced, bool hit, const TraceResult& R, const Trav& T, float)
+    {
+        if (fin) {
+            if (!traced) {
+                if (P.world > 1) storeRGB(fb, slot, mk3(0.0f, 0.0f, 0.0f)); // padding pixels of edge tiles
+            } else if (!hit) {
+                storeRGB(fb, outIdx, mk3(0.0f, 0.0f, 0.0f)); // trace(): miss -> black, src/main.cpp:288-294
+            }
+        }
+        pushHitRecord(S, B, 0, fin && traced && hit, R, T.o, T.d, outIdx, -1);
+    }
+};
+
+struct BouncePolicy {
+    const DevScene& S;
+    const WaveBuffers& B;
+    float* fb;
+    int level;
+    int pathId, outIdx;
+    RT_DEV bool load(int i, V3& o, V3& d, float& tIn, float& eps, float& maxDist)
+    {
+        const float4 r0 = B.bounceQ[2 * (size_t)i], r1 = B.bounceQ[2 * (size_t)i + 1];
+        o = mk3(r0);
+        d = mk3(r1);
+        tIn = r0.w;
+        pathId = f2i(r1.w);
+        outIdx = B.pathPix[pathId];
+        eps = 0.0f;
+        maxDist = 0.0f;
+        return true;
+    }
+    RT_DEV void retire(bool fin, int, bool, bool hit, const TraceResult& R, const Trav& T, float)
+    {
+        if (fin && !hit) // reflected colour is black; unwind the levels above (src/main.cpp:288-294 then :263)
+            storeRGB(fb, outIdx, foldPath(B.pathState, B.cap, level, pathId, mk3(0.0f, 0.0f, 0.0f)));
+        pushHitRecord(S, B, level, fin && hit, R, T.o, T.d, outIdx, pathId);
+    }
+};
+
+struct ShadowPolicy {
+    const WaveBuffers& B;
+    const float4* lights;
+    int nL;
+    RT_DEV bool load(int i, V3& o, V3& d, float& tIn, float& eps, float& maxDist)
+    { // pointInShadow, src/main.cpp:104-135
+        const int h = i / nL, l = i - h * nL;
+        const float4 a = B.hitQ[3 * (size_t)h];
+        const V3 pointOn = mk3(a);
+        const V3 lightPos = mk3(__ldg(lights + 2 * l));
+        const V3 fromPosToLight = lightPos - pointOn;
+        d = normalize3(fromPosToLight);
+        eps = 0.001f;
+        o = pointOn + eps * d;
+        tIn = FLT_MAX;
+        maxDist = length3(fromPosToLight);
+        return true;
+    }
+    RT_DEV void retire(bool fin, int i, bool, bool shadowed, const TraceResult&, const Trav&, float)
+    {
+        if (fin) B.lit[i] = shadowed ? 0 : 1;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_primary_p(DevScene S, const FrameParams* __restrict__ Pp, WaveBuffers B,
+                                                   const int* __restrict__ tileList, float* __restrict__ fb, int* work)
+{
+    const FrameParams P = *Pp;
+    PrimaryPolicy pol{S, P, B, tileList, fb, -1};
+    persistentTraverse<false>(S, pol, P.nSlots, work);
+}
+
+__global__ void __launch_bounds__(128) k_bounce_closest_p(DevScene S, WaveBuffers B, int level, float* __restrict__ fb, int* work)
+{
+    BouncePolicy pol{S, B, fb, level, -1, 0};
+    persistentTraverse<false>(S, pol, B.counts[CGRT_CNT_BOUNCE + level], work);
+}
+
+__global__ void __launch_bounds__(128) k_shadow_p(DevScene S, const FrameParams* __restrict__ Pp,
+                                                  const float4* __restrict__ lights, WaveBuffers B, int level, int* work)
+{
+    const int nL = Pp->nLights;
+    ShadowPolicy pol{B, lights, nL};
+    persistentTraverse<true>(S, pol, B.counts[CGRT_CNT_HIT + level] * nL, work);
+}
+
 // ---- shading + bounce emission: one thread per hit.  shading/shade, src/main.cpp:61-98, 220-264 ---------------------------
 __global__ void __launch_bounds__(128) k_shade(DevScene S, const FrameParams* __restrict__ Pp,
                                                const float4* __restrict__ lights, WaveBuffers B, int level,
@@ -611,11 +805,12 @@ int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams&
         cudaMemsetAsync(fb, 0, px * 3 * sizeof(float), st);
         return 0;
     }
-    const int persistent = numSMs * 16; // 16 CTAs x 128 threads = 2048 threads/SM when registers allow
+    const int persistent = numSMs * 8; // persistent warps: 8 CTAs x 4 warps per SM (register-limited residency is 5-8 CTAs)
     const int gPrimary = gridFor((size_t)hP.nSlots, 128, 1 << 30);
     traceBegin(tr, 0, st);
+    int workSlot = CGRT_CNT_WORK;
     if (countTests) k_primary<true><<<gPrimary, 128, 0, st>>>(S, dP, B, dTileList, fb);
-    else k_primary<false><<<gPrimary, 128, 0, st>>>(S, dP, B, dTileList, fb);
+    else k_primary_p<<<min(gPrimary, persistent), 128, 0, st>>>(S, dP, B, dTileList, fb, B.counts + workSlot++);
     traceEnd(tr, 0, st);
     launches++;
     const int gHit = gridFor((size_t)hP.nSlots, 128, persistent);
@@ -624,14 +819,14 @@ int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams&
         if (level > 0) {
             traceBegin(tr, 1, st);
             if (countTests) k_bounce_closest<true><<<gHit, 128, 0, st>>>(S, B, level, fb);
-            else k_bounce_closest<false><<<gHit, 128, 0, st>>>(S, B, level, fb);
+            else k_bounce_closest_p<<<gHit, 128, 0, st>>>(S, B, level, fb, B.counts + workSlot++);
             traceEnd(tr, 1, st);
             launches++;
         }
         if (hP.nLights > 0) {
             traceBegin(tr, 2, st);
             if (countTests) k_shadow<true><<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level);
-            else k_shadow<false><<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level);
+            else k_shadow_p<<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level, B.counts + workSlot++);
             traceEnd(tr, 2, st);
             launches++;
         }

@@ -47,7 +47,8 @@ namespace cgrt {
 #define CGRT_MAX_LEVELS 16                      // upper bound on cgrt_render_params::trace_limit
 #define CGRT_CNT_HIT 0                          // counts[CGRT_CNT_HIT + level]    = hits found at `level`
 #define CGRT_CNT_BOUNCE CGRT_MAX_LEVELS         // counts[CGRT_CNT_BOUNCE + level] = rays queued for `level` (level >= 1)
-#define CGRT_CNT_TOTAL (2 * CGRT_MAX_LEVELS + 1)
+#define CGRT_CNT_WORK (2 * CGRT_MAX_LEVELS + 1)  // counts[CGRT_CNT_WORK + k] = work counter of the k-th persistent launch of the frame
+#define CGRT_CNT_TOTAL (CGRT_CNT_WORK + 2 * CGRT_MAX_LEVELS + 2)
 #define CGRT_PARAM_BLOCK_HEADER 128             // bytes reserved for FrameParams in the per-frame block; lights follow
 
 // Per-frame constants, evaluated on the host with libm exactly as Trackball does (framework/src/trackball.cpp:70-73, 92-103)
