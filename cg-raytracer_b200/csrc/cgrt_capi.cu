@@ -192,6 +192,9 @@ struct cgrt_scene {
     DevBuf<uint8_t> lit;
     DevBuf<int> pathPix, counts, tileList;
     DevBuf<unsigned long long> tests;
+    DevBuf<float4> hitRec;
+    DevBuf<int> hitList, pathDepth;
+    bool lastPathPipeline = false;
     std::vector<cudaEvent_t> traceEvents;
     WaveTrace trace{};
     bool lastCounted = false;
@@ -228,7 +231,7 @@ static void destroyScene(cgrt_scene* s)
     s->triN0.release(); s->triN1.release(); s->triN2.release(); s->mats.release(); s->spheres.release();
     s->origToLeaf.release(); s->subNodes.release(); s->subRoot.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->frame.release();
-    s->tests.release();
+    s->tests.release(); s->hitRec.release(); s->hitList.release(); s->pathDepth.release();
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->hParamRing) cudaFreeHost(s->hParamRing);
     if (s->hFramePinned) cudaFreeHost(s->hFramePinned);
@@ -796,11 +799,19 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
     const size_t cap = (size_t)std::max(P.nSlots, 1);
     const int nL = std::max(P.nLights, 1);
     const int levels = std::max(P.traceLimit - 1, 1);
-    RC(s->hitQ.ensure(cap * 3));
-    RC(s->bounceQ.ensure(cap * 2));
-    RC(s->lit.ensure(cap * nL));
+    const int pathLevels = std::max(P.traceLimit, 1);
+    if (p->flags & CGRT_RENDER_COUNT) { // level-by-level counting pipeline
+        RC(s->hitQ.ensure(cap * 3));
+        RC(s->bounceQ.ensure(cap * 2));
+        RC(s->lit.ensure(cap * nL));
+        RC(s->pathState.ensure(cap * 2 * levels));
+    } else { // path pipeline: one record per (path, level)
+        RC(s->hitRec.ensure(cap * pathLevels * 3));
+        RC(s->hitList.ensure(cap * pathLevels));
+        RC(s->pathDepth.ensure(cap));
+        RC(s->lit.ensure(cap * pathLevels * nL));
+    }
     RC(s->pathPix.ensure(cap));
-    RC(s->pathState.ensure(cap * 2 * levels));
     RC(s->counts.ensure(CGRT_CNT_TOTAL));
     RC(s->tests.ensure(6));
     // parameter block: FrameParams header + lights (2 x float4 each)
@@ -860,9 +871,26 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
     s->trace.classMask = p->flags & CGRT_RENDER_PROFILE_ALL;
     const bool countTests = (p->flags & CGRT_RENDER_COUNT) != 0;
     CK(cudaEventRecord(s->ev0, st));
-    const int launches = launchWavefront(s->dev, (const FrameParams*)s->dParamBlock.p, P,
-                                         (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), B, dTiles, d_out,
-                                         s->di.numSMs, countTests, &s->trace, st);
+    int launches;
+    if (countTests) {
+        launches = launchWavefront(s->dev, (const FrameParams*)s->dParamBlock.p, P,
+                                   (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), B, dTiles, d_out,
+                                   s->di.numSMs, true, &s->trace, st);
+    } else {
+        PathBuffers PB;
+        PB.hitRec = s->hitRec.p;
+        PB.hitList = s->hitList.p;
+        PB.lit = s->lit.p;
+        PB.pathPix = s->pathPix.p;
+        PB.pathDepth = s->pathDepth.p;
+        PB.counts = s->counts.p;
+        PB.cap = B.cap;
+        PB.levels = std::max(P.traceLimit, 1);
+        launches = launchPathPipeline(s->dev, (const FrameParams*)s->dParamBlock.p, P,
+                                      (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), PB, dTiles, d_out,
+                                      s->di.numSMs, &s->trace, st);
+    }
+    s->lastPathPipeline = !countTests;
     CK(cudaEventRecord(s->ev1, st));
     s->lastCounted = countTests;
     CK(cudaGetLastError());
@@ -899,10 +927,16 @@ int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
         }
     }
     stats->primary = primary;
-    stats->primary_hit = (uint64_t)counts[CGRT_CNT_HIT + 0];
-    for (int l = 0; l < P.traceLimit; l++) {
-        stats->shadow += (uint64_t)counts[CGRT_CNT_HIT + l] * (uint64_t)P.nLights;
-        if (l >= 1) stats->bounce += (uint64_t)counts[CGRT_CNT_BOUNCE + l];
+    if (s->lastPathPipeline) {
+        stats->primary_hit = (uint64_t)counts[CGRT_CNT_PATHS];
+        stats->shadow = (uint64_t)counts[CGRT_CNT_HITS] * (uint64_t)P.nLights;
+        stats->bounce = (uint64_t)counts[CGRT_CNT_BOUNCES];
+    } else {
+        stats->primary_hit = (uint64_t)counts[CGRT_CNT_HIT + 0];
+        for (int l = 0; l < P.traceLimit; l++) {
+            stats->shadow += (uint64_t)counts[CGRT_CNT_HIT + l] * (uint64_t)P.nLights;
+            if (l >= 1) stats->bounce += (uint64_t)counts[CGRT_CNT_BOUNCE + l];
+        }
     }
     if (P.traceLimit == 0) stats->primary = 0;
     stats->kernel_launches = s->lastLaunches;

@@ -395,7 +395,8 @@ __global__ void __launch_bounds__(128) k_shadow(DevScene S, const FrameParams* _
 // keeps its lanes busy instead of idling until its slowest ray is done; rays that miss the root box (most primary rays)
 // cost one converged refill round. A Policy supplies the rays and consumes the results:
 //     bool load(int idx, V3& o, V3& d, float& tIn, float& eps, float& maxDist)   false = nothing to trace for this index
-//     void retire(bool fin, int idx, bool traced, bool result, const TraceResult& R, const Trav& T, float tIn)   (all lanes)
+//     bool retire(bool fin, int idx, bool traced, bool result, const TraceResult& R, const Trav& T, V3& o, V3& d, float& tIn)
+//          called by ALL lanes; returns true when the lane continues with a follow-up ray (o, d, tIn) of the same item
 // =================================================================================================================
 #define CGRT_STEPS_PER_ROUND 6
 #define CGRT_REFILL_MIN_IDLE 6
@@ -470,8 +471,15 @@ RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCou
         R.sphere = -1; R.tri = -1; R.t = tIn;
         bool result = false;
         if (fin && traced) result = travFinish<ANY>(S, T, state, eps, maxDist, R);
-        P.retire(fin, idx, traced, result, R, T, tIn);
-        if (fin) idx = -1;
+        V3 no, nd;
+        const bool again = P.retire(fin, idx, traced, result, R, T, no, nd, tIn);
+        if (fin) {
+            if (again) {
+                state = travBegin(S, T, no, nd, tIn) ? TRAV_CONTINUE : TRAV_DONE;
+            } else {
+                idx = -1;
+            }
+        }
     }
 }
 
@@ -497,7 +505,7 @@ struct PrimaryPolicy {
         maxDist = 0.0f;
         return true;
     }
-    RT_DEV void retire(bool fin, int slot, bool traced, bool hit, const TraceResult& R, const Trav& T, float)
+    RT_DEV bool retire(bool fin, int slot, bool traced, bool hit, const TraceResult& R, const Trav& T, V3&, V3&, float&)
     {
         if (fin) {
             if (!traced) {
@@ -507,6 +515,7 @@ struct PrimaryPolicy {
             }
         }
         pushHitRecord(S, B, 0, fin && traced && hit, R, T.o, T.d, outIdx, -1);
+        return false;
     }
 };
 
@@ -528,11 +537,12 @@ struct BouncePolicy {
         maxDist = 0.0f;
         return true;
     }
-    RT_DEV void retire(bool fin, int, bool, bool hit, const TraceResult& R, const Trav& T, float)
+    RT_DEV bool retire(bool fin, int, bool, bool hit, const TraceResult& R, const Trav& T, V3&, V3&, float&)
     {
         if (fin && !hit) // reflected colour is black; unwind the levels above (src/main.cpp:288-294 then :263)
             storeRGB(fb, outIdx, foldPath(B.pathState, B.cap, level, pathId, mk3(0.0f, 0.0f, 0.0f)));
         pushHitRecord(S, B, level, fin && hit, R, T.o, T.d, outIdx, pathId);
+        return false;
     }
 };
 
@@ -554,9 +564,10 @@ struct ShadowPolicy {
         maxDist = length3(fromPosToLight);
         return true;
     }
-    RT_DEV void retire(bool fin, int i, bool, bool shadowed, const TraceResult&, const Trav&, float)
+    RT_DEV bool retire(bool fin, int i, bool, bool shadowed, const TraceResult&, const Trav&, V3&, V3&, float&)
     {
         if (fin) B.lit[i] = shadowed ? 0 : 1;
+        return false;
     }
 };
 
@@ -580,6 +591,189 @@ __global__ void __launch_bounds__(128) k_shadow_p(DevScene S, const FrameParams*
     const int nL = Pp->nLights;
     ShadowPolicy pol{B, lights, nL};
     persistentTraverse<true>(S, pol, B.counts[CGRT_CNT_HIT + level] * nL, work);
+}
+
+// =================================================================================================================
+// Path pipeline (production): k_paths -> k_shadow_all -> k_shade_paths
+// =================================================================================================================
+// getFinalColor/trace/shade (src/main.cpp:241-310) for one pixel is a chain: primary ray, then one reflection ray per
+// mirror hit while level + 1 < trace limit. A lane of k_paths follows that chain itself (the follow-up ray of shade(),
+// main.cpp:252-256, is handed straight back to the traversal), so the chain costs no kernel boundary; the shadow rays
+// (pointInShadow) do not influence the chain and are traced afterwards for all levels at once.
+struct PathsPolicy {
+    const DevScene& S;
+    const FrameParams& P;
+    const PathBuffers& B;
+    const int* tileList;
+    float* fb;
+    int outIdx, level, path; // per lane
+    RT_DEV bool load(int slot, V3& o, V3& d, float& tIn, float& eps, float& maxDist)
+    {
+        int x, y;
+        level = 0;
+        path = -1;
+        if (!slotToPixel(P, tileList, slot, x, y, outIdx)) {
+            outIdx = -1;
+            return false;
+        }
+        o = mk3(P.camX, P.camY, P.camZ);
+        d = primaryDirection(P, x, y);
+        tIn = FLT_MAX;
+        eps = 0.0f;
+        maxDist = 0.0f;
+        return true;
+    }
+    RT_DEV bool retire(bool fin, int slot, bool traced, bool hit, const TraceResult& R, const Trav& T, V3& no, V3& nd, float& nt)
+    {
+        const bool isHit = fin && traced && hit;
+        const int newPath = warpPush(B.counts + CGRT_CNT_PATHS, isHit && level == 0);
+        const int listPos = warpPush(B.counts + CGRT_CNT_HITS, isHit);
+        bool again = false;
+        if (fin) {
+            if (!traced) {
+                if (P.world > 1) storeRGB(fb, slot, mk3(0.0f, 0.0f, 0.0f)); // padding pixels of edge tiles
+            } else if (!hit) {
+                if (level == 0) storeRGB(fb, outIdx, mk3(0.0f, 0.0f, 0.0f)); // trace(): miss -> black, main.cpp:288-294
+            } else {
+                if (level == 0) {
+                    path = newPath;
+                    B.pathPix[path] = outIdx;
+                }
+                V3 nn;
+                int mat;
+                if (R.sphere >= 0) {
+                    nn = R.sphereN;
+                    mat = R.tri >= 0 ? f2i(__ldg(S.triV1 + R.tri).w) : -1;
+                } else {
+                    const int i = R.tri;
+                    const float4 v0 = __ldg(S.triV0 + i), v1 = __ldg(S.triV1 + i), v2 = __ldg(S.triV2 + i);
+                    const float4 n0 = __ldg(S.triN0 + i), n1 = __ldg(S.triN1 + i), n2 = __ldg(S.triN2 + i);
+                    const float4 pl = __ldg(S.triPl + i);
+                    float al, be, ga;
+                    hitEpilogue(mk3(v0), mk3(v1), mk3(v2), mk3(n0), mk3(n1), mk3(n2), mk3(pl), T.o, T.d, R.t, al, be, ga, nn);
+                    mat = f2i(v1.w);
+                }
+                const V3 pointOn = T.o + T.d * R.t; // main.cpp:164
+                const int rec = path * B.levels + level;
+                float4* r = B.hitRec + 3 * (size_t)rec;
+                r[0] = make_float4(pointOn.x, pointOn.y, pointOn.z, i2f(mat));
+                r[1] = make_float4(nn.x, nn.y, nn.z, 0.0f);
+                r[2] = make_float4(T.d.x, T.d.y, T.d.z, 0.0f);
+                B.hitList[listPos] = rec;
+                B.pathDepth[path] = level + 1;
+                const float ksz = mat >= 0 ? __ldg(S.mats + 2 * mat + 1).z : 0.0f;
+                if (!(ksz <= 0.01f) && level + 1 < P.traceLimit) { // shade(): mirror test main.cpp:246, trace limit :267
+                    const V3 reflected = normalize3(reflect3(T.d, nn)); // ComputeReflectedRay, main.cpp:252-256
+                    nt = length3(T.d);
+                    const float epsilon = 0.001f;
+                    no = pointOn + epsilon * reflected;
+                    nd = reflected;
+                    level++;
+                    again = true;
+                }
+            }
+        }
+        const unsigned am = __ballot_sync(0xffffffffu, again);
+        if (am && (threadIdx.x & 31) == __ffs(am) - 1) atomicAdd(B.counts + CGRT_CNT_BOUNCES, __popc(am));
+        return again;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_paths(DevScene S, const FrameParams* __restrict__ Pp, PathBuffers B,
+                                               const int* __restrict__ tileList, float* __restrict__ fb, int* work)
+{
+    const FrameParams P = *Pp;
+    PathsPolicy pol{S, P, B, tileList, fb, -1, 0, -1};
+    persistentTraverse<false>(S, pol, P.nSlots, work);
+}
+
+struct ShadowAllPolicy {
+    const PathBuffers& B;
+    const float4* lights;
+    int nL;
+    int out; // per lane: index of the lit flag
+    RT_DEV bool load(int i, V3& o, V3& d, float& tIn, float& eps, float& maxDist)
+    { // pointInShadow, src/main.cpp:104-135
+        const int h = i / nL, l = i - h * nL;
+        const int rec = B.hitList[h];
+        out = rec * nL + l;
+        const V3 pointOn = mk3(B.hitRec[3 * (size_t)rec]);
+        const V3 lightPos = mk3(__ldg(lights + 2 * l));
+        const V3 fromPosToLight = lightPos - pointOn;
+        d = normalize3(fromPosToLight);
+        eps = 0.001f;
+        o = pointOn + eps * d;
+        tIn = FLT_MAX;
+        maxDist = length3(fromPosToLight);
+        return true;
+    }
+    RT_DEV bool retire(bool fin, int, bool, bool shadowed, const TraceResult&, const Trav&, V3&, V3&, float&)
+    {
+        if (fin) B.lit[out] = shadowed ? 0 : 1;
+        return false;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_shadow_all(DevScene S, const FrameParams* __restrict__ Pp,
+                                                    const float4* __restrict__ lights, PathBuffers B, int* work)
+{
+    const int nL = Pp->nLights;
+    ShadowAllPolicy pol{B, lights, nL, 0};
+    persistentTraverse<true>(S, pol, B.counts[CGRT_CNT_HITS] * nL, work);
+}
+
+// direct colour of one hit record: shading(), src/main.cpp:160-235 (point-light loop :220-232)
+RT_DEV V3 directColour(const DevScene& S, const float4* __restrict__ lights, int nL, const float4& a, const float4& b,
+                       const float4& c, const uint8_t* __restrict__ lit, V3& ks)
+{
+    const V3 P = mk3(a), N = mk3(b), D = mk3(c);
+    const int mat = f2i(a.w);
+    float4 m0 = make_float4(0.0f, 0.0f, 0.0f, 1.0f), m1 = make_float4(0.0f, 0.0f, 0.0f, 1.0f); // default HitInfo material
+    if (mat >= 0) { m0 = __ldg(S.mats + 2 * mat); m1 = __ldg(S.mats + 2 * mat + 1); }
+    const V3 kd = mk3(m0);
+    ks = mk3(m1);
+    const float shininess = m0.w;
+    V3 result = mk3(0.0f, 0.0f, 0.0f);
+    for (int l = 0; l < nL; l++) {
+        const V3 lightPos = mk3(__ldg(lights + 2 * l)), lightCol = mk3(__ldg(lights + 2 * l + 1));
+        const V3 fromPosToLight = normalize3(lightPos - P);
+        if (!lit[l]) continue;
+        V3 diffuse = mk3(0.0f, 0.0f, 0.0f), specular = diffuse;
+        const float diffuseCos = dot3(fromPosToLight, N); // diffuseOneLight, main.cpp:84-98
+        if (!(diffuseCos <= 0)) diffuse = (lightCol * kd) * diffuseCos;
+        const V3 reflected = normalize3(reflect3(D, N)); // specularOneLight, main.cpp:61-82
+        const float specularCos = dot3(reflected, fromPosToLight);
+        if (!(specularCos <= 0)) {
+            const float pw = (float)pow((double)specularCos, (double)shininess);
+            specular = (lightCol * ks) * pw;
+        }
+        result = result + diffuse;
+        result = result + specular;
+    }
+    return result;
+}
+
+// one thread per path: direct colour of every level, then the recursion unwound innermost first (main.cpp:241-264)
+__global__ void __launch_bounds__(128) k_shade_paths(DevScene S, const FrameParams* __restrict__ Pp,
+                                                     const float4* __restrict__ lights, PathBuffers B, float* __restrict__ fb)
+{
+    const int nL = Pp->nLights;
+    const int n = B.counts[CGRT_CNT_PATHS];
+    for (int path = blockIdx.x * blockDim.x + threadIdx.x; path < n; path += gridDim.x * blockDim.x) {
+        const int depth = B.pathDepth[path];
+        V3 direct[CGRT_MAX_LEVELS], ksv[CGRT_MAX_LEVELS];
+        for (int k = 0; k < depth; k++) {
+            const int rec = path * B.levels + k;
+            const float4* r = B.hitRec + 3 * (size_t)rec;
+            direct[k] = directColour(S, lights, nL, r[0], r[1], r[2], B.lit + (size_t)rec * nL, ksv[k]);
+        }
+        // deepest level: its reflection (if the surface is a mirror) is black - either the reflected ray missed or
+        // trace(level + 1) hit the recursion limit (main.cpp:267-272)
+        int k = depth - 1;
+        V3 colour = (ksv[k].z <= 0.01f) ? direct[k] : direct[k] + mk3(0.0f, 0.0f, 0.0f) * ksv[k];
+        for (k = depth - 2; k >= 0; k--) colour = direct[k] + colour * ksv[k];
+        storeRGB(fb, B.pathPix[path], colour);
+    }
 }
 
 // ---- shading + bounce emission: one thread per hit.  shading/shade, src/main.cpp:61-98, 220-264 ---------------------------
@@ -835,6 +1029,35 @@ int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams&
         traceEnd(tr, 3, st);
         launches++;
     }
+    return launches;
+}
+
+int launchPathPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
+                       const PathBuffers& B, const int* dTileList, float* fb, int numSMs, WaveTrace* tr, cudaStream_t st)
+{
+    cudaMemsetAsync(B.counts, 0, sizeof(int) * CGRT_CNT_TOTAL, st);
+    if (hP.traceLimit <= 0) { // trace(0, ...) returns black for every pixel without casting a ray, src/main.cpp:267-272
+        const size_t px = hP.world == 1 ? (size_t)hP.width * hP.height : (size_t)hP.nSlots;
+        cudaMemsetAsync(fb, 0, px * 3 * sizeof(float), st);
+        return 0;
+    }
+    int launches = 0;
+    const int persistent = numSMs * 8;
+    traceBegin(tr, 0, st);
+    k_paths<<<min(gridFor((size_t)hP.nSlots, 128, 1 << 30), persistent), 128, 0, st>>>(S, dP, B, dTileList, fb,
+                                                                                        B.counts + CGRT_CNT_WORK);
+    traceEnd(tr, 0, st);
+    launches++;
+    if (hP.nLights > 0) {
+        traceBegin(tr, 2, st);
+        k_shadow_all<<<persistent, 128, 0, st>>>(S, dP, dLights, B, B.counts + CGRT_CNT_WORK + 1);
+        traceEnd(tr, 2, st);
+        launches++;
+    }
+    traceBegin(tr, 3, st);
+    k_shade_paths<<<gridFor((size_t)hP.nSlots, 128, numSMs * 16), 128, 0, st>>>(S, dP, dLights, B, fb);
+    traceEnd(tr, 3, st);
+    launches++;
     return launches;
 }
 

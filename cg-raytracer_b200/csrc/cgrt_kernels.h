@@ -48,7 +48,10 @@ namespace cgrt {
 #define CGRT_CNT_HIT 0                          // counts[CGRT_CNT_HIT + level]    = hits found at `level`
 #define CGRT_CNT_BOUNCE CGRT_MAX_LEVELS         // counts[CGRT_CNT_BOUNCE + level] = rays queued for `level` (level >= 1)
 #define CGRT_CNT_WORK (2 * CGRT_MAX_LEVELS + 1)  // counts[CGRT_CNT_WORK + k] = work counter of the k-th persistent launch of the frame
-#define CGRT_CNT_TOTAL (CGRT_CNT_WORK + 2 * CGRT_MAX_LEVELS + 2)
+#define CGRT_CNT_PATHS (CGRT_CNT_WORK + 2 * CGRT_MAX_LEVELS + 2) // path pipeline: pixels whose primary ray hit (= paths)
+#define CGRT_CNT_HITS (CGRT_CNT_PATHS + 1)                      // path pipeline: hit records of all levels
+#define CGRT_CNT_BOUNCES (CGRT_CNT_PATHS + 2)                   // path pipeline: reflection rays traced
+#define CGRT_CNT_TOTAL (CGRT_CNT_PATHS + 3)
 #define CGRT_PARAM_BLOCK_HEADER 128             // bytes reserved for FrameParams in the per-frame block; lights follow
 
 // Per-frame constants, evaluated on the host with libm exactly as Trackball does (framework/src/trackball.cpp:70-73, 92-103)
@@ -77,6 +80,20 @@ struct WaveBuffers {
     size_t cap;
 };
 
+// Queues of the production pipeline (cgrt_kernels.cu "path pipeline"): one persistent closest-hit kernel follows every
+// path from its primary ray through its mirror bounces and leaves one hit record per (path, level); all shadow rays of the
+// frame are then traced by one any-hit launch and one shading launch folds each path back to its pixel.
+struct PathBuffers {
+    float4* hitRec;    // [path * levels + level] 3 x float4: [P | matId] [N | -] [D | -]
+    int* hitList;      // [i] = path * levels + level, compacted list of all hit records (shadow work items)
+    uint8_t* lit;      // [(path * levels + level) * nLights + light] 1 = light reaches the point
+    int* pathPix;      // [path] output index of the path's pixel
+    int* pathDepth;    // [path] number of levels that recorded a hit
+    int* counts;       // shared with WaveBuffers::counts
+    size_t cap;        // paths the buffers can hold (= local pixel slots)
+    int levels;        // trace limit the buffers are laid out for
+};
+
 // optional per-kernel event trace of one wavefront (classes: 0 primary, 1 bounce closest-hit, 2 shadow, 3 shade)
 struct WaveTrace {
     cudaEvent_t* ev;   // 2 * maxKernels events
@@ -103,6 +120,8 @@ void launchGenerateRays(const FrameParams* dP, int nPixels, float4* rays, cudaSt
 int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
                     const WaveBuffers& B, const int* dTileList, float* fb, int numSMs, bool countTests, WaveTrace* tr,
                     cudaStream_t st);
+int launchPathPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
+                       const PathBuffers& B, const int* dTileList, float* fb, int numSMs, WaveTrace* tr, cudaStream_t st);
 void launchAssemble(const float* gathered, size_t perRankFloats, const int* tileLists, const int* tileCounts, int maxTiles,
                     int world, int tileW, int tileH, int tilesX, int width, int height, float* frame, int numSMs,
                     cudaStream_t st);
