@@ -101,6 +101,7 @@ struct Trav {
     int hitTri;
     int sp, node, subBase;
     bool useSub, inLeaf;
+    bool fastRef; // reference-node box tests may go through the filtered (division-free) path for this ray
     LeafBest best;
 };
 // the traversal stack lives outside the struct so that the scalars above stay in registers
@@ -141,7 +142,79 @@ RT_DEV bool travBegin(const DevScene& S, Trav& T, const V3& o, const V3& d, floa
     T.inv.x = ax == 0.0f ? 1e30f : 1.0f / d.x;
     T.inv.y = ay == 0.0f ? 1e30f : 1.0f / d.y;
     T.inv.z = az == 0.0f ? 1e30f : 1.0f / d.z;
+    // filtered reference box tests need finite non-zero reciprocals and no overflow in (box - o) * inv
+    T.fastRef = ax >= 1e-15f && ax <= 1e15f && ay >= 1e-15f && ay <= 1e15f && az >= 1e-15f && az <= 1e15f &&
+                fabsf(o.x) <= 1e15f && fabsf(o.y) <= 1e15f && fabsf(o.z) <= 1e15f;
     return true;
+}
+
+// ---- filtered evaluation of the reference's exact box test ----------------------------------------------------------------
+// slabTest (src/ray_tracing.cpp:162-200) needs six IEEE divisions; almost every call is decided with a wide margin, and its
+// numeric result matters only when two children have to be ordered or a pending sibling is pruned. The filter evaluates the
+// slab distances as (box - o) * fl(1/d): each such value differs from the reference's correctly rounded quotient by at most
+// 3 ulp, so with rho = 1e-6 relative (+ tau absolute, for the subnormal range) slack every comparison of the reference is
+// either decided with certainty or declared ambiguous; ambiguous cases fall back to slabTest itself. Outcomes are therefore
+// exactly the reference's, the divisions are just not executed when they cannot matter.
+// Measured on B200 (profiles/r01_tuning.md): the filter removes ~25 % of the executed instructions of a reference-node step
+// but does not shorten the frame (the kernels are bound by divergence / instruction fetch, not by the division pipe), so it
+// is compiled out by default; -DCGRT_USE_FILTER=1 enables it (the parity suite passes either way).
+#ifndef CGRT_USE_FILTER
+#define CGRT_USE_FILTER 0
+#endif
+#define CGRT_RHO 1e-6f
+#define CGRT_TAU 1e-30f
+RT_DEV float errBound(float x) { return fabsf(x) * CGRT_RHO + CGRT_TAU; }
+
+// the exact test, kept out of line: it is the rare fallback of the filter and would otherwise be inlined six times
+CGRT_RARE bool slabTestOutOfLine(const float4& lo, const float4& hi, const V3& o, const V3& d, float rayT, float& tHit)
+{
+    return slabTest(mk3(lo), mk3(hi), o, d, rayT, tHit);
+}
+
+// hit: the reference's boolean; t: its distance (exact when `exact`, otherwise within errBound(t) of it)
+RT_DEV void boxFiltered(const float4& lo, const float4& hi, const V3& o, const V3& d, const V3& inv, bool fast, float rayT,
+                        bool& hit, float& t, bool& exact)
+{
+    if (CGRT_USE_FILTER && fast) {
+        const float q0x = (lo.x - o.x) * inv.x, q1x = (hi.x - o.x) * inv.x;
+        const float q0y = (lo.y - o.y) * inv.y, q1y = (hi.y - o.y) * inv.y;
+        const float q0z = (lo.z - o.z) * inv.z, q1z = (hi.z - o.z) * inv.z;
+        const float tin = fmaxf(fmaxf(fminf(q0x, q1x), fminf(q0y, q1y)), fminf(q0z, q1z));
+        const float tout = fminf(fminf(fmaxf(q0x, q1x), fmaxf(q0y, q1y)), fmaxf(q0z, q1z));
+        const float ein = errBound(tin), eout = errBound(tout);
+        if (tout + eout < 0.0f || tin - ein > tout + eout) { // certainly `tOut < 0` or `tIn > tOut`
+            hit = false;
+            return;
+        }
+        float cur, ecur;
+        bool branch = false;
+        if (tin + ein < 0.0f) { cur = tout; ecur = eout; branch = true; }        // certainly tIn < 0: inside the slabs
+        else if (tin - ein >= 0.0f) { cur = tin; ecur = ein; branch = true; }   // certainly tIn >= 0
+        if (branch) {
+            if (cur - ecur >= rayT) { // certainly `currentT >= ray.t`
+                hit = false;
+                return;
+            }
+            if (tin + ein <= tout - eout && tout - eout >= 0.0f && cur + ecur < rayT) { // certainly a hit
+                hit = true;
+                t = cur;
+                exact = false;
+                return;
+            }
+        }
+    }
+    float te = 0.0f;
+    hit = slabTestOutOfLine(lo, hi, o, d, rayT, te);
+    t = te;
+    exact = true;
+}
+
+// the reference's distance of a box that is known to be hit (used when an approximate distance is not decisive)
+CGRT_RARE float boxExactT(const float4& lo, const float4& hi, const V3& o, const V3& d)
+{
+    float te = 0.0f;
+    slabTest(mk3(lo), mk3(hi), o, d, __int_as_float(0x7f800000), te);
+    return te;
 }
 
 // Node classes of the state machine. The current node id encodes its class: reference nodes are plain indices into
@@ -149,6 +222,7 @@ RT_DEV bool travBegin(const DevScene& S, Trav& T, const V3& o, const V3& d, floa
 // leaf and carries its triangle range directly (bit 28 = count-1, bits 0..27 = first position), so a sub-tree leaf costs
 // no node fetch.
 #define CGRT_LEAFFLAG 0x20000000
+#define CGRT_KEYAPPROX 0x10000000 // reference stack entry whose key is a filtered (approximate) box distance
 #define CGRT_LEAFCNT_SHIFT 28
 #define CGRT_POS_MASK 0x0fffffff
 enum { CLS_REF = 0, CLS_SUBINNER = 1, CLS_SUBLEAF = 2, CLS_NONE = 3 };
@@ -164,7 +238,7 @@ RT_DEV int subChildId(int index, const float4& lo, const float4& hi)
 }
 
 // pop: next pending node that is not pruned, committing the reference leaf when its sub-tree entries are gone
-RT_DEV int travPop(Trav& T, TravStack& K)
+RT_DEV int travPop(const DevScene& S, Trav& T, TravStack& K)
 {
     const float slack = 1.000001f;
     while (true) {
@@ -178,10 +252,22 @@ RT_DEV int travPop(Trav& T, TravStack& K)
         const float key = K.t[T.sp];
         if (n & CGRT_SUBFLAG) {
             if (key > T.best.t * slack) continue;
+            T.node = n;
+            return TRAV_CONTINUE;
+        }
+        // reference sibling: skipped iff ray.t < tSecond (intersectChildrenHierarchically, bvh.cpp:572-595)
+        const int ni = n & ~CGRT_KEYAPPROX;
+        if (n & CGRT_KEYAPPROX) {
+            const float e = errBound(key);
+            if (T.t < key - e) continue;
+            if (!(T.t >= key + e)) { // not decisive: compare with the reference's exact distance of that box
+                const float tS = boxExactT(__ldg(S.nodes + 2 * ni), __ldg(S.nodes + 2 * ni + 1), T.o, T.d);
+                if (T.t < tS) continue;
+            }
         } else {
             if (T.t < key) continue;
         }
-        T.node = n;
+        T.node = ni;
         return TRAV_CONTINUE;
     }
 }
@@ -205,47 +291,56 @@ RT_DEV int travStepRef(const DevScene& S, Trav& T, TravStack& K, float eps, floa
             return TRAV_CONTINUE;
         }
         const uint32_t end = a + b;
+#pragma unroll 1
         for (uint32_t i = a; i < end; i++) {
             if (leafCandidate(S, (int)i, o, d, T.best)) {
                 if (ANY && !(T.best.t + eps >= maxDist)) return TRAV_FIRED;
             }
         }
         if (T.best.pos >= 0) { T.t = T.best.t; T.hitTri = T.best.pos; }
-        return travPop(T, K);
+        return travPop(S, T, K);
     }
     // ---- reference inner node: intersectNonLeaf + intersectDeeper, exact arithmetic
     const int L = (int)a, Rn = (int)a + 1;
     const float4 l0 = __ldg(S.nodes + 2 * L), l1 = __ldg(S.nodes + 2 * L + 1);
     const float4 r0 = __ldg(S.nodes + 2 * L + 2), r1 = __ldg(S.nodes + 2 * L + 3);
-    float tL = -1.0f, tR = -1.0f, tmp;
-    if (slabTest(mk3(l0), mk3(l1), o, d, T.t, tmp)) tL = tmp;
-    if (slabTest(mk3(r0), mk3(r1), o, d, T.t, tmp)) tR = tmp;
+    bool hL, hR, exL = true, exR = true;
+    float tL = -1.0f, tR = -1.0f;
+    boxFiltered(l0, l1, o, d, T.inv, T.fastRef, T.t, hL, tL, exL);
+    boxFiltered(r0, r1, o, d, T.inv, T.fastRef, T.t, hR, tR, exR);
     const bool inL = startsInBox(o, mk3(l0), mk3(l1));
     const bool inR = startsInBox(o, mk3(r0), mk3(r1));
     int first = -1, second = -1;
     float tS = -1.0f;
+    bool keyApprox = false;
     if (inL && inR) { // both visited unconditionally, left operand of `|` first (g++ order)
         first = L; second = Rn; tS = -1.0f;
     } else if (inL) {
         first = L;
-        if (!(tR < 0)) { second = Rn; tS = tR; }
+        if (hR) { second = Rn; tS = tR; keyApprox = !exR; }
     } else if (inR) {
         first = Rn;
-        if (!(tL < 0)) { second = L; tS = tL; }
-    } else {
-        if (tL < 0 && tR < 0) {
-        } else if (tL < 0) {
-            first = Rn;
-        } else if (tR < 0) {
-            first = L;
-        } else if (tL < tR) {
-            first = L; second = Rn; tS = tR;
-        } else {
-            first = Rn; second = L; tS = tL;
+        if (hL) { second = L; tS = tL; keyApprox = !exL; }
+    } else if (hL && hR) {
+        // nearer child first: `tLeft < tRight` (bvh.cpp:626); decide from the approximate distances when they are
+        // separated by more than their error bounds, otherwise from the exact ones
+        bool leftFirst;
+        if (tL + errBound(tL) < tR - errBound(tR) && !(exL && exR)) leftFirst = true;
+        else if (tL - errBound(tL) >= tR + errBound(tR) && !(exL && exR)) leftFirst = false;
+        else {
+            if (!exL) { tL = boxExactT(l0, l1, o, d); exL = true; }
+            if (!exR) { tR = boxExactT(r0, r1, o, d); exR = true; }
+            leftFirst = tL < tR;
         }
+        if (leftFirst) { first = L; second = Rn; tS = tR; keyApprox = !exR; }
+        else { first = Rn; second = L; tS = tL; keyApprox = !exL; }
+    } else if (hL) {
+        first = L;
+    } else if (hR) {
+        first = Rn;
     }
     if (second >= 0) {
-        K.n[T.sp] = second;
+        K.n[T.sp] = keyApprox ? (second | CGRT_KEYAPPROX) : second;
         K.t[T.sp] = tS;
         T.sp++;
     }
@@ -253,7 +348,7 @@ RT_DEV int travStepRef(const DevScene& S, Trav& T, TravStack& K, float eps, floa
         T.node = first;
         return TRAV_CONTINUE;
     }
-    return travPop(T, K);
+    return travPop(S, T, K);
 }
 
 // one step on a sub-tree inner node: tolerant slab tests, nearer child first
@@ -279,7 +374,7 @@ RT_DEV int travStepSubInner(const DevScene& S, Trav& T, TravStack& K)
         T.node = hL ? idL : idR;
         return TRAV_CONTINUE;
     }
-    return travPop(T, K);
+    return travPop(S, T, K);
 }
 
 // one step on a sub-tree leaf: exact tests of the few triangles that survived the culling
@@ -288,12 +383,13 @@ RT_DEV int travStepSubLeaf(const DevScene& S, Trav& T, TravStack& K, float eps, 
 {
     const int first = T.node & CGRT_POS_MASK;
     const int count = ((T.node >> CGRT_LEAFCNT_SHIFT) & 1) + 1;
+#pragma unroll 1
     for (int i = first; i < first + count; i++) {
         if (leafCandidate(S, i, T.o, T.d, T.best)) {
             if (ANY && !(T.best.t + eps >= maxDist)) return TRAV_FIRED;
         }
     }
-    return travPop(T, K);
+    return travPop(S, T, K);
 }
 
 template <bool ANY>

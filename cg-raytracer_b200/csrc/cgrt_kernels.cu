@@ -4,6 +4,8 @@
 #include "cgrt_device.cuh"
 
 #include <float.h>
+#include <stdlib.h>
+#include <string>
 
 namespace cgrt {
 
@@ -398,16 +400,65 @@ __global__ void __launch_bounds__(128) k_shadow(DevScene S, const FrameParams* _
 //     bool retire(bool fin, int idx, bool traced, bool result, const TraceResult& R, const Trav& T, V3& o, V3& d, float& tIn)
 //          called by ALL lanes; returns true when the lane continues with a follow-up ray (o, d, tIn) of the same item
 // =================================================================================================================
-#define CGRT_STEPS_PER_ROUND 6
-#define CGRT_REFILL_MIN_IDLE 6
+// Scheduling knobs of the persistent warps (environment CGRT_TUNE="steps=6,idle=6,vote=1,wref=4,wsub=16,wleaf=8,blocks=8"
+// overrides the defaults at library load; they change speed only, never results).
 // vote weights ~ 1 / (instructions of one step of the class): exact reference node ~260, tolerant sub-tree node ~60,
 // sub-tree leaf (<= 2 exact triangle tests) ~120
+#ifndef CGRT_STEPS_PER_ROUND
+#define CGRT_STEPS_PER_ROUND 12
+#endif
+#ifndef CGRT_VOTE
+#define CGRT_VOTE 1
+#endif
+#ifndef CGRT_MINBLOCKS
+#define CGRT_MINBLOCKS 8 // 8 CTAs x 4 warps per SM: caps the traversal kernels at 64 registers
+#endif
+#define CGRT_REFILL_MIN_IDLE 6
 #define CGRT_W_REF 4
 #define CGRT_W_SUBINNER 16
 #define CGRT_W_SUBLEAF 8
+struct Tuning {
+    int steps = 12;  // traversal steps between two refill / retire rounds
+    int idle = 6;    // refill as soon as this many lanes of the warp are idle
+    int vote = 1;    // 1: each step runs the node class picked by the warp vote; 0: every lane steps every iteration
+    int wref = 4, wsub = 16, wleaf = 8;
+    int blocks = 8;  // persistent CTAs (128 threads) per SM
+};
+static Tuning g_tune;
+static bool g_tuneLoaded = false;
+static const Tuning& tuning()
+{
+    if (!g_tuneLoaded) {
+        g_tuneLoaded = true;
+        const char* e = getenv("CGRT_TUNE");
+        if (e) {
+            std::string s(e);
+            size_t pos = 0;
+            while (pos < s.size()) {
+                size_t c = s.find(',', pos);
+                if (c == std::string::npos) c = s.size();
+                const std::string kv = s.substr(pos, c - pos);
+                const size_t eq = kv.find('=');
+                if (eq != std::string::npos) {
+                    const std::string key = kv.substr(0, eq);
+                    const int v = atoi(kv.c_str() + eq + 1);
+                    if (key == "steps") g_tune.steps = v;
+                    else if (key == "idle") g_tune.idle = v;
+                    else if (key == "vote") g_tune.vote = v;
+                    else if (key == "wref") g_tune.wref = v;
+                    else if (key == "wsub") g_tune.wsub = v;
+                    else if (key == "wleaf") g_tune.wleaf = v;
+                    else if (key == "blocks") g_tune.blocks = v;
+                }
+                pos = c + 1;
+            }
+        }
+    }
+    return g_tune;
+}
 
 template <bool ANY, class Policy>
-RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCounter)
+RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCounter, const Tuning& U)
 {
     Trav T;
     TravStack K;
@@ -452,6 +503,11 @@ RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCou
 #pragma unroll 1
         for (int it = 0; it < CGRT_STEPS_PER_ROUND; it++) {
             const bool run = idx >= 0 && state == TRAV_CONTINUE;
+#if !CGRT_VOTE
+            if (__ballot_sync(0xffffffffu, run) == 0u) break;
+            if (run) state = travStep<ANY>(S, T, K, eps, maxDist);
+            continue;
+#endif
             const int cls = run ? travClass(T.node) : CLS_NONE;
             const int s0 = __popc(__ballot_sync(0xffffffffu, cls == CLS_REF)) * CGRT_W_REF;
             const int s1 = __popc(__ballot_sync(0xffffffffu, cls == CLS_SUBINNER)) * CGRT_W_SUBINNER;
@@ -572,25 +628,25 @@ struct ShadowPolicy {
 };
 
 __global__ void __launch_bounds__(128) k_primary_p(DevScene S, const FrameParams* __restrict__ Pp, WaveBuffers B,
-                                                   const int* __restrict__ tileList, float* __restrict__ fb, int* work)
+                                                   const int* __restrict__ tileList, float* __restrict__ fb, int* work, Tuning U)
 {
     const FrameParams P = *Pp;
     PrimaryPolicy pol{S, P, B, tileList, fb, -1};
-    persistentTraverse<false>(S, pol, P.nSlots, work);
+    persistentTraverse<false>(S, pol, P.nSlots, work, U);
 }
 
-__global__ void __launch_bounds__(128) k_bounce_closest_p(DevScene S, WaveBuffers B, int level, float* __restrict__ fb, int* work)
+__global__ void __launch_bounds__(128) k_bounce_closest_p(DevScene S, WaveBuffers B, int level, float* __restrict__ fb, int* work, Tuning U)
 {
     BouncePolicy pol{S, B, fb, level, -1, 0};
-    persistentTraverse<false>(S, pol, B.counts[CGRT_CNT_BOUNCE + level], work);
+    persistentTraverse<false>(S, pol, B.counts[CGRT_CNT_BOUNCE + level], work, U);
 }
 
 __global__ void __launch_bounds__(128) k_shadow_p(DevScene S, const FrameParams* __restrict__ Pp,
-                                                  const float4* __restrict__ lights, WaveBuffers B, int level, int* work)
+                                                  const float4* __restrict__ lights, WaveBuffers B, int level, int* work, Tuning U)
 {
     const int nL = Pp->nLights;
     ShadowPolicy pol{B, lights, nL};
-    persistentTraverse<true>(S, pol, B.counts[CGRT_CNT_HIT + level] * nL, work);
+    persistentTraverse<true>(S, pol, B.counts[CGRT_CNT_HIT + level] * nL, work, U);
 }
 
 // =================================================================================================================
@@ -679,12 +735,12 @@ struct PathsPolicy {
     }
 };
 
-__global__ void __launch_bounds__(128) k_paths(DevScene S, const FrameParams* __restrict__ Pp, PathBuffers B,
-                                               const int* __restrict__ tileList, float* __restrict__ fb, int* work)
+__global__ void __launch_bounds__(128, CGRT_MINBLOCKS) k_paths(DevScene S, const FrameParams* __restrict__ Pp, PathBuffers B,
+                                               const int* __restrict__ tileList, float* __restrict__ fb, int* work, Tuning U)
 {
     const FrameParams P = *Pp;
     PathsPolicy pol{S, P, B, tileList, fb, -1, 0, -1};
-    persistentTraverse<false>(S, pol, P.nSlots, work);
+    persistentTraverse<false>(S, pol, P.nSlots, work, U);
 }
 
 struct ShadowAllPolicy {
@@ -714,12 +770,12 @@ struct ShadowAllPolicy {
     }
 };
 
-__global__ void __launch_bounds__(128) k_shadow_all(DevScene S, const FrameParams* __restrict__ Pp,
-                                                    const float4* __restrict__ lights, PathBuffers B, int* work)
+__global__ void __launch_bounds__(128, CGRT_MINBLOCKS) k_shadow_all(DevScene S, const FrameParams* __restrict__ Pp,
+                                                    const float4* __restrict__ lights, PathBuffers B, int* work, Tuning U)
 {
     const int nL = Pp->nLights;
     ShadowAllPolicy pol{B, lights, nL, 0};
-    persistentTraverse<true>(S, pol, B.counts[CGRT_CNT_HITS] * nL, work);
+    persistentTraverse<true>(S, pol, B.counts[CGRT_CNT_HITS] * nL, work, U);
 }
 
 // direct colour of one hit record: shading(), src/main.cpp:160-235 (point-light loop :220-232)
@@ -1004,7 +1060,7 @@ int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams&
     traceBegin(tr, 0, st);
     int workSlot = CGRT_CNT_WORK;
     if (countTests) k_primary<true><<<gPrimary, 128, 0, st>>>(S, dP, B, dTileList, fb);
-    else k_primary_p<<<min(gPrimary, persistent), 128, 0, st>>>(S, dP, B, dTileList, fb, B.counts + workSlot++);
+    else k_primary_p<<<min(gPrimary, persistent), 128, 0, st>>>(S, dP, B, dTileList, fb, B.counts + workSlot++, tuning());
     traceEnd(tr, 0, st);
     launches++;
     const int gHit = gridFor((size_t)hP.nSlots, 128, persistent);
@@ -1013,14 +1069,14 @@ int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams&
         if (level > 0) {
             traceBegin(tr, 1, st);
             if (countTests) k_bounce_closest<true><<<gHit, 128, 0, st>>>(S, B, level, fb);
-            else k_bounce_closest_p<<<gHit, 128, 0, st>>>(S, B, level, fb, B.counts + workSlot++);
+            else k_bounce_closest_p<<<gHit, 128, 0, st>>>(S, B, level, fb, B.counts + workSlot++, tuning());
             traceEnd(tr, 1, st);
             launches++;
         }
         if (hP.nLights > 0) {
             traceBegin(tr, 2, st);
             if (countTests) k_shadow<true><<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level);
-            else k_shadow_p<<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level, B.counts + workSlot++);
+            else k_shadow_p<<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level, B.counts + workSlot++, tuning());
             traceEnd(tr, 2, st);
             launches++;
         }
@@ -1042,15 +1098,15 @@ int launchPathPipeline(const DevScene& S, const FrameParams* dP, const FramePara
         return 0;
     }
     int launches = 0;
-    const int persistent = numSMs * 8;
+    const int persistent = numSMs * tuning().blocks;
     traceBegin(tr, 0, st);
     k_paths<<<min(gridFor((size_t)hP.nSlots, 128, 1 << 30), persistent), 128, 0, st>>>(S, dP, B, dTileList, fb,
-                                                                                        B.counts + CGRT_CNT_WORK);
+                                                                                        B.counts + CGRT_CNT_WORK, tuning());
     traceEnd(tr, 0, st);
     launches++;
     if (hP.nLights > 0) {
         traceBegin(tr, 2, st);
-        k_shadow_all<<<persistent, 128, 0, st>>>(S, dP, dLights, B, B.counts + CGRT_CNT_WORK + 1);
+        k_shadow_all<<<persistent, 128, 0, st>>>(S, dP, dLights, B, B.counts + CGRT_CNT_WORK + 1, tuning());
         traceEnd(tr, 2, st);
         launches++;
     }
