@@ -232,6 +232,8 @@ def main():
     cls_rays = [st_count["primary"], st_count["bounce"], st_count["shadow"]]
     alg_bytes_class = [B_RAY * cls_rays[c] + B_BOX * st_count["box_tests"][c] + B_TRI * st_count["tri_tests"][c] for c in range(3)]
     alg_bytes_frame_local = sum(alg_bytes_class)
+    if st_prof["class_launches"][1] == 0:  # path pipeline: k_paths traces the primary AND the bounce rays
+        alg_bytes_class = [alg_bytes_class[0] + alg_bytes_class[1], 0, alg_bytes_class[2]]
     tot = torch.tensor([rays_local, st_count["primary"], st_count["shadow"], st_count["bounce"], alg_bytes_frame_local],
                        dtype=torch.float64, device=dev)
     if world > 1:

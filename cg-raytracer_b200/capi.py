@@ -172,7 +172,8 @@ def make_camera(W, H, fovy_deg=50.0, dist=3.0, look_at=(0.0, 0.0, 0.0), euler_de
 
 
 K_PRIMARY, K_BOUNCE, K_SHADOW, K_SHADE = 0, 1, 2, 3
-KERNEL_CLASS_NAMES = ["k_primary", "k_bounce_closest", "k_shadow", "k_shade"]
+# production (path pipeline) kernels per class; class 1 is only launched by the level-by-level counting pipeline
+KERNEL_CLASS_NAMES = ["k_paths", "k_bounce_closest", "k_shadow_all", "k_shade_paths"]
 RENDER_PROFILE_ALL, RENDER_COUNT = 0xF, 0x100
 
 

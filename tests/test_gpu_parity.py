@@ -328,3 +328,35 @@ def test_c4_soup_properties(capi, oracle, gpu):
     sample = np.random.default_rng(1).choice(len(rays), 20000, replace=False)
     g = b.intersect(rays[sample])
     assert hits_equal(h[sample], g, flat.canonical_ids())
+
+
+# ---- the reference-named C++ interface (host/cgrt_host.h) driven the way the reference's main() drives it -----------------------
+def test_cpp_host_mirror_cli(capi, oracle, gpu, tmp_path):
+    import os
+    import struct
+    import subprocess
+    from conftest import ROOT
+    cli = os.path.join(ROOT, "cg-raytracer_b200", "cgrt_cli")
+    assert os.path.exists(cli), "build() must have produced the headless C++ harness"
+    out = tmp_path / "render.bmp"
+    W, H, L = 160, 90, 3
+    # no data directory on the GPU box: the Dragon preset falls back to the named stand-in
+    r = subprocess.run([cli, str(tmp_path), "Dragon", str(W), str(H), str(L), str(out), "80", "45"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Time to render image" in r.stdout and "levels=12" in r.stdout
+    d = capi.dragon_standin()
+    flat = ob.FlatScene(d.vcount, d.tcount, d.vertices, d.triangles, d.materials, d.spheres)
+    ref, cnt = oracle.scene(flat, d.lights).bvh().render(ob.default_camera(W, H), W, H, trace_limit=L)
+    assert f"primary={cnt['primary']} primary_hit={cnt['primary_hit']} shadow={cnt['shadow']} bounce={cnt['bounce']}" in r.stdout
+    raw = open(out, "rb").read()
+    off, = struct.unpack_from("<I", raw, 10)
+    px = np.frombuffer(raw, np.uint8, offset=off).reshape(H, W, 4)[::-1][..., [2, 1, 0]].astype(np.int32)
+    want = (np.clip(ref, 0, 1) * np.float32(255)).astype(np.int32)
+    assert np.abs(px - want).max() <= 1  # 1/255
+    # the debug ray ("R" key, main.cpp:747-753) through BoundingVolumeHierarchy::intersect(Ray&, HitInfo&)
+    rays = oracle.generate_rays(ob.default_camera(W, H), W, H)
+    g = oracle.scene(flat, d.lights).bvh().intersect(rays[45 * W + 80: 45 * W + 81])[0]
+    line = [l for l in r.stdout.splitlines() if l.startswith("debug ray")][0]
+    assert f"hit={int(g['tri'] >= 0)}" in line
+    if g["tri"] >= 0:
+        assert f"t={g['t']:.9g}" in line
