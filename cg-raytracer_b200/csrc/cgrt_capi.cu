@@ -16,6 +16,9 @@
 #include <vector>
 
 using namespace cgrt;
+#ifdef CGRT_INSTRUMENT
+namespace cgrt { void readInstrumentation(unsigned long long* out, bool reset); }
+#endif
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg)
@@ -1053,6 +1056,10 @@ int cgrt_quantize_rgba8(int device, const float* d_frame, size_t n_pixels, uint8
     CK(cudaGetLastError());
     return CGRT_OK;
 }
+
+#ifdef CGRT_INSTRUMENT
+void cgrt_debug_instrumentation(unsigned long long* out, int reset) { cgrt::readInstrumentation(out, reset != 0); }
+#endif
 
 // ---- memory helpers ------------------------------------------------------------------------------------------------
 int cgrt_device_malloc(int device, size_t bytes, void** out)

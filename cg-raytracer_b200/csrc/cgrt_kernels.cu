@@ -414,9 +414,11 @@ __global__ void __launch_bounds__(128) k_shadow(DevScene S, const FrameParams* _
 #define CGRT_MINBLOCKS 8 // 8 CTAs x 4 warps per SM: caps the traversal kernels at 64 registers
 #endif
 #define CGRT_REFILL_MIN_IDLE 6
+#ifndef CGRT_W_REF
 #define CGRT_W_REF 4
 #define CGRT_W_SUBINNER 16
 #define CGRT_W_SUBLEAF 8
+#endif
 struct Tuning {
     int steps = 12;  // traversal steps between two refill / retire rounds
     int idle = 6;    // refill as soon as this many lanes of the warp are idle
@@ -457,6 +459,17 @@ static const Tuning& tuning()
     return g_tune;
 }
 
+#ifdef CGRT_INSTRUMENT
+// [0] iterations, [1] lanes running summed over iterations, [2..4] iterations that chose class k, [5..7] lanes stepped in
+// class k, [8] refill rounds, [9] lanes refilled, [10] retire rounds, [11] lanes retired, [12] cycles in steps,
+// [13] cycles in refill, [14] cycles in retire, [15] warps
+__device__ unsigned long long g_instr[16];
+// the value is evaluated by ALL lanes (it may contain warp collectives); lane 0 adds it
+#define INSTR_ADD(i, v) do { const unsigned long long v_ = (unsigned long long)(v); if ((threadIdx.x & 31) == 0) atomicAdd(&g_instr[i], v_); } while (0)
+#else
+#define INSTR_ADD(i, v) do { } while (0)
+#endif
+
 template <bool ANY, class Policy>
 RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCounter, const Tuning& U)
 {
@@ -469,11 +482,15 @@ RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCou
     bool exhausted = false;     // warp-uniform: the work counter has run past n
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
+    INSTR_ADD(15, 1);
     while (true) {
         // ---- refill
         const unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
         const int nIdle = __popc(idle);
         if (!exhausted && (nIdle >= CGRT_REFILL_MIN_IDLE || idle == 0xffffffffu)) {
+#ifdef CGRT_INSTRUMENT
+            const long long c0 = clock64();
+#endif
             const int leader = __ffs(idle) - 1;
             int base = 0;
             if (lane == leader) base = atomicAdd(workCounter, nIdle);
@@ -491,6 +508,37 @@ RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCou
                     }
                 }
             }
+#ifdef CGRT_INSTRUMENT
+            INSTR_ADD(8, 1); INSTR_ADD(9, nIdle); INSTR_ADD(13, clock64() - c0);
+#endif
+        }
+        // ---- retire finished lanes (collective) BEFORE stepping: fresh rays that miss the root box (most primary rays) are
+        // retired and replaced right away, in converged refill rounds, until the warp holds enough live rays
+        {
+            const bool fin = idx >= 0 && state != TRAV_CONTINUE;
+            if (__ballot_sync(0xffffffffu, fin) != 0u) {
+#ifdef CGRT_INSTRUMENT
+                const long long c0 = clock64();
+                INSTR_ADD(10, 1); INSTR_ADD(11, __popc(__ballot_sync(0xffffffffu, fin)));
+#endif
+                TraceResult R;
+                R.sphere = -1; R.tri = -1; R.t = tIn;
+                bool result = false;
+                if (fin && traced) result = travFinish<ANY>(S, T, state, eps, maxDist, R);
+                V3 no, nd;
+                const bool again = P.retire(fin, idx, traced, result, R, T, no, nd, tIn);
+                if (fin) {
+                    if (again) {
+                        state = travBegin(S, T, no, nd, tIn) ? TRAV_CONTINUE : TRAV_DONE;
+                    } else {
+                        idx = -1;
+                    }
+                }
+#ifdef CGRT_INSTRUMENT
+                INSTR_ADD(14, clock64() - c0);
+#endif
+                continue;
+            }
         }
         if (__ballot_sync(0xffffffffu, idx >= 0) == 0u) {
             if (exhausted) break;
@@ -500,9 +548,15 @@ RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCou
         // Each iteration executes ONE node class, chosen by a warp vote that maximises lanes-advanced per instruction
         // (weights ~ 1 / cost of the class's step); lanes waiting in another class keep their state. This trades a little
         // latency for not paying all three code paths on every iteration.
+#ifdef CGRT_INSTRUMENT
+        const long long cs0 = clock64();
+#endif
 #pragma unroll 1
         for (int it = 0; it < CGRT_STEPS_PER_ROUND; it++) {
             const bool run = idx >= 0 && state == TRAV_CONTINUE;
+#ifdef CGRT_INSTRUMENT
+            INSTR_ADD(0, 1); INSTR_ADD(1, __popc(__ballot_sync(0xffffffffu, run)));
+#endif
 #if !CGRT_VOTE
             if (__ballot_sync(0xffffffffu, run) == 0u) break;
             if (run) state = travStep<ANY>(S, T, K, eps, maxDist);
@@ -514,28 +568,19 @@ RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCou
             const int s2 = __popc(__ballot_sync(0xffffffffu, cls == CLS_SUBLEAF)) * CGRT_W_SUBLEAF;
             if ((s0 | s1 | s2) == 0) break;
             if (s0 >= s1 && s0 >= s2) {
+                INSTR_ADD(2, 1); INSTR_ADD(5, s0 / CGRT_W_REF);
                 if (cls == CLS_REF) state = travStepRef<ANY>(S, T, K, eps, maxDist);
             } else if (s1 >= s2) {
+                INSTR_ADD(3, 1); INSTR_ADD(6, s1 / CGRT_W_SUBINNER);
                 if (cls == CLS_SUBINNER) state = travStepSubInner(S, T, K);
             } else {
+                INSTR_ADD(4, 1); INSTR_ADD(7, s2 / CGRT_W_SUBLEAF);
                 if (cls == CLS_SUBLEAF) state = travStepSubLeaf<ANY>(S, T, K, eps, maxDist);
             }
         }
-        // ---- retire finished lanes (collective)
-        const bool fin = idx >= 0 && state != TRAV_CONTINUE;
-        TraceResult R;
-        R.sphere = -1; R.tri = -1; R.t = tIn;
-        bool result = false;
-        if (fin && traced) result = travFinish<ANY>(S, T, state, eps, maxDist, R);
-        V3 no, nd;
-        const bool again = P.retire(fin, idx, traced, result, R, T, no, nd, tIn);
-        if (fin) {
-            if (again) {
-                state = travBegin(S, T, no, nd, tIn) ? TRAV_CONTINUE : TRAV_DONE;
-            } else {
-                idx = -1;
-            }
-        }
+#ifdef CGRT_INSTRUMENT
+        INSTR_ADD(12, clock64() - cs0);
+#endif
     }
 }
 
@@ -1126,6 +1171,17 @@ void launchAssemble(const float* gathered, size_t perRankFloats, const int* tile
     k_assemble<<<gridFor(total, 256, numSMs * 8), 256, 0, st>>>(gathered, perRankFloats, tileLists, tileCounts, maxTiles,
                                                                world, tileW, tileH, tilesX, width, height, frame);
 }
+
+#ifdef CGRT_INSTRUMENT
+void readInstrumentation(unsigned long long* out, bool reset)
+{
+    cudaMemcpyFromSymbol(out, g_instr, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_instr, z, sizeof z);
+    }
+}
+#endif
 
 void launchQuantize(const float* frame, size_t nPixels, uint8_t* rgba, cudaStream_t st)
 {

@@ -1,0 +1,25 @@
+"""Debug: per-kernel scheduling counters of the persistent warps (library built with -DCGRT_INSTRUMENT)."""
+import os, sys, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import __graft_entry__ as ge
+capi = ge.load_package().capi
+lib = capi.load_library()
+d = capi.dragon_standin()
+s = capi.Scene(d, lights=d.lights)
+W, H, L = 1920, 1080, 5
+cam = capi.make_camera(W, H)
+s.render(cam, W, H, trace_limit=L)
+out = (C.c_ulonglong * 16)()
+lib.cgrt_debug_instrumentation(out, 1)
+_, st = s.render(cam, W, H, trace_limit=L)
+lib.cgrt_debug_instrumentation(out, 1)
+v = [int(x) for x in out]
+print("stats", st)
+print("warps %d iterations %d avg running lanes/iter %.2f" % (v[15], v[0], v[1] / max(v[0], 1)))
+for k, name in enumerate(("REF", "SUBINNER", "SUBLEAF")):
+    print("  class %-8s chosen %9d iterations (%.1f%%), avg lanes stepped %.2f" % (name, v[2 + k], 100.0 * v[2 + k] / max(v[0], 1), v[5 + k] / max(v[2 + k], 1)))
+print("refill rounds %d lanes %d (%.1f/round); retire rounds %d lanes %d (%.1f/round)" % (v[8], v[9], v[9] / max(v[8], 1), v[10], v[11], v[11] / max(v[10], 1)))
+tot = v[12] + v[13] + v[14]
+print("cycles: steps %.1f%% refill %.1f%% retire %.1f%%; per warp total %.0f cycles; per iteration %.0f cycles" % (100.0 * v[12] / tot, 100.0 * v[13] / tot, 100.0 * v[14] / tot, tot / max(v[15], 1), v[12] / max(v[0], 1)))
