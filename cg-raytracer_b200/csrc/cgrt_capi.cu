@@ -177,8 +177,8 @@ struct cgrt_scene {
     int64_t nTris = 0;
     int nMeshes = 0;
 
-    DevBuf<float4> nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, subNodes;
-    DevBuf<int> origToLeaf, subRoot;
+    DevBuf<float4> nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, pairs;
+    DevBuf<int> origToLeaf;
     DevScene dev{};
 
     std::vector<cgrt_point_light> lights;
@@ -232,7 +232,7 @@ static void destroyScene(cgrt_scene* s)
     cudaSetDevice(s->device);
     s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
     s->triN0.release(); s->triN1.release(); s->triN2.release(); s->mats.release(); s->spheres.release();
-    s->origToLeaf.release(); s->subNodes.release(); s->subRoot.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
+    s->origToLeaf.release(); s->pairs.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->frame.release();
     s->tests.release(); s->hitRec.release(); s->hitList.release(); s->pathDepth.release();
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
@@ -391,18 +391,58 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     UP(triN0, hn[0]); UP(triN1, hn[1]); UP(triN2, hn[2]);
     UP(mats, hMats);
     UP(origToLeaf, hOrigToLeaf);
-    std::vector<float4> hSub(s->bvh.subNodes.size() * 2);
-    for (size_t i = 0; i < s->bvh.subNodes.size(); i++) {
-        const SubNode& n = s->bvh.subNodes[i];
-        float fa, fb;
-        std::memcpy(&fa, &n.a, 4);
-        std::memcpy(&fb, &n.b, 4);
-        hSub[2 * i] = make_float4(n.lo[0], n.lo[1], n.lo[2], fa);
-        hSub[2 * i + 1] = make_float4(n.hi[0], n.hi[1], n.hi[2], fb);
-    }
+    // ---- the production traversal's node array: one 4 x float4 entry per inner node (reference or sub-tree) holding both
+    // children with their visit ids (encoding documented in cgrt_device.cuh)
+    const uint32_t ID_MASK = 0x03ffffffu, ID_REFLEAF = 0x10000000u, ID_TRI = 0x20000000u, ID_SUB = 0x40000000u,
+                   ID_REFSCAN = 0x80000000u;
     if (s->bvh.subRoot.size() != NN) s->bvh.subRoot.assign(NN, -1);
-    UP(subNodes, hSub);
-    UP(subRoot, s->bvh.subRoot);
+    const int nRefPairs = NN > 0 ? (int)(NN - 1) / 2 : 0;
+    std::vector<int> subPairOf(s->bvh.subNodes.size(), -1);
+    int nSubPairs = 0;
+    for (size_t j = 0; j < s->bvh.subNodes.size(); j++)
+        if (s->bvh.subNodes[j].b == 0) subPairOf[j] = nSubPairs++;
+    if ((size_t)nRefPairs + nSubPairs > ID_MASK || T > ID_MASK || NN > ID_MASK) {
+        destroyScene(s);
+        return fail(CGRT_ERR_INVALID, "scene too large for the 26-bit node ids of the traversal");
+    }
+    auto pack = [](const float lo[3], const float hi[3], uint32_t w0, uint32_t w1, float4* out) {
+        float f0, f1;
+        std::memcpy(&f0, &w0, 4);
+        std::memcpy(&f1, &w1, 4);
+        out[0] = make_float4(lo[0], lo[1], lo[2], f0);
+        out[1] = make_float4(hi[0], hi[1], hi[2], f1);
+    };
+    auto refId = [&](int cidx) -> uint32_t {
+        const HostNode& n = s->bvh.nodes[cidx];
+        if (!n.isLeaf) return (uint32_t)((n.child0 - 1) / 2);
+        const int sr = s->bvh.subRoot[cidx];
+        if (sr >= 0) return ID_REFLEAF | (uint32_t)(nRefPairs + subPairOf[sr]);
+        return ID_REFSCAN | (uint32_t)cidx;
+    };
+    auto subId = [&](int k) -> uint32_t {
+        const SubNode& n = s->bvh.subNodes[k];
+        if (n.b == 0) return ID_SUB | (uint32_t)(nRefPairs + subPairOf[k]);
+        return ID_SUB | ID_TRI | ((uint32_t)(n.b - 1) << 26) | (uint32_t)n.a;
+    };
+    std::vector<float4> hPairs(((size_t)nRefPairs + nSubPairs) * 4);
+    for (size_t i = 0; i < NN; i++) {
+        const HostNode& n = s->bvh.nodes[i];
+        if (n.isLeaf) continue;
+        float4* out = hPairs.data() + 4 * (size_t)((n.child0 - 1) / 2);
+        const HostNode &l = s->bvh.nodes[n.child0], &r = s->bvh.nodes[n.child1];
+        pack(l.lo, l.hi, refId(n.child0), (uint32_t)n.child0, out);
+        pack(r.lo, r.hi, refId(n.child1), (uint32_t)n.child1, out + 2);
+    }
+    for (size_t j = 0; j < s->bvh.subNodes.size(); j++) {
+        const SubNode& n = s->bvh.subNodes[j];
+        if (n.b != 0) continue;
+        float4* out = hPairs.data() + 4 * (size_t)(nRefPairs + subPairOf[j]);
+        const SubNode &l = s->bvh.subNodes[n.a], &r = s->bvh.subNodes[n.a + 1];
+        pack(l.lo, l.hi, subId(n.a), 0u, out);
+        pack(r.lo, r.hi, subId(n.a + 1), 0u, out + 2);
+    }
+    s->dev.rootId = NN > 0 ? (int)refId(0) : 0;
+    UP(pairs, hPairs);
 #undef UP
     rc = s->triPl.ensure(T);
     if (rc) { destroyScene(s); return rc; }
@@ -423,8 +463,7 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     s->dev.triN0 = s->triN0.p; s->dev.triN1 = s->triN1.p; s->dev.triN2 = s->triN2.p;
     s->dev.mats = s->mats.p;
     s->dev.origToLeaf = s->origToLeaf.p;
-    s->dev.subNodes = s->bvh.subNodes.empty() ? nullptr : s->subNodes.p;
-    s->dev.subRoot = s->subRoot.p;
+    s->dev.pairs = s->pairs.p;
     s->dev.nNodes = (int)NN;
     s->dev.nTris = (int)T;
     s->dev.nMeshes = d->n_meshes;

@@ -69,48 +69,66 @@ RT_DEV bool leafCandidate(const DevScene& S, int i, const V3& o, const V3& d, Le
     return true;
 }
 
-// Tolerant slab test against a pre-expanded sub-tree box with the per-ray reciprocal direction. Never reports a miss for a box
-// that contains a point the reference could accept at a distance <= bt (bvh_build.cpp: soundness argument).
-RT_DEV bool slabLoose(const float4& lo, const float4& hi, const V3& o, const V3& inv, float bt, float& tNear)
-{
-    const float t0x = (lo.x - o.x) * inv.x, t1x = (hi.x - o.x) * inv.x;
-    const float t0y = (lo.y - o.y) * inv.y, t1y = (hi.y - o.y) * inv.y;
-    const float t0z = (lo.z - o.z) * inv.z, t1z = (hi.z - o.z) * inv.z;
-    const float tIn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
-    const float tOut = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-    tNear = tIn;
-    const float slack = 1.000001f;
-    return !(tOut < 0.0f || tIn > tOut * slack || tIn > bt * slack);
-}
-
 #define CGRT_SUBSTACK 40
-#define CGRT_SUBFLAG 0x40000000 // stack / current-node ids with this bit set refer to S.subNodes
 
-// ---- the production traversal: one node per step, reference nodes and sub-tree nodes on ONE stack, resumable --------------
+// ---- the production traversal ---------------------------------------------------------------------------------------------
 // Same visiting order, pruning and accept arithmetic as traverseStrict below (which documents the mapping to the reference's
-// functions); the difference is purely structural. Every step handles exactly one node - a reference inner node (exact
-// ordered logic), a reference leaf without sub-tree (sequential scan), a sub-tree inner node (tolerant slab tests) or a
-// sub-tree leaf (exact triangle tests) - so that the lanes of a warp advance in lock-step instead of waiting for each other's
-// nested loops, and so that a lane whose ray is finished can be handed a new ray between steps (persistent warps,
-// cgrt_kernels.cu). Stack entries carry a key: for a reference sibling the entry distance tSecond (skipped iff
-// ray.t < tSecond, intersectChildrenHierarchically), for a sub-tree node its tolerant entry distance (skipped iff it lies
-// beyond the leaf's best distance). A reference leaf's result is committed when its sub-tree entries are gone.
+// functions); the difference is structural:
+//  * One node per step, resumable (persistent warps hand a finished lane a new ray between steps, cgrt_kernels.cu).
+//  * Reference nodes and the nodes of the culling sub-trees live in ONE array of child pairs (DevScene::pairs, 4 x float4:
+//    both children's boxes, each with a 2-word descriptor), so a step is one 64-byte fetch, and the inner-node step is the
+//    same instruction stream for both kinds: slab distances as (box - o) * fl(1/d), then a short kind-specific decision.
+//      - sub-tree pair: tolerant test against pre-expanded boxes, nearer child first, pruned against the leaf's best distance;
+//      - reference pair: the reference's exact decisions (intersectNonLeaf / intersectDeeper, bvh.cpp:679-736). The slab
+//        distances computed this way differ from the reference's correctly rounded quotients by at most 3 ulp, so with
+//        rho = 1e-6 relative (+ tau absolute) slack every comparison of slabTest (ray_tracing.cpp:162-200) is either decided
+//        with certainty or declared ambiguous; ambiguous cases (and rays with extreme direction components) evaluate
+//        slabTest itself. Its numeric result matters only for ordering two hit children and for pruning a pending sibling;
+//        there too the approximate value is used when it is decisive and the exact one is computed otherwise.
+//    Outcomes are therefore exactly the reference's; divisions are only executed when they can matter.
+//  * Stack entries carry a key: for a reference sibling the entry distance tSecond (skipped iff ray.t < tSecond,
+//    intersectChildrenHierarchically), for a sub-tree node its tolerant entry distance (skipped iff beyond the leaf's best).
+//    A reference leaf's result is committed when its sub-tree entries are gone.
+//
+// Node ids (child descriptors w0, stack entries, Trav::node):
+//   bits 0..25 index: pair index (inner nodes) | first triangle position (CGRT_TRI) | reference node index (CGRT_REFSCAN)
+//   bit 26  count-1 of a CGRT_TRI leaf        bit 27  CGRT_KEYAPPROX (stack only: the key is an approximate distance)
+//   bit 28  CGRT_REFLEAF: a reference leaf entered through its sub-tree (index = pair of the sub-tree root)
+//   bit 29  CGRT_TRI: sub-tree leaf           bit 30  CGRT_SUB: sub-tree semantics      bit 31  CGRT_REFSCAN: reference
+//   leaf scanned triangle by triangle (leaves too small for a sub-tree, or rays excluded from the tolerant tests)
+#define CGRT_IDX_MASK 0x03ffffffu
+#define CGRT_TRICNT_SHIFT 26
+#define CGRT_KEYAPPROX 0x08000000u
+#define CGRT_REFLEAF 0x10000000u
+#define CGRT_TRI 0x20000000u
+#define CGRT_SUB 0x40000000u
+#define CGRT_REFSCAN 0x80000000u
+
+#define CGRT_RHO 1e-6f
+#define CGRT_TAU 1e-30f
+RT_DEV float errBound(float x) { return fabsf(x) * CGRT_RHO + CGRT_TAU; }
+
 struct Trav {
     V3 o, d, inv;
     float t;
     int hitTri;
-    int sp, node, subBase;
-    bool useSub, inLeaf;
-    bool fastRef; // reference-node box tests may go through the filtered (division-free) path for this ray
+    int sp, subBase;
+    uint32_t node;
+    bool useSub;  // the ray may use the culling sub-trees (tolerant tests are safe for it)
+    bool fastRef; // reference box tests may be decided from (box - o) * inv for this ray
+    bool inLeaf;
     LeafBest best;
 };
 // the traversal stack lives outside the struct so that the scalars above stay in registers
 struct TravStack {
-    int n[CGRT_STACK + CGRT_SUBSTACK];
+    uint32_t n[CGRT_STACK + CGRT_SUBSTACK];
     float t[CGRT_STACK + CGRT_SUBSTACK];
+    int r[CGRT_STACK + CGRT_SUBSTACK]; // reference node index of a reference entry (exact re-evaluation of its key)
 };
 
 enum { TRAV_CONTINUE = 0, TRAV_DONE = 1, TRAV_FIRED = 2 };
+enum { CLS_INNER = 0, CLS_LEAF = 1, CLS_NONE = 2 };
+RT_DEV int travClass(uint32_t node) { return (node & (CGRT_TRI | CGRT_REFSCAN)) ? CLS_LEAF : CLS_INNER; }
 
 // intersectDataStructure (bvh.cpp:831-844): returns true iff the tree has to be traversed for this ray.
 RT_DEV bool travBegin(const DevScene& S, Trav& T, const V3& o, const V3& d, float tIn)
@@ -120,7 +138,6 @@ RT_DEV bool travBegin(const DevScene& S, Trav& T, const V3& o, const V3& d, floa
     T.t = tIn;
     T.hitTri = -1;
     T.sp = 0;
-    T.node = 0;
     T.subBase = 0;
     T.inLeaf = false;
     T.best.t = tIn; T.best.pos = -1; T.best.rank = -1; T.best.shortcut = false;
@@ -132,63 +149,91 @@ RT_DEV bool travBegin(const DevScene& S, Trav& T, const V3& o, const V3& d, floa
         enter = slabTest(mk3(rq0), mk3(rq1), o, d, tIn, tmp);
     }
     if (!enter) return false;
-    // per-ray data of the tolerant sub-tree slab test; rays with extreme direction components scan leaves instead
     const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    // tolerant sub-tree tests: zero components are fine (huge finite reciprocal), extreme magnitudes are not
     const bool okx = (ax == 0.0f) || (ax >= 1e-20f && ax <= 1e20f);
     const bool oky = (ay == 0.0f) || (ay >= 1e-20f && ay <= 1e20f);
     const bool okz = (az == 0.0f) || (az >= 1e-20f && az <= 1e20f);
     const bool fin = fabsf(o.x) <= 1e30f && fabsf(o.y) <= 1e30f && fabsf(o.z) <= 1e30f; // false for NaN
-    T.useSub = S.subNodes != nullptr && okx && oky && okz && fin;
+    T.useSub = okx && oky && okz && fin;
     T.inv.x = ax == 0.0f ? 1e30f : 1.0f / d.x;
     T.inv.y = ay == 0.0f ? 1e30f : 1.0f / d.y;
     T.inv.z = az == 0.0f ? 1e30f : 1.0f / d.z;
     // filtered reference box tests need finite non-zero reciprocals and no overflow in (box - o) * inv
     T.fastRef = ax >= 1e-15f && ax <= 1e15f && ay >= 1e-15f && ay <= 1e15f && az >= 1e-15f && az <= 1e15f &&
                 fabsf(o.x) <= 1e15f && fabsf(o.y) <= 1e15f && fabsf(o.z) <= 1e15f;
+    const uint32_t root = (uint32_t)S.rootId;
+    T.node = ((root & CGRT_REFLEAF) && !T.useSub) ? (CGRT_REFSCAN | 0u) : root;
     return true;
 }
 
-// ---- filtered evaluation of the reference's exact box test ----------------------------------------------------------------
-// slabTest (src/ray_tracing.cpp:162-200) needs six IEEE divisions; almost every call is decided with a wide margin, and its
-// numeric result matters only when two children have to be ordered or a pending sibling is pruned. The filter evaluates the
-// slab distances as (box - o) * fl(1/d): each such value differs from the reference's correctly rounded quotient by at most
-// 3 ulp, so with rho = 1e-6 relative (+ tau absolute, for the subnormal range) slack every comparison of the reference is
-// either decided with certainty or declared ambiguous; ambiguous cases fall back to slabTest itself. Outcomes are therefore
-// exactly the reference's, the divisions are just not executed when they cannot matter.
-// Measured on B200 (profiles/r01_tuning.md): the filter removes ~25 % of the executed instructions of a reference-node step
-// but does not shorten the frame (the kernels are bound by divergence / instruction fetch, not by the division pipe), so it
-// is compiled out by default; -DCGRT_USE_FILTER=1 enables it (the parity suite passes either way).
-#ifndef CGRT_USE_FILTER
-#define CGRT_USE_FILTER 0
-#endif
-#define CGRT_RHO 1e-6f
-#define CGRT_TAU 1e-30f
-RT_DEV float errBound(float x) { return fabsf(x) * CGRT_RHO + CGRT_TAU; }
-
-// the exact test, kept out of line: it is the rare fallback of the filter and would otherwise be inlined six times
-CGRT_RARE bool slabTestOutOfLine(const float4& lo, const float4& hi, const V3& o, const V3& d, float rayT, float& tHit)
+// the reference's distance of a box that is known to be hit (used when an approximate distance is not decisive)
+RT_DEV float boxExactT(const float4& lo, const float4& hi, const V3& o, const V3& d)
 {
-    return slabTest(mk3(lo), mk3(hi), o, d, rayT, tHit);
+    float te = 0.0f;
+    slabTest(mk3(lo), mk3(hi), o, d, __int_as_float(0x7f800000), te);
+    return te;
 }
 
-// hit: the reference's boolean; t: its distance (exact when `exact`, otherwise within errBound(t) of it)
-RT_DEV void boxFiltered(const float4& lo, const float4& hi, const V3& o, const V3& d, const V3& inv, bool fast, float rayT,
-                        bool& hit, float& t, bool& exact)
+// pop: next pending node that is not pruned, committing the reference leaf when its sub-tree entries are gone
+RT_DEV int travPop(const DevScene& S, Trav& T, TravStack& K)
 {
-    if (CGRT_USE_FILTER && fast) {
-        const float q0x = (lo.x - o.x) * inv.x, q1x = (hi.x - o.x) * inv.x;
-        const float q0y = (lo.y - o.y) * inv.y, q1y = (hi.y - o.y) * inv.y;
-        const float q0z = (lo.z - o.z) * inv.z, q1z = (hi.z - o.z) * inv.z;
-        const float tin = fmaxf(fmaxf(fminf(q0x, q1x), fminf(q0y, q1y)), fminf(q0z, q1z));
-        const float tout = fminf(fminf(fmaxf(q0x, q1x), fmaxf(q0y, q1y)), fmaxf(q0z, q1z));
+    const float slack = 1.000001f;
+    while (true) {
+        if (T.inLeaf && T.sp == T.subBase) {
+            if (T.best.pos >= 0) { T.t = T.best.t; T.hitTri = T.best.pos; }
+            T.inLeaf = false;
+        }
+        if (T.sp == 0) return TRAV_DONE;
+        T.sp--;
+        const uint32_t n = K.n[T.sp];
+        const float key = K.t[T.sp];
+        if (n & CGRT_SUB) {
+            if (key > T.best.t * slack) continue;
+            T.node = n;
+            return TRAV_CONTINUE;
+        }
+        // reference sibling: skipped iff ray.t < tSecond (intersectChildrenHierarchically, bvh.cpp:572-595)
+        if (n & CGRT_KEYAPPROX) {
+            const float e = errBound(key);
+            if (T.t < key - e) continue;
+            if (!(T.t >= key + e)) { // not decisive: compare with the reference's exact distance of that box
+                const int ri = K.r[T.sp];
+                const float tS = boxExactT(__ldg(S.nodes + 2 * ri), __ldg(S.nodes + 2 * ri + 1), T.o, T.d);
+                if (T.t < tS) continue;
+            }
+        } else {
+            if (T.t < key) continue;
+        }
+        T.node = n & ~CGRT_KEYAPPROX;
+        return TRAV_CONTINUE;
+    }
+}
+
+// slab distances of one child box from the per-ray reciprocals
+RT_DEV void slabApprox(const float4& lo, const float4& hi, const V3& o, const V3& inv, float& tin, float& tout)
+{
+    const float q0x = (lo.x - o.x) * inv.x, q1x = (hi.x - o.x) * inv.x;
+    const float q0y = (lo.y - o.y) * inv.y, q1y = (hi.y - o.y) * inv.y;
+    const float q0z = (lo.z - o.z) * inv.z, q1z = (hi.z - o.z) * inv.z;
+    tin = fmaxf(fmaxf(fminf(q0x, q1x), fminf(q0y, q1y)), fminf(q0z, q1z));
+    tout = fminf(fminf(fmaxf(q0x, q1x), fmaxf(q0y, q1y)), fmaxf(q0z, q1z));
+}
+
+// the reference's box test decided from approximate slab distances when that is certain, else by slabTest itself.
+// hit: the reference's boolean; t: its distance (exact when `exact`, otherwise within errBound(t) of it)
+RT_DEV void refBoxDecide(const float4& lo, const float4& hi, const V3& o, const V3& d, bool fast, float tin, float tout,
+                         float rayT, bool& hit, float& t, bool& exact)
+{
+    if (fast) {
         const float ein = errBound(tin), eout = errBound(tout);
         if (tout + eout < 0.0f || tin - ein > tout + eout) { // certainly `tOut < 0` or `tIn > tOut`
             hit = false;
             return;
         }
-        float cur, ecur;
+        float cur = 0.0f, ecur = 0.0f;
         bool branch = false;
-        if (tin + ein < 0.0f) { cur = tout; ecur = eout; branch = true; }        // certainly tIn < 0: inside the slabs
+        if (tin + ein < 0.0f) { cur = tout; ecur = eout; branch = true; }        // certainly tIn < 0
         else if (tin - ein >= 0.0f) { cur = tin; ecur = ein; branch = true; }   // certainly tIn >= 0
         if (branch) {
             if (cur - ecur >= rayT) { // certainly `currentT >= ray.t`
@@ -204,201 +249,138 @@ RT_DEV void boxFiltered(const float4& lo, const float4& hi, const V3& o, const V
         }
     }
     float te = 0.0f;
-    hit = slabTestOutOfLine(lo, hi, o, d, rayT, te);
+    hit = slabTest(mk3(lo), mk3(hi), o, d, rayT, te);
     t = te;
     exact = true;
 }
 
-// the reference's distance of a box that is known to be hit (used when an approximate distance is not decisive)
-CGRT_RARE float boxExactT(const float4& lo, const float4& hi, const V3& o, const V3& d)
+// one step on an inner node (reference pair or sub-tree pair)
+RT_DEV int travStepInner(const DevScene& S, Trav& T, TravStack& K)
 {
-    float te = 0.0f;
-    slabTest(mk3(lo), mk3(hi), o, d, __int_as_float(0x7f800000), te);
-    return te;
-}
-
-// Node classes of the state machine. The current node id encodes its class: reference nodes are plain indices into
-// S.nodes; CGRT_SUBFLAG marks a sub-tree inner node (index into S.subNodes); CGRT_SUBFLAG|CGRT_LEAFFLAG marks a sub-tree
-// leaf and carries its triangle range directly (bit 28 = count-1, bits 0..27 = first position), so a sub-tree leaf costs
-// no node fetch.
-#define CGRT_LEAFFLAG 0x20000000
-#define CGRT_KEYAPPROX 0x10000000 // reference stack entry whose key is a filtered (approximate) box distance
-#define CGRT_LEAFCNT_SHIFT 28
-#define CGRT_POS_MASK 0x0fffffff
-enum { CLS_REF = 0, CLS_SUBINNER = 1, CLS_SUBLEAF = 2, CLS_NONE = 3 };
-RT_DEV int travClass(int node)
-{
-    return !(node & CGRT_SUBFLAG) ? CLS_REF : ((node & CGRT_LEAFFLAG) ? CLS_SUBLEAF : CLS_SUBINNER);
-}
-RT_DEV int subChildId(int index, const float4& lo, const float4& hi)
-{
-    const int b = f2i(hi.w);
-    if (b == 0) return index | CGRT_SUBFLAG;
-    return CGRT_SUBFLAG | CGRT_LEAFFLAG | ((b - 1) << CGRT_LEAFCNT_SHIFT) | f2i(lo.w);
-}
-
-// pop: next pending node that is not pruned, committing the reference leaf when its sub-tree entries are gone
-RT_DEV int travPop(const DevScene& S, Trav& T, TravStack& K)
-{
-    const float slack = 1.000001f;
-    while (true) {
-        if (T.inLeaf && T.sp == T.subBase) {
-            if (T.best.pos >= 0) { T.t = T.best.t; T.hitTri = T.best.pos; }
-            T.inLeaf = false;
-        }
-        if (T.sp == 0) return TRAV_DONE;
-        T.sp--;
-        const int n = K.n[T.sp];
-        const float key = K.t[T.sp];
-        if (n & CGRT_SUBFLAG) {
-            if (key > T.best.t * slack) continue;
-            T.node = n;
-            return TRAV_CONTINUE;
-        }
-        // reference sibling: skipped iff ray.t < tSecond (intersectChildrenHierarchically, bvh.cpp:572-595)
-        const int ni = n & ~CGRT_KEYAPPROX;
-        if (n & CGRT_KEYAPPROX) {
-            const float e = errBound(key);
-            if (T.t < key - e) continue;
-            if (!(T.t >= key + e)) { // not decisive: compare with the reference's exact distance of that box
-                const float tS = boxExactT(__ldg(S.nodes + 2 * ni), __ldg(S.nodes + 2 * ni + 1), T.o, T.d);
-                if (T.t < tS) continue;
-            }
-        } else {
-            if (T.t < key) continue;
-        }
-        T.node = ni;
-        return TRAV_CONTINUE;
-    }
-}
-
-// one step on a reference node
-template <bool ANY>
-RT_DEV int travStepRef(const DevScene& S, Trav& T, TravStack& K, float eps, float maxDist)
-{
-    const V3 o = T.o, d = T.d;
-    const int node = T.node;
-    const float4 q0 = __ldg(S.nodes + 2 * node), q1 = __ldg(S.nodes + 2 * node + 1);
-    const uint32_t a = (uint32_t)f2i(q0.w), b = (uint32_t)f2i(q1.w);
-    if (b != 0u) {
-        // ---- reference leaf
+    uint32_t id = T.node;
+    if (id & CGRT_REFLEAF) { // entering a reference leaf through its sub-tree (intersectLeaf, evaluated order-independently)
         T.best.t = T.t; T.best.pos = -1; T.best.rank = -1; T.best.shortcut = false;
-        const int sr = T.useSub ? __ldg(S.subRoot + node) : -1;
-        if (sr >= 0) {
-            T.inLeaf = true;
-            T.subBase = T.sp;
-            T.node = sr | CGRT_SUBFLAG; // the root of a sub-tree is always an inner node (leaves below 8 triangles have none)
-            return TRAV_CONTINUE;
+        T.inLeaf = true;
+        T.subBase = T.sp;
+        id = (id & CGRT_IDX_MASK) | CGRT_SUB;
+    }
+    const bool isSub = (id & CGRT_SUB) != 0u;
+    const float4* pr = S.pairs + 4 * (size_t)(id & CGRT_IDX_MASK);
+    const float4 l0 = __ldg(pr), l1 = __ldg(pr + 1), r0 = __ldg(pr + 2), r1 = __ldg(pr + 3);
+    const V3 o = T.o;
+    float tinL, toutL, tinR, toutR;
+    slabApprox(l0, l1, o, T.inv, tinL, toutL);
+    slabApprox(r0, r1, o, T.inv, tinR, toutR);
+    uint32_t idL = (uint32_t)f2i(l0.w), idR = (uint32_t)f2i(r0.w);
+    uint32_t first = 0u, second = 0u;
+    bool haveFirst = false, haveSecond = false;
+    float key = -1.0f;
+    int keyRef = 0;
+    if (isSub) {
+        // tolerant test against pre-expanded boxes; never a miss for a box that holds a point the reference could accept
+        const float slack = 1.000001f;
+        const float bt = T.best.t;
+        const bool hL = !(toutL < 0.0f || tinL > toutL * slack || tinL > bt * slack);
+        const bool hR = !(toutR < 0.0f || tinR > toutR * slack || tinR > bt * slack);
+        const bool leftFirst = tinL <= tinR;
+        if (hL && hR) {
+            first = leftFirst ? idL : idR;
+            second = leftFirst ? idR : idL;
+            key = leftFirst ? tinR : tinL;
+            haveFirst = haveSecond = true;
+        } else if (hL || hR) {
+            first = hL ? idL : idR;
+            haveFirst = true;
         }
-        const uint32_t end = a + b;
-#pragma unroll 1
-        for (uint32_t i = a; i < end; i++) {
-            if (leafCandidate(S, (int)i, o, d, T.best)) {
-                if (ANY && !(T.best.t + eps >= maxDist)) return TRAV_FIRED;
+    } else {
+        // intersectNonLeaf + intersectDeeper with the reference's exact outcomes
+        const V3 d = T.d;
+        if (!T.useSub) { // this ray scans reference leaves instead of using their sub-trees
+            if (idL & CGRT_REFLEAF) idL = CGRT_REFSCAN | (uint32_t)f2i(l1.w);
+            if (idR & CGRT_REFLEAF) idR = CGRT_REFSCAN | (uint32_t)f2i(r1.w);
+        }
+        bool hL, hR, exL = true, exR = true;
+        float tL = -1.0f, tR = -1.0f;
+        refBoxDecide(l0, l1, o, d, T.fastRef, tinL, toutL, T.t, hL, tL, exL);
+        refBoxDecide(r0, r1, o, d, T.fastRef, tinR, toutR, T.t, hR, tR, exR);
+        const bool inL = startsInBox(o, mk3(l0), mk3(l1));
+        const bool inR = startsInBox(o, mk3(r0), mk3(r1));
+        bool keyApprox = false, secondIsRight = false;
+        if (inL && inR) { // both visited unconditionally, left operand of `|` first (g++ order)
+            first = idL; second = idR; haveFirst = haveSecond = true; secondIsRight = true; key = -1.0f;
+        } else if (inL) {
+            first = idL; haveFirst = true;
+            if (hR) { second = idR; haveSecond = true; secondIsRight = true; key = tR; keyApprox = !exR; }
+        } else if (inR) {
+            first = idR; haveFirst = true;
+            if (hL) { second = idL; haveSecond = true; key = tL; keyApprox = !exL; }
+        } else if (hL && hR) {
+            // nearer child first: `tLeft < tRight` (bvh.cpp:626), from the approximate distances when they are separated
+            // by more than their error bounds, otherwise from the exact ones
+            bool leftFirst;
+            if (!(exL && exR) && tL + errBound(tL) < tR - errBound(tR)) leftFirst = true;
+            else if (!(exL && exR) && tL - errBound(tL) >= tR + errBound(tR)) leftFirst = false;
+            else {
+                if (!exL) { tL = boxExactT(l0, l1, o, d); exL = true; }
+                if (!exR) { tR = boxExactT(r0, r1, o, d); exR = true; }
+                leftFirst = tL < tR;
             }
+            haveFirst = haveSecond = true;
+            if (leftFirst) { first = idL; second = idR; secondIsRight = true; key = tR; keyApprox = !exR; }
+            else { first = idR; second = idL; key = tL; keyApprox = !exL; }
+        } else if (hL) {
+            first = idL; haveFirst = true;
+        } else if (hR) {
+            first = idR; haveFirst = true;
         }
-        if (T.best.pos >= 0) { T.t = T.best.t; T.hitTri = T.best.pos; }
-        return travPop(S, T, K);
+        if (keyApprox) second |= CGRT_KEYAPPROX;
+        keyRef = f2i(secondIsRight ? r1.w : l1.w);
     }
-    // ---- reference inner node: intersectNonLeaf + intersectDeeper, exact arithmetic
-    const int L = (int)a, Rn = (int)a + 1;
-    const float4 l0 = __ldg(S.nodes + 2 * L), l1 = __ldg(S.nodes + 2 * L + 1);
-    const float4 r0 = __ldg(S.nodes + 2 * L + 2), r1 = __ldg(S.nodes + 2 * L + 3);
-    bool hL, hR, exL = true, exR = true;
-    float tL = -1.0f, tR = -1.0f;
-    boxFiltered(l0, l1, o, d, T.inv, T.fastRef, T.t, hL, tL, exL);
-    boxFiltered(r0, r1, o, d, T.inv, T.fastRef, T.t, hR, tR, exR);
-    const bool inL = startsInBox(o, mk3(l0), mk3(l1));
-    const bool inR = startsInBox(o, mk3(r0), mk3(r1));
-    int first = -1, second = -1;
-    float tS = -1.0f;
-    bool keyApprox = false;
-    if (inL && inR) { // both visited unconditionally, left operand of `|` first (g++ order)
-        first = L; second = Rn; tS = -1.0f;
-    } else if (inL) {
-        first = L;
-        if (hR) { second = Rn; tS = tR; keyApprox = !exR; }
-    } else if (inR) {
-        first = Rn;
-        if (hL) { second = L; tS = tL; keyApprox = !exL; }
-    } else if (hL && hR) {
-        // nearer child first: `tLeft < tRight` (bvh.cpp:626); decide from the approximate distances when they are
-        // separated by more than their error bounds, otherwise from the exact ones
-        bool leftFirst;
-        if (tL + errBound(tL) < tR - errBound(tR) && !(exL && exR)) leftFirst = true;
-        else if (tL - errBound(tL) >= tR + errBound(tR) && !(exL && exR)) leftFirst = false;
-        else {
-            if (!exL) { tL = boxExactT(l0, l1, o, d); exL = true; }
-            if (!exR) { tR = boxExactT(r0, r1, o, d); exR = true; }
-            leftFirst = tL < tR;
-        }
-        if (leftFirst) { first = L; second = Rn; tS = tR; keyApprox = !exR; }
-        else { first = Rn; second = L; tS = tL; keyApprox = !exL; }
-    } else if (hL) {
-        first = L;
-    } else if (hR) {
-        first = Rn;
-    }
-    if (second >= 0) {
-        K.n[T.sp] = keyApprox ? (second | CGRT_KEYAPPROX) : second;
-        K.t[T.sp] = tS;
+    if (haveSecond) {
+        K.n[T.sp] = second;
+        K.t[T.sp] = key;
+        K.r[T.sp] = keyRef;
         T.sp++;
     }
-    if (first >= 0) {
+    if (haveFirst) {
         T.node = first;
         return TRAV_CONTINUE;
     }
     return travPop(S, T, K);
 }
 
-// one step on a sub-tree inner node: tolerant slab tests, nearer child first
-RT_DEV int travStepSubInner(const DevScene& S, Trav& T, TravStack& K)
-{
-    const int sn = T.node & CGRT_POS_MASK;
-    const int a = f2i(__ldg(S.subNodes + 2 * sn).w);
-    const float4 l0 = __ldg(S.subNodes + 2 * a), l1 = __ldg(S.subNodes + 2 * a + 1);
-    const float4 r0 = __ldg(S.subNodes + 2 * a + 2), r1 = __ldg(S.subNodes + 2 * a + 3);
-    float tL, tR;
-    const bool hL = slabLoose(l0, l1, T.o, T.inv, T.best.t, tL);
-    const bool hR = slabLoose(r0, r1, T.o, T.inv, T.best.t, tR);
-    const int idL = subChildId(a, l0, l1), idR = subChildId(a + 1, r0, r1);
-    if (hL && hR) {
-        const bool leftFirst = tL <= tR;
-        K.n[T.sp] = leftFirst ? idR : idL;
-        K.t[T.sp] = leftFirst ? tR : tL;
-        T.sp++;
-        T.node = leftFirst ? idL : idR;
-        return TRAV_CONTINUE;
-    }
-    if (hL || hR) {
-        T.node = hL ? idL : idR;
-        return TRAV_CONTINUE;
-    }
-    return travPop(S, T, K);
-}
-
-// one step on a sub-tree leaf: exact tests of the few triangles that survived the culling
+// one step on a leaf: the triangles of a sub-tree leaf (folded into the reference leaf's running best), or a whole
+// reference leaf scanned in order
 template <bool ANY>
-RT_DEV int travStepSubLeaf(const DevScene& S, Trav& T, TravStack& K, float eps, float maxDist)
+RT_DEV int travStepLeaf(const DevScene& S, Trav& T, TravStack& K, float eps, float maxDist)
 {
-    const int first = T.node & CGRT_POS_MASK;
-    const int count = ((T.node >> CGRT_LEAFCNT_SHIFT) & 1) + 1;
+    const uint32_t id = T.node;
+    int first, count;
+    const bool scan = (id & CGRT_REFSCAN) != 0u;
+    if (scan) {
+        const int ri = (int)(id & CGRT_IDX_MASK);
+        first = f2i(__ldg(S.nodes + 2 * ri).w);
+        count = f2i(__ldg(S.nodes + 2 * ri + 1).w);
+        T.best.t = T.t; T.best.pos = -1; T.best.rank = -1; T.best.shortcut = false;
+    } else {
+        first = (int)(id & CGRT_IDX_MASK);
+        count = (int)((id >> CGRT_TRICNT_SHIFT) & 1u) + 1;
+    }
 #pragma unroll 1
     for (int i = first; i < first + count; i++) {
         if (leafCandidate(S, i, T.o, T.d, T.best)) {
             if (ANY && !(T.best.t + eps >= maxDist)) return TRAV_FIRED;
         }
     }
+    if (scan && T.best.pos >= 0) { T.t = T.best.t; T.hitTri = T.best.pos; }
     return travPop(S, T, K);
 }
 
 template <bool ANY>
 RT_DEV int travStep(const DevScene& S, Trav& T, TravStack& K, float eps, float maxDist)
 {
-    const int cls = travClass(T.node);
-    if (cls == CLS_REF) return travStepRef<ANY>(S, T, K, eps, maxDist);
-    if (cls == CLS_SUBINNER) return travStepSubInner(S, T, K);
-    return travStepSubLeaf<ANY>(S, T, K, eps, maxDist);
+    if (travClass(T.node) == CLS_INNER) return travStepInner(S, T, K);
+    return travStepLeaf<ANY>(S, T, K, eps, maxDist);
 }
 
 // After the tree: the sphere loop of BoundingVolumeHierarchy::intersect (bvh.cpp:878-879) and the result record.

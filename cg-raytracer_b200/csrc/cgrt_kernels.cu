@@ -414,10 +414,10 @@ __global__ void __launch_bounds__(128) k_shadow(DevScene S, const FrameParams* _
 #define CGRT_MINBLOCKS 8 // 8 CTAs x 4 warps per SM: caps the traversal kernels at 64 registers
 #endif
 #define CGRT_REFILL_MIN_IDLE 6
-#ifndef CGRT_W_REF
-#define CGRT_W_REF 4
-#define CGRT_W_SUBINNER 16
-#define CGRT_W_SUBLEAF 8
+// vote weights of the two node classes (lanes x weight, larger wins): plain majority by default
+#ifndef CGRT_W_INNER
+#define CGRT_W_INNER 1
+#define CGRT_W_LEAF 1
 #endif
 struct Tuning {
     int steps = 12;  // traversal steps between two refill / retire rounds
@@ -563,19 +563,15 @@ RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCou
             continue;
 #endif
             const int cls = run ? travClass(T.node) : CLS_NONE;
-            const int s0 = __popc(__ballot_sync(0xffffffffu, cls == CLS_REF)) * CGRT_W_REF;
-            const int s1 = __popc(__ballot_sync(0xffffffffu, cls == CLS_SUBINNER)) * CGRT_W_SUBINNER;
-            const int s2 = __popc(__ballot_sync(0xffffffffu, cls == CLS_SUBLEAF)) * CGRT_W_SUBLEAF;
-            if ((s0 | s1 | s2) == 0) break;
-            if (s0 >= s1 && s0 >= s2) {
-                INSTR_ADD(2, 1); INSTR_ADD(5, s0 / CGRT_W_REF);
-                if (cls == CLS_REF) state = travStepRef<ANY>(S, T, K, eps, maxDist);
-            } else if (s1 >= s2) {
-                INSTR_ADD(3, 1); INSTR_ADD(6, s1 / CGRT_W_SUBINNER);
-                if (cls == CLS_SUBINNER) state = travStepSubInner(S, T, K);
+            const int s0 = __popc(__ballot_sync(0xffffffffu, cls == CLS_INNER)) * CGRT_W_INNER;
+            const int s1 = __popc(__ballot_sync(0xffffffffu, cls == CLS_LEAF)) * CGRT_W_LEAF;
+            if ((s0 | s1) == 0) break;
+            if (s0 >= s1) {
+                INSTR_ADD(2, 1); INSTR_ADD(5, s0 / CGRT_W_INNER);
+                if (cls == CLS_INNER) state = travStepInner(S, T, K);
             } else {
-                INSTR_ADD(4, 1); INSTR_ADD(7, s2 / CGRT_W_SUBLEAF);
-                if (cls == CLS_SUBLEAF) state = travStepSubLeaf<ANY>(S, T, K, eps, maxDist);
+                INSTR_ADD(3, 1); INSTR_ADD(6, s1 / CGRT_W_LEAF);
+                if (cls == CLS_LEAF) state = travStepLeaf<ANY>(S, T, K, eps, maxDist);
             }
         }
 #ifdef CGRT_INSTRUMENT
