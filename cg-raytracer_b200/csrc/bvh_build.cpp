@@ -283,11 +283,12 @@ TriBox conservativeBox(const float* p0, const float* p1, const float* p2)
     return tb;
 }
 
-struct SubBuilder {
+struct WideBuilder {
     const std::vector<TriBox>& boxes; // per position (leaf order at entry)
     std::vector<int32_t>& order;      // positions being permuted (values index `boxes`)
-    std::vector<SubNode>& nodes;
+    std::vector<WideNode>& nodes;
     int subLeafSize;
+    int base; // first position of the reference leaf in the global arrays
 
     void bounds(int begin, int end, float lo[3], float hi[3]) const
     {
@@ -301,18 +302,9 @@ struct SubBuilder {
         }
     }
 
-    // builds the node for [begin,end) into nodes[self]; children are allocated adjacently
-    void build(int self, int begin, int end, int base)
+    // median split of [begin,end) along the longest centroid axis; returns the split point
+    int split(int begin, int end)
     {
-        SubNode n;
-        bounds(begin, end, n.lo, n.hi);
-        const int count = end - begin;
-        if (count <= subLeafSize) {
-            n.a = base + begin;
-            n.b = count;
-            nodes[self] = n;
-            return;
-        }
         float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
         for (int i = begin; i < end; i++)
             for (int k = 0; k < 3; k++) {
@@ -322,19 +314,52 @@ struct SubBuilder {
         int axis = 0;
         if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
         if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
-        const int mid = begin + count / 2;
+        const int mid = begin + (end - begin) / 2;
         std::nth_element(order.begin() + begin, order.begin() + mid, order.begin() + end, [&](int32_t x, int32_t y) {
             const float cx = boxes[x].c[axis], cy = boxes[y].c[axis];
             return cx < cy || (cx == cy && x < y);
         });
-        const int left = (int)nodes.size();
-        nodes.push_back(SubNode());
-        nodes.push_back(SubNode());
-        n.a = left;
-        n.b = 0;
+        return mid;
+    }
+
+    // builds the wide node for [begin,end) into nodes[self]
+    void build(int self, int begin, int end)
+    {
+        // three binary levels collapsed: up to 8 sub-ranges, a range is not split further once it fits a sub-leaf
+        std::vector<std::pair<int, int>> ranges{{begin, end}};
+        for (int level = 0; level < 3; level++) {
+            std::vector<std::pair<int, int>> next;
+            for (const auto& r : ranges) {
+                if (r.second - r.first <= subLeafSize) {
+                    next.push_back(r);
+                    continue;
+                }
+                const int mid = split(r.first, r.second);
+                next.push_back({r.first, mid});
+                next.push_back({mid, r.second});
+            }
+            ranges.swap(next);
+        }
+        WideNode n;
+        for (int c = 0; c < 8; c++) {
+            for (int k = 0; k < 3; k++) { n.lo[c][k] = FLT_MAX; n.hi[c][k] = -FLT_MAX; } // inverted: never hit
+            n.id[c] = 0u;
+        }
+        std::vector<int> childNode(ranges.size(), -1);
+        for (size_t c = 0; c < ranges.size(); c++) {
+            const int b = ranges[c].first, e = ranges[c].second;
+            bounds(b, e, n.lo[c], n.hi[c]);
+            if (e - b <= subLeafSize) {
+                n.id[c] = 0x40000000u | 0x20000000u | ((uint32_t)(e - b - 1) << 26) | (uint32_t)(base + b);
+            } else {
+                childNode[c] = (int)nodes.size();
+                nodes.push_back(WideNode());
+                n.id[c] = 0x40000000u | (uint32_t)childNode[c];
+            }
+        }
         nodes[self] = n;
-        build(left, begin, mid, base);
-        build(left + 1, mid, end, base);
+        for (size_t c = 0; c < ranges.size(); c++)
+            if (childNode[c] >= 0) build(childNode[c], ranges[c].first, ranges[c].second);
     }
 };
 
@@ -342,18 +367,20 @@ struct SubBuilder {
 
 void buildLeafSubTrees(const std::vector<MeshView>& meshes, BuiltBVH& bvh, int minLeafForSubTree, int subLeafSize)
 {
+    if (subLeafSize > 8) subLeafSize = 8;
+    if (subLeafSize < 1) subLeafSize = 1;
     const size_t T = bvh.leafTris.size();
     bvh.leafTrisReferenceOrder = bvh.leafTris;
     bvh.leafRank.assign(T, 0);
-    bvh.subNodes.clear();
-    bvh.subRoot.assign(bvh.nodes.size(), -1);
+    bvh.wide.clear();
+    bvh.wideRoot.assign(bvh.nodes.size(), -1);
     std::vector<LeafTri> permuted = bvh.leafTris;
     for (size_t ni = 0; ni < bvh.nodes.size(); ni++) {
         const HostNode& n = bvh.nodes[ni];
         if (!n.isLeaf) continue;
         const int first = n.firstTri, count = n.triCount;
         for (int i = 0; i < count; i++) bvh.leafRank[first + i] = i;
-        if (count < minLeafForSubTree) continue;
+        if (count < minLeafForSubTree || count <= subLeafSize) continue;
         std::vector<TriBox> boxes(count);
         for (int i = 0; i < count; i++) {
             const LeafTri lt = bvh.leafTris[first + i];
@@ -364,11 +391,11 @@ void buildLeafSubTrees(const std::vector<MeshView>& meshes, BuiltBVH& bvh, int m
         }
         std::vector<int32_t> order(count);
         for (int i = 0; i < count; i++) order[i] = i;
-        const int root = (int)bvh.subNodes.size();
-        bvh.subNodes.push_back(SubNode());
-        SubBuilder sb{boxes, order, bvh.subNodes, subLeafSize};
-        sb.build(root, 0, count, first);
-        bvh.subRoot[ni] = root;
+        const int root = (int)bvh.wide.size();
+        bvh.wide.push_back(WideNode());
+        WideBuilder wb{boxes, order, bvh.wide, subLeafSize, first};
+        wb.build(root, 0, count);
+        bvh.wideRoot[ni] = root;
         for (int i = 0; i < count; i++) {
             permuted[first + i] = bvh.leafTris[first + order[i]];
             bvh.leafRank[first + i] = order[i];

@@ -28,12 +28,13 @@ struct LeafTri {
     int32_t tri; // mesh-local triangle index
 };
 
-// Node of the culling sub-trees that refine the (large) leaves of the reference tree. Boxes are pre-expanded so that
-// culling is conservative with respect to the reference's floating-point accept test (see buildLeafSubTrees).
-struct SubNode {
-    float lo[3], hi[3];
-    int32_t a; // inner: index of the left child in BuiltBVH::subNodes (right = a + 1); leaf: first position in leafTris
-    int32_t b; // inner: 0; leaf: triangle count (> 0)
+// 8-wide node of the culling sub-trees that refine the (large) leaves of the reference tree. Boxes are pre-expanded so that
+// culling is conservative with respect to the reference's floating-point accept test (see buildLeafSubTrees). Unused child
+// slots have an inverted box (never hit). Child ids are already in the traversal's encoding (cgrt_device.cuh):
+// CGRT_SUB | wide node index, or CGRT_SUB | CGRT_TRI | (count-1) << 26 | first position.
+struct WideNode {
+    float lo[8][3], hi[8][3];
+    uint32_t id[8];
 };
 
 struct BuiltBVH {
@@ -41,19 +42,20 @@ struct BuiltBVH {
     std::vector<LeafTri> leafTris;   // after buildLeafSubTrees: permuted inside each reference leaf (sub-tree order)
     std::vector<int32_t> leafRank;   // per position: rank of that triangle in the reference's own leaf order
     std::vector<LeafTri> leafTrisReferenceOrder; // the reference's visiting order (intersectLeaf), kept for introspection
-    std::vector<SubNode> subNodes;
-    std::vector<int32_t> subRoot;    // per reference node: root of its sub-tree in subNodes, -1 = scan the leaf
+    std::vector<WideNode> wide;
+    std::vector<int32_t> wideRoot;   // per reference node: root of its sub-tree in `wide`, -1 = scan the leaf
     int numLevels = 0;
 };
 
 // maxDepth: the reference literal is 12 (bvh.cpp:48); leaves are nodes at level maxDepth-1 or single-mesh/single-triangle nodes.
 void buildReferenceBVH(const std::vector<MeshView>& meshes, int maxDepth, BuiltBVH& out);
 
-// Refine every reference leaf with more than `minLeafForSubTree` triangles by a binary culling tree (median split of the
-// centroids along the longest axis, `subLeafSize` triangles per sub-leaf). The reference tree itself is untouched: the
-// traversal still visits reference nodes in the reference's order with the reference's exact box arithmetic; inside a
-// reference leaf the sub-tree only decides which triangles need the exact test. Triangles whose accept region cannot be
-// bounded tightly (non-finite coordinates, minimum angle below ~0.01 rad) get an unbounded box, i.e. they are always tested.
-void buildLeafSubTrees(const std::vector<MeshView>& meshes, BuiltBVH& bvh, int minLeafForSubTree = 8, int subLeafSize = 2);
+// Refine every reference leaf with at least `minLeafForSubTree` triangles by an 8-wide culling tree (median splits of the
+// centroids along the longest axis, three binary levels collapsed into one node, at most `subLeafSize` <= 8 triangles per
+// sub-leaf). The reference tree itself is untouched: the traversal still visits reference nodes in the reference's order
+// with the reference's exact box decisions; inside a reference leaf the sub-tree only decides which triangles need the exact
+// test. Triangles whose accept region cannot be bounded tightly (non-finite coordinates, minimum angle below ~0.01 rad) get
+// an unbounded box, i.e. they are always tested.
+void buildLeafSubTrees(const std::vector<MeshView>& meshes, BuiltBVH& bvh, int minLeafForSubTree = 8, int subLeafSize = 6);
 
 } // namespace cgrt

@@ -177,7 +177,7 @@ struct cgrt_scene {
     int64_t nTris = 0;
     int nMeshes = 0;
 
-    DevBuf<float4> nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, pairs;
+    DevBuf<float4> nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, pairs, wide;
     DevBuf<int> origToLeaf;
     DevScene dev{};
 
@@ -232,7 +232,7 @@ static void destroyScene(cgrt_scene* s)
     cudaSetDevice(s->device);
     s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
     s->triN0.release(); s->triN1.release(); s->triN2.release(); s->mats.release(); s->spheres.release();
-    s->origToLeaf.release(); s->pairs.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
+    s->origToLeaf.release(); s->pairs.release(); s->wide.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->frame.release();
     s->tests.release(); s->hitRec.release(); s->hitList.release(); s->pathDepth.release();
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
@@ -395,13 +395,9 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     // children with their visit ids (encoding documented in cgrt_device.cuh)
     const uint32_t ID_MASK = 0x03ffffffu, ID_REFLEAF = 0x10000000u, ID_TRI = 0x20000000u, ID_SUB = 0x40000000u,
                    ID_REFSCAN = 0x80000000u;
-    if (s->bvh.subRoot.size() != NN) s->bvh.subRoot.assign(NN, -1);
+    if (s->bvh.wideRoot.size() != NN) s->bvh.wideRoot.assign(NN, -1);
     const int nRefPairs = NN > 0 ? (int)(NN - 1) / 2 : 0;
-    std::vector<int> subPairOf(s->bvh.subNodes.size(), -1);
-    int nSubPairs = 0;
-    for (size_t j = 0; j < s->bvh.subNodes.size(); j++)
-        if (s->bvh.subNodes[j].b == 0) subPairOf[j] = nSubPairs++;
-    if ((size_t)nRefPairs + nSubPairs > ID_MASK || T > ID_MASK || NN > ID_MASK) {
+    if ((size_t)nRefPairs > ID_MASK || s->bvh.wide.size() > ID_MASK || T > ID_MASK || NN > ID_MASK) {
         destroyScene(s);
         return fail(CGRT_ERR_INVALID, "scene too large for the 26-bit node ids of the traversal");
     }
@@ -415,16 +411,12 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     auto refId = [&](int cidx) -> uint32_t {
         const HostNode& n = s->bvh.nodes[cidx];
         if (!n.isLeaf) return (uint32_t)((n.child0 - 1) / 2);
-        const int sr = s->bvh.subRoot[cidx];
-        if (sr >= 0) return ID_REFLEAF | (uint32_t)(nRefPairs + subPairOf[sr]);
+        const int wr = s->bvh.wideRoot[cidx];
+        if (wr >= 0) return ID_REFLEAF | (uint32_t)wr;
         return ID_REFSCAN | (uint32_t)cidx;
     };
-    auto subId = [&](int k) -> uint32_t {
-        const SubNode& n = s->bvh.subNodes[k];
-        if (n.b == 0) return ID_SUB | (uint32_t)(nRefPairs + subPairOf[k]);
-        return ID_SUB | ID_TRI | ((uint32_t)(n.b - 1) << 26) | (uint32_t)n.a;
-    };
-    std::vector<float4> hPairs(((size_t)nRefPairs + nSubPairs) * 4);
+    (void)ID_TRI; (void)ID_SUB;
+    std::vector<float4> hPairs((size_t)nRefPairs * 4);
     for (size_t i = 0; i < NN; i++) {
         const HostNode& n = s->bvh.nodes[i];
         if (n.isLeaf) continue;
@@ -433,14 +425,22 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
         pack(l.lo, l.hi, refId(n.child0), (uint32_t)n.child0, out);
         pack(r.lo, r.hi, refId(n.child1), (uint32_t)n.child1, out + 2);
     }
-    for (size_t j = 0; j < s->bvh.subNodes.size(); j++) {
-        const SubNode& n = s->bvh.subNodes[j];
-        if (n.b != 0) continue;
-        float4* out = hPairs.data() + 4 * (size_t)(nRefPairs + subPairOf[j]);
-        const SubNode &l = s->bvh.subNodes[n.a], &r = s->bvh.subNodes[n.a + 1];
-        pack(l.lo, l.hi, subId(n.a), 0u, out);
-        pack(r.lo, r.hi, subId(n.a + 1), 0u, out + 2);
+    std::vector<float4> hWide(s->bvh.wide.size() * 14);
+    for (size_t j = 0; j < s->bvh.wide.size(); j++) {
+        const WideNode& n = s->bvh.wide[j];
+        float4* out = hWide.data() + 14 * j;
+        for (int k = 0; k < 3; k++)
+            for (int h = 0; h < 2; h++) {
+                out[2 * k + h] = make_float4(n.lo[4 * h][k], n.lo[4 * h + 1][k], n.lo[4 * h + 2][k], n.lo[4 * h + 3][k]);
+                out[6 + 2 * k + h] = make_float4(n.hi[4 * h][k], n.hi[4 * h + 1][k], n.hi[4 * h + 2][k], n.hi[4 * h + 3][k]);
+            }
+        for (int h = 0; h < 2; h++) {
+            float f[4];
+            std::memcpy(f, &n.id[4 * h], 16);
+            out[12 + h] = make_float4(f[0], f[1], f[2], f[3]);
+        }
     }
+    UP(wide, hWide);
     s->dev.rootId = NN > 0 ? (int)refId(0) : 0;
     UP(pairs, hPairs);
 #undef UP
@@ -464,6 +464,7 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     s->dev.mats = s->mats.p;
     s->dev.origToLeaf = s->origToLeaf.p;
     s->dev.pairs = s->pairs.p;
+    s->dev.wide = s->wide.p;
     s->dev.nNodes = (int)NN;
     s->dev.nTris = (int)T;
     s->dev.nMeshes = d->n_meshes;

@@ -92,10 +92,12 @@ RT_DEV bool leafCandidate(const DevScene& S, int i, const V3& o, const V3& d, Le
 //
 // Node ids (child descriptors w0, stack entries, Trav::node):
 //   bits 0..25 index: pair index (inner nodes) | first triangle position (CGRT_TRI) | reference node index (CGRT_REFSCAN)
-//   bit 26  count-1 of a CGRT_TRI leaf        bit 27  CGRT_KEYAPPROX (stack only: the key is an approximate distance)
-//   bit 28  CGRT_REFLEAF: a reference leaf entered through its sub-tree (index = pair of the sub-tree root)
-//   bit 29  CGRT_TRI: sub-tree leaf           bit 30  CGRT_SUB: sub-tree semantics      bit 31  CGRT_REFSCAN: reference
-//   leaf scanned triangle by triangle (leaves too small for a sub-tree, or rays excluded from the tolerant tests)
+//   bits 26..28 count-1 of a CGRT_TRI leaf (ids with CGRT_TRI only)
+//   bit 27  CGRT_KEYAPPROX (reference stack entries only: the key is an approximate distance)
+//   bit 28  CGRT_REFLEAF: a reference leaf entered through its sub-tree (index = wide node of the sub-tree root)
+//   bit 29  CGRT_TRI: sub-tree leaf           bit 30  CGRT_SUB: sub-tree node (index = wide node unless CGRT_TRI)
+//   bit 31  CGRT_REFSCAN: reference leaf scanned triangle by triangle (leaves too small for a sub-tree, or rays excluded
+//   from the tolerant tests)
 #define CGRT_IDX_MASK 0x03ffffffu
 #define CGRT_TRICNT_SHIFT 26
 #define CGRT_KEYAPPROX 0x08000000u
@@ -127,8 +129,12 @@ struct TravStack {
 };
 
 enum { TRAV_CONTINUE = 0, TRAV_DONE = 1, TRAV_FIRED = 2 };
-enum { CLS_INNER = 0, CLS_LEAF = 1, CLS_NONE = 2 };
-RT_DEV int travClass(uint32_t node) { return (node & (CGRT_TRI | CGRT_REFSCAN)) ? CLS_LEAF : CLS_INNER; }
+enum { CLS_REF = 0, CLS_WIDE = 1, CLS_LEAF = 2, CLS_NONE = 3 };
+RT_DEV int travClass(uint32_t node)
+{
+    if (node & (CGRT_TRI | CGRT_REFSCAN)) return CLS_LEAF;
+    return (node & (CGRT_SUB | CGRT_REFLEAF)) ? CLS_WIDE : CLS_REF;
+}
 
 // intersectDataStructure (bvh.cpp:831-844): returns true iff the tree has to be traversed for this ray.
 RT_DEV bool travBegin(const DevScene& S, Trav& T, const V3& o, const V3& d, float tIn)
@@ -254,92 +260,60 @@ RT_DEV void refBoxDecide(const float4& lo, const float4& hi, const V3& o, const 
     exact = true;
 }
 
-// one step on an inner node (reference pair or sub-tree pair)
-RT_DEV int travStepInner(const DevScene& S, Trav& T, TravStack& K)
+// one step on a reference inner node: intersectNonLeaf + intersectDeeper with the reference's exact outcomes
+RT_DEV int travStepRef(const DevScene& S, Trav& T, TravStack& K)
 {
-    uint32_t id = T.node;
-    if (id & CGRT_REFLEAF) { // entering a reference leaf through its sub-tree (intersectLeaf, evaluated order-independently)
-        T.best.t = T.t; T.best.pos = -1; T.best.rank = -1; T.best.shortcut = false;
-        T.inLeaf = true;
-        T.subBase = T.sp;
-        id = (id & CGRT_IDX_MASK) | CGRT_SUB;
-    }
-    const bool isSub = (id & CGRT_SUB) != 0u;
-    const float4* pr = S.pairs + 4 * (size_t)(id & CGRT_IDX_MASK);
+    const float4* pr = S.pairs + 4 * (size_t)(T.node & CGRT_IDX_MASK);
     const float4 l0 = __ldg(pr), l1 = __ldg(pr + 1), r0 = __ldg(pr + 2), r1 = __ldg(pr + 3);
-    const V3 o = T.o;
+    const V3 o = T.o, d = T.d;
     float tinL, toutL, tinR, toutR;
     slabApprox(l0, l1, o, T.inv, tinL, toutL);
     slabApprox(r0, r1, o, T.inv, tinR, toutR);
     uint32_t idL = (uint32_t)f2i(l0.w), idR = (uint32_t)f2i(r0.w);
+    if (!T.useSub) { // this ray scans reference leaves instead of using their sub-trees
+        if (idL & CGRT_REFLEAF) idL = CGRT_REFSCAN | (uint32_t)f2i(l1.w);
+        if (idR & CGRT_REFLEAF) idR = CGRT_REFSCAN | (uint32_t)f2i(r1.w);
+    }
+    bool hL, hR, exL = true, exR = true;
+    float tL = -1.0f, tR = -1.0f;
+    refBoxDecide(l0, l1, o, d, T.fastRef, tinL, toutL, T.t, hL, tL, exL);
+    refBoxDecide(r0, r1, o, d, T.fastRef, tinR, toutR, T.t, hR, tR, exR);
+    const bool inL = startsInBox(o, mk3(l0), mk3(l1));
+    const bool inR = startsInBox(o, mk3(r0), mk3(r1));
     uint32_t first = 0u, second = 0u;
-    bool haveFirst = false, haveSecond = false;
+    bool haveFirst = false, haveSecond = false, keyApprox = false, secondIsRight = false;
     float key = -1.0f;
-    int keyRef = 0;
-    if (isSub) {
-        // tolerant test against pre-expanded boxes; never a miss for a box that holds a point the reference could accept
-        const float slack = 1.000001f;
-        const float bt = T.best.t;
-        const bool hL = !(toutL < 0.0f || tinL > toutL * slack || tinL > bt * slack);
-        const bool hR = !(toutR < 0.0f || tinR > toutR * slack || tinR > bt * slack);
-        const bool leftFirst = tinL <= tinR;
-        if (hL && hR) {
-            first = leftFirst ? idL : idR;
-            second = leftFirst ? idR : idL;
-            key = leftFirst ? tinR : tinL;
-            haveFirst = haveSecond = true;
-        } else if (hL || hR) {
-            first = hL ? idL : idR;
-            haveFirst = true;
+    if (inL && inR) { // both visited unconditionally, left operand of `|` first (g++ order)
+        first = idL; second = idR; haveFirst = haveSecond = true; secondIsRight = true; key = -1.0f;
+    } else if (inL) {
+        first = idL; haveFirst = true;
+        if (hR) { second = idR; haveSecond = true; secondIsRight = true; key = tR; keyApprox = !exR; }
+    } else if (inR) {
+        first = idR; haveFirst = true;
+        if (hL) { second = idL; haveSecond = true; key = tL; keyApprox = !exL; }
+    } else if (hL && hR) {
+        // nearer child first: `tLeft < tRight` (bvh.cpp:626), from the approximate distances when they are separated
+        // by more than their error bounds, otherwise from the exact ones
+        bool leftFirst;
+        if (!(exL && exR) && tL + errBound(tL) < tR - errBound(tR)) leftFirst = true;
+        else if (!(exL && exR) && tL - errBound(tL) >= tR + errBound(tR)) leftFirst = false;
+        else {
+            if (!exL) { tL = boxExactT(l0, l1, o, d); exL = true; }
+            if (!exR) { tR = boxExactT(r0, r1, o, d); exR = true; }
+            leftFirst = tL < tR;
         }
-    } else {
-        // intersectNonLeaf + intersectDeeper with the reference's exact outcomes
-        const V3 d = T.d;
-        if (!T.useSub) { // this ray scans reference leaves instead of using their sub-trees
-            if (idL & CGRT_REFLEAF) idL = CGRT_REFSCAN | (uint32_t)f2i(l1.w);
-            if (idR & CGRT_REFLEAF) idR = CGRT_REFSCAN | (uint32_t)f2i(r1.w);
-        }
-        bool hL, hR, exL = true, exR = true;
-        float tL = -1.0f, tR = -1.0f;
-        refBoxDecide(l0, l1, o, d, T.fastRef, tinL, toutL, T.t, hL, tL, exL);
-        refBoxDecide(r0, r1, o, d, T.fastRef, tinR, toutR, T.t, hR, tR, exR);
-        const bool inL = startsInBox(o, mk3(l0), mk3(l1));
-        const bool inR = startsInBox(o, mk3(r0), mk3(r1));
-        bool keyApprox = false, secondIsRight = false;
-        if (inL && inR) { // both visited unconditionally, left operand of `|` first (g++ order)
-            first = idL; second = idR; haveFirst = haveSecond = true; secondIsRight = true; key = -1.0f;
-        } else if (inL) {
-            first = idL; haveFirst = true;
-            if (hR) { second = idR; haveSecond = true; secondIsRight = true; key = tR; keyApprox = !exR; }
-        } else if (inR) {
-            first = idR; haveFirst = true;
-            if (hL) { second = idL; haveSecond = true; key = tL; keyApprox = !exL; }
-        } else if (hL && hR) {
-            // nearer child first: `tLeft < tRight` (bvh.cpp:626), from the approximate distances when they are separated
-            // by more than their error bounds, otherwise from the exact ones
-            bool leftFirst;
-            if (!(exL && exR) && tL + errBound(tL) < tR - errBound(tR)) leftFirst = true;
-            else if (!(exL && exR) && tL - errBound(tL) >= tR + errBound(tR)) leftFirst = false;
-            else {
-                if (!exL) { tL = boxExactT(l0, l1, o, d); exL = true; }
-                if (!exR) { tR = boxExactT(r0, r1, o, d); exR = true; }
-                leftFirst = tL < tR;
-            }
-            haveFirst = haveSecond = true;
-            if (leftFirst) { first = idL; second = idR; secondIsRight = true; key = tR; keyApprox = !exR; }
-            else { first = idR; second = idL; key = tL; keyApprox = !exL; }
-        } else if (hL) {
-            first = idL; haveFirst = true;
-        } else if (hR) {
-            first = idR; haveFirst = true;
-        }
-        if (keyApprox) second |= CGRT_KEYAPPROX;
-        keyRef = f2i(secondIsRight ? r1.w : l1.w);
+        haveFirst = haveSecond = true;
+        if (leftFirst) { first = idL; second = idR; secondIsRight = true; key = tR; keyApprox = !exR; }
+        else { first = idR; second = idL; key = tL; keyApprox = !exL; }
+    } else if (hL) {
+        first = idL; haveFirst = true;
+    } else if (hR) {
+        first = idR; haveFirst = true;
     }
     if (haveSecond) {
-        K.n[T.sp] = second;
+        K.n[T.sp] = keyApprox ? (second | CGRT_KEYAPPROX) : second;
         K.t[T.sp] = key;
-        K.r[T.sp] = keyRef;
+        K.r[T.sp] = f2i(secondIsRight ? r1.w : l1.w);
         T.sp++;
     }
     if (haveFirst) {
@@ -347,6 +321,66 @@ RT_DEV int travStepInner(const DevScene& S, Trav& T, TravStack& K)
         return TRAV_CONTINUE;
     }
     return travPop(S, T, K);
+}
+
+// one step on an 8-wide sub-tree node: tolerant tests of all children against their pre-expanded boxes (never a miss for a
+// box that holds a point the reference could accept); the nearest hit child is visited next, the others are stacked with
+// their entry distance and pruned against the leaf's best distance when popped
+RT_DEV int travStepWide(const DevScene& S, Trav& T, TravStack& K)
+{
+    uint32_t id = T.node;
+    if (id & CGRT_REFLEAF) { // entering a reference leaf through its sub-tree (intersectLeaf, evaluated order-independently)
+        T.best.t = T.t; T.best.pos = -1; T.best.rank = -1; T.best.shortcut = false;
+        T.inLeaf = true;
+        T.subBase = T.sp;
+    }
+    const float4* w = S.wide + 14 * (size_t)(id & CGRT_IDX_MASK);
+    const float slack = 1.000001f;
+    const float bt = T.best.t * slack;
+    const V3 o = T.o, inv = T.inv;
+    float tin[8];
+    uint32_t cid[8];
+    unsigned hitMask = 0u;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const float4 lx = __ldg(w + 0 + h), ly = __ldg(w + 2 + h), lz = __ldg(w + 4 + h);
+        const float4 hx = __ldg(w + 6 + h), hy = __ldg(w + 8 + h), hz = __ldg(w + 10 + h);
+        const float4 ci = __ldg(w + 12 + h);
+        const float lox[4] = {lx.x, lx.y, lx.z, lx.w}, loy[4] = {ly.x, ly.y, ly.z, ly.w}, loz[4] = {lz.x, lz.y, lz.z, lz.w};
+        const float hix[4] = {hx.x, hx.y, hx.z, hx.w}, hiy[4] = {hy.x, hy.y, hy.z, hy.w}, hiz[4] = {hz.x, hz.y, hz.z, hz.w};
+        const float cw[4] = {ci.x, ci.y, ci.z, ci.w};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float q0x = (lox[c] - o.x) * inv.x, q1x = (hix[c] - o.x) * inv.x;
+            const float q0y = (loy[c] - o.y) * inv.y, q1y = (hiy[c] - o.y) * inv.y;
+            const float q0z = (loz[c] - o.z) * inv.z, q1z = (hiz[c] - o.z) * inv.z;
+            const float ti = fmaxf(fmaxf(fminf(q0x, q1x), fminf(q0y, q1y)), fminf(q0z, q1z));
+            const float to = fminf(fminf(fmaxf(q0x, q1x), fmaxf(q0y, q1y)), fmaxf(q0z, q1z));
+            const uint32_t ii = (uint32_t)f2i(cw[c]);
+            const bool hit = ii != 0u && !(to < 0.0f || ti > to * slack || ti > bt);
+            tin[4 * h + c] = ti;
+            cid[4 * h + c] = ii;
+            if (hit) hitMask |= 1u << (4 * h + c);
+        }
+    }
+    if (hitMask == 0u) return travPop(S, T, K);
+    // nearest hit child first
+    int best = -1;
+    float bestT = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        if ((hitMask >> c & 1u) && (best < 0 || tin[c] < bestT)) { best = c; bestT = tin[c]; }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        if ((hitMask >> c & 1u) && c != best) {
+            K.n[T.sp] = cid[c];
+            K.t[T.sp] = tin[c];
+            T.sp++;
+        }
+    }
+    T.node = cid[best];
+    return TRAV_CONTINUE;
 }
 
 // one step on a leaf: the triangles of a sub-tree leaf (folded into the reference leaf's running best), or a whole
@@ -364,7 +398,7 @@ RT_DEV int travStepLeaf(const DevScene& S, Trav& T, TravStack& K, float eps, flo
         T.best.t = T.t; T.best.pos = -1; T.best.rank = -1; T.best.shortcut = false;
     } else {
         first = (int)(id & CGRT_IDX_MASK);
-        count = (int)((id >> CGRT_TRICNT_SHIFT) & 1u) + 1;
+        count = (int)((id >> CGRT_TRICNT_SHIFT) & 7u) + 1;
     }
 #pragma unroll 1
     for (int i = first; i < first + count; i++) {
@@ -379,7 +413,9 @@ RT_DEV int travStepLeaf(const DevScene& S, Trav& T, TravStack& K, float eps, flo
 template <bool ANY>
 RT_DEV int travStep(const DevScene& S, Trav& T, TravStack& K, float eps, float maxDist)
 {
-    if (travClass(T.node) == CLS_INNER) return travStepInner(S, T, K);
+    const int cls = travClass(T.node);
+    if (cls == CLS_REF) return travStepRef(S, T, K);
+    if (cls == CLS_WIDE) return travStepWide(S, T, K);
     return travStepLeaf<ANY>(S, T, K, eps, maxDist);
 }
 

@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(128) k_shadow(DevScene S, const FrameParams* _
 // vote weights ~ 1 / (instructions of one step of the class): exact reference node ~260, tolerant sub-tree node ~60,
 // sub-tree leaf (<= 2 exact triangle tests) ~120
 #ifndef CGRT_STEPS_PER_ROUND
-#define CGRT_STEPS_PER_ROUND 12
+#define CGRT_STEPS_PER_ROUND 24
 #endif
 #ifndef CGRT_VOTE
 #define CGRT_VOTE 1
@@ -415,9 +415,10 @@ __global__ void __launch_bounds__(128) k_shadow(DevScene S, const FrameParams* _
 #endif
 #define CGRT_REFILL_MIN_IDLE 6
 // vote weights of the two node classes (lanes x weight, larger wins): plain majority by default
-#ifndef CGRT_W_INNER
-#define CGRT_W_INNER 1
-#define CGRT_W_LEAF 1
+#ifndef CGRT_W_REF
+#define CGRT_W_REF 1
+#define CGRT_W_WIDE 1
+#define CGRT_W_LEAF 2
 #endif
 struct Tuning {
     int steps = 12;  // traversal steps between two refill / retire rounds
@@ -563,14 +564,18 @@ RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCou
             continue;
 #endif
             const int cls = run ? travClass(T.node) : CLS_NONE;
-            const int s0 = __popc(__ballot_sync(0xffffffffu, cls == CLS_INNER)) * CGRT_W_INNER;
-            const int s1 = __popc(__ballot_sync(0xffffffffu, cls == CLS_LEAF)) * CGRT_W_LEAF;
-            if ((s0 | s1) == 0) break;
-            if (s0 >= s1) {
-                INSTR_ADD(2, 1); INSTR_ADD(5, s0 / CGRT_W_INNER);
-                if (cls == CLS_INNER) state = travStepInner(S, T, K);
+            const int s0 = __popc(__ballot_sync(0xffffffffu, cls == CLS_REF)) * CGRT_W_REF;
+            const int s1 = __popc(__ballot_sync(0xffffffffu, cls == CLS_WIDE)) * CGRT_W_WIDE;
+            const int s2 = __popc(__ballot_sync(0xffffffffu, cls == CLS_LEAF)) * CGRT_W_LEAF;
+            if ((s0 | s1 | s2) == 0) break;
+            if (s0 >= s1 && s0 >= s2) {
+                INSTR_ADD(2, 1); INSTR_ADD(5, s0 / CGRT_W_REF);
+                if (cls == CLS_REF) state = travStepRef(S, T, K);
+            } else if (s1 >= s2) {
+                INSTR_ADD(3, 1); INSTR_ADD(6, s1 / CGRT_W_WIDE);
+                if (cls == CLS_WIDE) state = travStepWide(S, T, K);
             } else {
-                INSTR_ADD(3, 1); INSTR_ADD(6, s1 / CGRT_W_LEAF);
+                INSTR_ADD(4, 1); INSTR_ADD(7, s2 / CGRT_W_LEAF);
                 if (cls == CLS_LEAF) state = travStepLeaf<ANY>(S, T, K, eps, maxDist);
             }
         }

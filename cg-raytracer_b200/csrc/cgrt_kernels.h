@@ -14,10 +14,11 @@
 // triV0/1/2 : float4 per triangle: position.xyz ; triV0.w = global triangle id (bit-cast), triV1.w = mesh/material id,
 //             triV2.w = rank of the triangle in the reference's own leaf order (tie-break, see cgrt_device.cuh)
 //             Inside a reference leaf the triangles are stored in sub-tree order (bvh_build.cpp buildLeafSubTrees).
-// pairs     : the production traversal's node array: one entry of 4 x float4 per INNER node (reference node or node of a
-//             culling sub-tree), holding both children: [l.lo | l.w0] [l.hi | l.w1] [r.lo | r.w0] [r.hi | r.w1];
-//             w0 = id to visit the child with (encoding in cgrt_device.cuh), w1 = reference node index of the child
-//             (reference children only). Sub-tree boxes are pre-expanded (bvh_build.cpp). rootId = id of the root.
+// pairs     : the production traversal's reference-node array: one entry of 4 x float4 per inner reference node holding both
+//             children: [l.lo | l.w0] [l.hi | l.w1] [r.lo | r.w0] [r.hi | r.w1]; w0 = id to visit the child with (encoding
+//             in cgrt_device.cuh), w1 = reference node index of the child. rootId = id of the root.
+// wide      : 8-wide nodes of the culling sub-trees that refine the reference leaves, 14 x float4 each:
+//             lo.x[0..3] lo.x[4..7] lo.y.. lo.z.. hi.x.. hi.y.. hi.z.. id[0..3] id[4..7]; boxes pre-expanded (bvh_build.cpp)
 // triN0/1/2 : float4 per triangle: vertex normal.xyz (read only for the final hit)
 // mats      : 2 x float4 per mesh:  [kd.xyz | shininess] [ks.xyz | transparency]        (src/mesh.h:17-23)
 // spheres   : 3 x float4 per sphere: [center | radius] [kd | shininess] [ks | transparency]  (src/scene.h:36-40)
@@ -33,6 +34,7 @@ struct DevScene {
     const float4* mats;
     const float4* spheres;
     const float4* pairs;
+    const float4* wide;
     const int* origToLeaf; // global triangle id -> leaf-order index (brute-force path only)
     int nNodes;
     int nTris;

@@ -18,7 +18,7 @@ lib.cgrt_debug_instrumentation(out, 1)
 v = [int(x) for x in out]
 print("stats", st)
 print("warps %d iterations %d avg running lanes/iter %.2f" % (v[15], v[0], v[1] / max(v[0], 1)))
-for k, name in enumerate(("INNER", "LEAF")):
+for k, name in enumerate(("REF", "WIDE", "LEAF")):
     print("  class %-8s chosen %9d iterations (%.1f%%), avg lanes stepped %.2f" % (name, v[2 + k], 100.0 * v[2 + k] / max(v[0], 1), v[5 + k] / max(v[2 + k], 1)))
 print("refill rounds %d lanes %d (%.1f/round); retire rounds %d lanes %d (%.1f/round)" % (v[8], v[9], v[9] / max(v[8], 1), v[10], v[11], v[11] / max(v[10], 1)))
 tot = v[12] + v[13] + v[14]
