@@ -216,15 +216,15 @@ def main():
     d = capi.dragon_standin()
     scene = capi.Scene(d, lights=d.lights, device=local_rank)
     cam = capi.make_camera(WIDTH, HEIGHT)
-    R = distributed.TiledRenderer(scene, WIDTH, HEIGHT, TRACE_LIMIT, rank, world, local_rank)
+    R = distributed.TiledRenderer(scene, WIDTH, HEIGHT, TRACE_LIMIT, rank, world, local_rank,
+                                  mode=os.environ.get("CGRT_EXCHANGE"))  # p2p (default) | nccl
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # ---- untimed: warm-up, ray counts, reference test counts (algorithmic bytes), per-class kernel times
     for _ in range(args.warmup):
         R.render_device(cam)
     barrier()
-    R.render_device(cam, flags=capi.RENDER_COUNT)
-    st_count = scene.collect_stats()
+    st_count = R.count_pass(cam)
     R.render_device(cam, flags=capi.RENDER_PROFILE_ALL)
     st_prof = scene.collect_stats()
     rays_local = st_count["primary"] + st_count["shadow"] + st_count["bounce"]
@@ -263,7 +263,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = rays_frame * args.steps / (total_ms * 1e-3) / 1e6
-    launches_per_step = int(st["kernel_launches"]) + (1 if (world > 1 and rank == 0) else 0)
+    launches_per_step = int(st["kernel_launches"]) + R.extra_launches_per_frame()
+    timeouts = R.timeouts()
 
     # ---- end to end: host-buffer API, per-frame H2D of camera + lights, D2H of the float frame to pinned memory
     for _ in range(2):
@@ -305,7 +306,10 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (procedural dragon stand-in; data/dragon.obj is not in the reference checkout)",
             "config": {"workload": workload_name(d.n_triangles), "l2": "flushed between timed frames (256 MiB memset outside the event pair)",
-                       "parallelism": f"tiles{world}" if world > 1 else "single", "tile": "8x8 interleaved, row skew 3",
+                       "parallelism": f"tiles{world}" if world > 1 else "single", "tile": "8x8 interleaved, row skew 3, centre-out order",
+                       "exchange": {"single": "none", "p2p": "direct stores into rank 0's frame over NVLink peer memory + arrival/consumed flags",
+                                    "nccl": "NCCL gather of tile-major buffers + assemble kernel"}[R.mode],
+                       "exchange_fallback_reason": R.fallback_reason, "handoff_timeouts": timeouts,
                        "rays_per_frame": {"primary": n_primary, "shadow": n_shadow, "bounce": n_bounce},
                        "kernel_ms_per_frame_rank0": dict(zip(capi.KERNEL_CLASS_NAMES, [round(v, 4) for v in st_prof["class_ms"]])),
                        "kernel_launches_per_frame": dict(zip(capi.KERNEL_CLASS_NAMES, st_prof["class_launches"])),

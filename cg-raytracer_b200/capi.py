@@ -74,6 +74,8 @@ EXPORTS = [
     "cgrt_ray_sphere", "cgrt_generate_rays", "cgrt_render", "cgrt_render_device", "cgrt_render_collect_stats",
     "cgrt_tile_buffer_floats", "cgrt_tile_list", "cgrt_assemble_tiles", "cgrt_quantize_rgba8", "cgrt_device_malloc", "cgrt_device_free",
     "cgrt_host_alloc_pinned", "cgrt_host_free_pinned", "cgrt_memcpy_h2d", "cgrt_memcpy_d2h", "cgrt_device_synchronize",
+    "cgrt_memset_device", "cgrt_memcpy_d2h_async", "cgrt_peer_export", "cgrt_peer_open", "cgrt_peer_close",
+    "cgrt_flag_signal", "cgrt_flag_wait",
 ]
 
 _lib = None
@@ -130,6 +132,13 @@ def load_library(path=None):
         "cgrt_memcpy_h2d": (C.c_int, [C.c_int, vp, vp, sz]),
         "cgrt_memcpy_d2h": (C.c_int, [C.c_int, vp, vp, sz]),
         "cgrt_device_synchronize": (C.c_int, [C.c_int]),
+        "cgrt_memset_device": (C.c_int, [C.c_int, vp, C.c_int, sz, vp]),
+        "cgrt_memcpy_d2h_async": (C.c_int, [C.c_int, vp, vp, sz, vp]),
+        "cgrt_peer_export": (C.c_int, [C.c_int, vp, u8p]),
+        "cgrt_peer_open": (C.c_int, [C.c_int, u8p, C.POINTER(vp)]),
+        "cgrt_peer_close": (C.c_int, [C.c_int, vp]),
+        "cgrt_flag_signal": (C.c_int, [C.c_int, C.POINTER(vp), i32, C.c_uint32, vp]),
+        "cgrt_flag_wait": (C.c_int, [C.c_int, vp, i32, C.c_uint32, C.c_uint32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header/library drift
@@ -174,7 +183,8 @@ def make_camera(W, H, fovy_deg=50.0, dist=3.0, look_at=(0.0, 0.0, 0.0), euler_de
 K_PRIMARY, K_BOUNCE, K_SHADOW, K_SHADE = 0, 1, 2, 3
 # production (path pipeline) kernels per class; class 1 is only launched by the level-by-level counting pipeline
 KERNEL_CLASS_NAMES = ["k_paths", "k_bounce_closest", "k_shadow_all", "k_shade_paths"]
-RENDER_PROFILE_ALL, RENDER_COUNT = 0xF, 0x100
+RENDER_PROFILE_ALL, RENDER_COUNT, RENDER_SCREEN_LAYOUT = 0xF, 0x100, 0x200
+IPC_HANDLE_BYTES = 64
 
 
 def render_params(W, H, trace_limit=2, rank=0, world=1, tile_w=0, tile_h=0, flags=0):

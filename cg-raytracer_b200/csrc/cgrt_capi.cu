@@ -17,7 +17,7 @@
 
 using namespace cgrt;
 #ifdef CGRT_INSTRUMENT
-namespace cgrt { void readInstrumentation(unsigned long long* out, bool reset); }
+namespace cgrt { void readInstrumentation(unsigned long long* out, bool reset); void readTimeline(unsigned int* out, bool reset); }
 #endif
 
 static thread_local std::string g_err;
@@ -201,7 +201,10 @@ struct cgrt_scene {
     std::vector<cudaEvent_t> traceEvents;
     WaveTrace trace{};
     bool lastCounted = false;
-    std::vector<int> tileListHost;
+    // tile partition of the current frame geometry (rebuilt only when width/height/tile/world/rank change)
+    TileLayout layout;
+    DevBuf<int2> tileSeq; // production order: (global tile id, local tile index), centre-out
+    uint64_t primaryPixels = 0; // pixels of this rank inside the image
     int tileKey[6] = {0, 0, 0, 0, 0, 0};
     DevBuf<float> frame; // internal framebuffer for the host-pointer render
     float* hFramePinned = nullptr;
@@ -233,7 +236,7 @@ static void destroyScene(cgrt_scene* s)
     s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
     s->triN0.release(); s->triN1.release(); s->triN2.release(); s->mats.release(); s->spheres.release();
     s->origToLeaf.release(); s->pairs.release(); s->wide.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
-    s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->frame.release();
+    s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->tileSeq.release(); s->frame.release();
     s->tests.release(); s->hitRec.release(); s->hitList.release(); s->pathDepth.release();
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->hParamRing) cudaFreeHost(s->hParamRing);
@@ -809,10 +812,39 @@ int cgrt_tile_list(const cgrt_render_params* p, int32_t rank, int32_t* out, int3
 }
 
 static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, FrameParams& P,
-                        const int** dTileList)
+                        const int** dTileList, const int2** dTileSeq)
 {
-    TileLayout L;
-    makeTileLayout(*p, L);
+    const int tw = p->tile_w > 0 ? p->tile_w : 8, th = p->tile_h > 0 ? p->tile_h : 8;
+    const int key[6] = {p->width, p->height, tw, th, p->world, p->rank};
+    if (std::memcmp(key, s->tileKey, sizeof key) != 0 || !s->tileSeq.p) {
+        TileLayout& L = s->layout;
+        makeTileLayout(*p, L);
+        const std::vector<int>& mine = L.lists[p->rank];
+        // processing order: tiles sorted by the distance of their centre from the image centre. Scenes are normalised around
+        // the look-at point (mesh.cpp:143-166), so the object - and with it every long mirror chain - projects to the middle
+        // of the frame: those paths start first, the border tiles whose rays miss the root box fill the end of the launch.
+        std::vector<int2> seq(mine.size());
+        std::vector<std::pair<float, int>> order(mine.size());
+        s->primaryPixels = 0;
+        for (size_t lt = 0; lt < mine.size(); lt++) {
+            const int ty = mine[lt] / L.tilesX, tx = mine[lt] % L.tilesX;
+            const float cx = (tx + 0.5f) * L.tileW - 0.5f * p->width, cy = (ty + 0.5f) * L.tileH - 0.5f * p->height;
+            order[lt] = std::make_pair(cx * cx + cy * cy, (int)lt);
+            const int w = std::min(L.tileW, p->width - tx * L.tileW), h = std::min(L.tileH, p->height - ty * L.tileH);
+            s->primaryPixels += (uint64_t)w * h;
+        }
+        std::sort(order.begin(), order.end());
+        for (size_t k = 0; k < order.size(); k++) seq[k] = make_int2(mine[order[k].second], order[k].second);
+        RC(s->tileList.ensure(std::max<size_t>(mine.size(), 1)));
+        RC(s->tileSeq.ensure(std::max<size_t>(mine.size(), 1)));
+        CK(cudaDeviceSynchronize()); // a previous frame may still read the old lists
+        if (!mine.empty()) {
+            CK(cudaMemcpy(s->tileList.p, mine.data(), mine.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(s->tileSeq.p, seq.data(), seq.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        }
+        std::memcpy(s->tileKey, key, sizeof key);
+    }
+    const TileLayout& L = s->layout;
     std::memset(&P, 0, sizeof P);
     cameraConstants(*cam, P);
     P.width = p->width;
@@ -824,20 +856,10 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
     P.tilesX = L.tilesX;
     P.world = L.world;
     P.rank = p->rank;
-    const std::vector<int>& mine = L.lists[p->rank];
-    P.nSlots = (int)mine.size() * L.tileW * L.tileH;
-    *dTileList = nullptr;
-    if (L.world > 1) {
-        const int key[6] = {p->width, p->height, L.tileW, L.tileH, L.world, p->rank};
-        if (std::memcmp(key, s->tileKey, sizeof key) != 0 || !s->tileList.p) {
-            RC(s->tileList.ensure(mine.size()));
-            CK(cudaDeviceSynchronize()); // a previous frame may still read the old list
-            if (!mine.empty())
-                CK(cudaMemcpy(s->tileList.p, mine.data(), mine.size() * sizeof(int), cudaMemcpyHostToDevice));
-            std::memcpy(s->tileKey, key, sizeof key);
-        }
-        *dTileList = s->tileList.p;
-    }
+    P.screenLayout = (L.world == 1 || (p->flags & CGRT_RENDER_SCREEN_LAYOUT)) ? 1 : 0;
+    P.nSlots = (int)L.lists[p->rank].size() * L.tileW * L.tileH;
+    *dTileList = L.world > 1 ? s->tileList.p : nullptr;
+    *dTileSeq = s->tileSeq.p;
     // queues sized for the worst case (every pixel hits, every hit bounces); only the used prefix is touched
     const size_t cap = (size_t)std::max(P.nSlots, 1);
     const int nL = std::max(P.nLights, 1);
@@ -881,7 +903,10 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
     cudaStream_t st = (cudaStream_t)stream;
     FrameParams P;
     const int* dTiles = nullptr;
-    RC(prepareFrame(s, cam, p, P, &dTiles));
+    const int2* dSeq = nullptr;
+    RC(prepareFrame(s, cam, p, P, &dTiles, &dSeq));
+    if (P.screenLayout && P.world > 1 && (p->flags & CGRT_RENDER_COUNT))
+        return fail(CGRT_ERR_INVALID, "CGRT_RENDER_COUNT renders into the tile-major buffer; it cannot be combined with CGRT_RENDER_SCREEN_LAYOUT");
     // per-frame upload (camera constants + lights, read live from the scene like src/main.cpp:835-876 allows)
     unsigned char* slot = s->hParamRing + (size_t)s->ringPos * s->paramBlockBytes;
     s->ringPos = (s->ringPos + 1) % cgrt_scene::RING;
@@ -930,7 +955,7 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
         PB.cap = B.cap;
         PB.levels = std::max(P.traceLimit, 1);
         launches = launchPathPipeline(s->dev, (const FrameParams*)s->dParamBlock.p, P,
-                                      (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), PB, dTiles, d_out,
+                                      (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), PB, dSeq, d_out,
                                       s->di.numSMs, &s->trace, st);
     }
     s->lastPathPipeline = !countTests;
@@ -956,19 +981,7 @@ int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
     CK(cudaMemcpy(counts, s->counts.p, sizeof counts, cudaMemcpyDeviceToHost));
     const FrameParams& P = s->lastParams;
     // logical rays: primary = pixels of this rank inside the image
-    uint64_t primary = 0;
-    {
-        cgrt_render_params rp;
-        std::memset(&rp, 0, sizeof rp);
-        rp.width = P.width; rp.height = P.height; rp.world = P.world; rp.rank = P.rank; rp.tile_w = P.tileW; rp.tile_h = P.tileH;
-        TileLayout L;
-        makeTileLayout(rp, L);
-        for (int g : L.lists[P.rank]) {
-            const int ty = g / L.tilesX, tx = g % L.tilesX;
-            const int w = std::min(L.tileW, P.width - tx * L.tileW), h = std::min(L.tileH, P.height - ty * L.tileH);
-            primary += (uint64_t)w * h;
-        }
-    }
+    const uint64_t primary = s->primaryPixels;
     stats->primary = primary;
     if (s->lastPathPipeline) {
         stats->primary_hit = (uint64_t)counts[CGRT_CNT_PATHS];
@@ -1008,6 +1021,8 @@ int cgrt_render(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params*
     if (!s || !cam || !rgb) return fail(CGRT_ERR_INVALID, "null argument");
     RC(checkRenderParams(p));
     RC(useSceneDevice(s));
+    if (p->world > 1 && (p->flags & CGRT_RENDER_SCREEN_LAYOUT))
+        return fail(CGRT_ERR_INVALID, "CGRT_RENDER_SCREEN_LAYOUT is a device-pointer mode (cgrt_render_device)");
     const size_t frameFloats = (size_t)p->width * p->height * 3;
     const size_t outFloats = cgrt_tile_buffer_floats(p);
     {
@@ -1099,7 +1114,64 @@ int cgrt_quantize_rgba8(int device, const float* d_frame, size_t n_pixels, uint8
 
 #ifdef CGRT_INSTRUMENT
 void cgrt_debug_instrumentation(unsigned long long* out, int reset) { cgrt::readInstrumentation(out, reset != 0); }
+void cgrt_debug_timeline(unsigned int* out, int reset) { cgrt::readTimeline(out, reset != 0); }
 #endif
+
+// ---- peer memory + frame hand-off flags (multi-GPU, one process per GPU) ---------------------------------------------
+int cgrt_peer_export(int device, void* d_ptr, uint8_t* handle)
+{
+    if (!d_ptr || !handle) return fail(CGRT_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == CGRT_IPC_HANDLE_BYTES, "IPC handle size");
+    RC(useDevice(device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, d_ptr));
+    std::memcpy(handle, &h, sizeof h);
+    return CGRT_OK;
+}
+int cgrt_peer_open(int device, const uint8_t* handle, void** out)
+{
+    if (!handle || !out) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    CK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return CGRT_OK;
+}
+int cgrt_peer_close(int device, void* p)
+{
+    RC(useDevice(device));
+    CK(cudaIpcCloseMemHandle(p));
+    return CGRT_OK;
+}
+int cgrt_flag_signal(int device, uint32_t* const* d_flags, int32_t n, uint32_t seq, void* stream)
+{
+    if (n < 0 || n > CGRT_MAX_PEERS || (n && !d_flags)) return fail(CGRT_ERR_INVALID, "bad flag list");
+    RC(useDevice(device));
+    launchFlagSignal(d_flags, n, seq, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return CGRT_OK;
+}
+int cgrt_flag_wait(int device, const uint32_t* d_flags, int32_t n, uint32_t seq, uint32_t timeout_ms, uint32_t* d_status,
+                   void* stream)
+{
+    if (n < 0 || n > 1024 || (n && !d_flags)) return fail(CGRT_ERR_INVALID, "bad flag list");
+    RC(useDevice(device));
+    launchFlagWait(d_flags, n, seq, (unsigned long long)timeout_ms * 1000000ull, d_status, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return CGRT_OK;
+}
+int cgrt_memset_device(int device, void* p, int value, size_t bytes, void* stream)
+{
+    RC(useDevice(device));
+    CK(cudaMemsetAsync(p, value, bytes, (cudaStream_t)stream));
+    return CGRT_OK;
+}
+int cgrt_memcpy_d2h_async(int device, void* dst, const void* src, size_t bytes, void* stream)
+{
+    RC(useDevice(device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return CGRT_OK;
+}
 
 // ---- memory helpers ------------------------------------------------------------------------------------------------
 int cgrt_device_malloc(int device, size_t bytes, void** out)

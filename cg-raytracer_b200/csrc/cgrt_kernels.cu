@@ -227,6 +227,24 @@ RT_DEV bool slotToPixel(const FrameParams& P, const int* __restrict__ tileList, 
     return true;
 }
 
+// production form: processing position -> (global tile id, local tile index) through the per-frame tile sequence (tiles in
+// centre-out order so that the long mirror chains of the object start first and the trivially missing border pixels fill the
+// end of the launch). outIdx: Screen layout when P.screenLayout (single GPU, or direct writes into the peer-mapped frame of
+// rank 0), else the position in this rank's tile-major buffer; `local` is that position in either case.
+RT_DEV bool seqToPixel(const FrameParams& P, const int2* __restrict__ tileSeq, int slot, int& x, int& y, int& outIdx, int& local)
+{
+    const int tpx = P.tileW * P.tileH;
+    const int k = slot / tpx, q = slot - k * tpx;
+    const int2 e = __ldg(tileSeq + k);
+    const int ty = e.x / P.tilesX, tx = e.x - ty * P.tilesX;
+    x = tx * P.tileW + q % P.tileW;
+    y = ty * P.tileH + q / P.tileW;
+    local = e.y * tpx + q;
+    if (x >= P.width || y >= P.height) return false;
+    outIdx = P.screenLayout ? ((P.height - 1 - y) * P.width + x) : local; // Screen::setPixel row flip, src/screen.cpp:34
+    return true;
+}
+
 // warp-aggregated queue push: one atomic per warp, slots handed out by lane rank (ballot / popc / shfl)
 RT_DEV int warpPush(int* counter, bool want)
 {
@@ -465,6 +483,9 @@ static const Tuning& tuning()
 // class k, [8] refill rounds, [9] lanes refilled, [10] retire rounds, [11] lanes retired, [12] cycles in steps,
 // [13] cycles in refill, [14] cycles in retire, [15] warps
 __device__ unsigned long long g_instr[16];
+// timeline: per kernel kind (0 closest, 1 any) and 25 us bucket since the first burst of the launch: [warps bursting, lanes running]
+__device__ unsigned long long g_t0[2];
+__device__ unsigned int g_tl[2][128][2];
 // the value is evaluated by ALL lanes (it may contain warp collectives); lane 0 adds it
 #define INSTR_ADD(i, v) do { const unsigned long long v_ = (unsigned long long)(v); if ((threadIdx.x & 31) == 0) atomicAdd(&g_instr[i], v_); } while (0)
 #else
@@ -551,6 +572,19 @@ RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCou
         // latency for not paying all three code paths on every iteration.
 #ifdef CGRT_INSTRUMENT
         const long long cs0 = clock64();
+        {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            const int nRun = __popc(__ballot_sync(0xffffffffu, idx >= 0 && state == TRAV_CONTINUE));
+            if (lane == 0) {
+                const unsigned long long old = atomicMin(&g_t0[ANY ? 1 : 0], now);
+                const unsigned long long t0 = old < now ? old : now;
+                int b = (int)((now - t0) / 25000ull);
+                if (b > 127) b = 127;
+                atomicAdd(&g_tl[ANY ? 1 : 0][b][0], 1u);
+                atomicAdd(&g_tl[ANY ? 1 : 0][b][1], (unsigned)nRun);
+            }
+        }
 #endif
 #pragma unroll 1
         for (int it = 0; it < CGRT_STEPS_PER_ROUND; it++) {
@@ -706,16 +740,16 @@ struct PathsPolicy {
     const DevScene& S;
     const FrameParams& P;
     const PathBuffers& B;
-    const int* tileList;
+    const int2* tileSeq;
     float* fb;
     int outIdx, level, path; // per lane
     RT_DEV bool load(int slot, V3& o, V3& d, float& tIn, float& eps, float& maxDist)
     {
-        int x, y;
+        int x, y, local;
         level = 0;
         path = -1;
-        if (!slotToPixel(P, tileList, slot, x, y, outIdx)) {
-            outIdx = -1;
+        if (!seqToPixel(P, tileSeq, slot, x, y, outIdx, local)) {
+            outIdx = -1 - local; // padding pixel of an edge tile
             return false;
         }
         o = mk3(P.camX, P.camY, P.camZ);
@@ -733,7 +767,7 @@ struct PathsPolicy {
         bool again = false;
         if (fin) {
             if (!traced) {
-                if (P.world > 1) storeRGB(fb, slot, mk3(0.0f, 0.0f, 0.0f)); // padding pixels of edge tiles
+                if (!P.screenLayout) storeRGB(fb, -1 - outIdx, mk3(0.0f, 0.0f, 0.0f)); // padding pixels (tile-major buffer)
             } else if (!hit) {
                 if (level == 0) storeRGB(fb, outIdx, mk3(0.0f, 0.0f, 0.0f)); // trace(): miss -> black, main.cpp:288-294
             } else {
@@ -782,11 +816,21 @@ struct PathsPolicy {
 };
 
 __global__ void __launch_bounds__(128, CGRT_MINBLOCKS) k_paths(DevScene S, const FrameParams* __restrict__ Pp, PathBuffers B,
-                                               const int* __restrict__ tileList, float* __restrict__ fb, int* work, Tuning U)
+                                               const int2* __restrict__ tileSeq, float* __restrict__ fb, int* work, Tuning U)
 {
     const FrameParams P = *Pp;
-    PathsPolicy pol{S, P, B, tileList, fb, -1, 0, -1};
+    PathsPolicy pol{S, P, B, tileSeq, fb, -1, 0, -1};
     persistentTraverse<false>(S, pol, P.nSlots, work, U);
+}
+
+// trace limit 0 with direct writes into a shared frame: black for this rank's pixels only
+__global__ void k_clear_tiles(const FrameParams* __restrict__ Pp, const int2* __restrict__ tileSeq, float* __restrict__ fb)
+{
+    const FrameParams P = *Pp;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < P.nSlots; slot += gridDim.x * blockDim.x) {
+        int x, y, outIdx, local;
+        if (seqToPixel(P, tileSeq, slot, x, y, outIdx, local)) storeRGB(fb, outIdx, mk3(0.0f, 0.0f, 0.0f));
+    }
 }
 
 struct ShadowAllPolicy {
@@ -1135,10 +1179,14 @@ int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams&
 }
 
 int launchPathPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
-                       const PathBuffers& B, const int* dTileList, float* fb, int numSMs, WaveTrace* tr, cudaStream_t st)
+                       const PathBuffers& B, const int2* dTileSeq, float* fb, int numSMs, WaveTrace* tr, cudaStream_t st)
 {
     cudaMemsetAsync(B.counts, 0, sizeof(int) * CGRT_CNT_TOTAL, st);
     if (hP.traceLimit <= 0) { // trace(0, ...) returns black for every pixel without casting a ray, src/main.cpp:267-272
+        if (hP.world > 1 && hP.screenLayout) { // only this rank's pixels of the shared frame
+            k_clear_tiles<<<gridFor((size_t)hP.nSlots, 128, numSMs * 16), 128, 0, st>>>(dP, dTileSeq, fb);
+            return 1;
+        }
         const size_t px = hP.world == 1 ? (size_t)hP.width * hP.height : (size_t)hP.nSlots;
         cudaMemsetAsync(fb, 0, px * 3 * sizeof(float), st);
         return 0;
@@ -1146,7 +1194,7 @@ int launchPathPipeline(const DevScene& S, const FrameParams* dP, const FramePara
     int launches = 0;
     const int persistent = numSMs * tuning().blocks;
     traceBegin(tr, 0, st);
-    k_paths<<<min(gridFor((size_t)hP.nSlots, 128, 1 << 30), persistent), 128, 0, st>>>(S, dP, B, dTileList, fb,
+    k_paths<<<min(gridFor((size_t)hP.nSlots, 128, 1 << 30), persistent), 128, 0, st>>>(S, dP, B, dTileSeq, fb,
                                                                                         B.counts + CGRT_CNT_WORK, tuning());
     traceEnd(tr, 0, st);
     launches++;
@@ -1173,6 +1221,60 @@ void launchAssemble(const float* gathered, size_t perRankFloats, const int* tile
                                                                world, tileW, tileH, tilesX, width, height, frame);
 }
 
+// =================================================================================================================
+// Frame hand-off between the GPUs of one box (one process per GPU). With CGRT_RENDER_SCREEN_LAYOUT every rank stores its
+// pixels straight into the frame of rank 0 through NVLink peer memory, so the only exchange step left is "my pixels of frame
+// `seq` have landed" (rank r -> rank 0) and "frame `seq` has been consumed, you may overwrite it" (rank 0 -> rank r):
+// 32-bit sequence numbers in device memory, written with system-scope release and polled with system-scope acquire.
+// =================================================================================================================
+struct FlagPtrs {
+    uint32_t* p[CGRT_MAX_PEERS];
+};
+
+// runs after everything enqueued before it on the stream (kernel boundary), so the stores of the shading kernels are complete
+__global__ void k_flag_signal(FlagPtrs f, int n, uint32_t seq)
+{
+    const int i = threadIdx.x;
+    if (i >= n || f.p[i] == nullptr) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[i]), "r"(seq) : "memory");
+}
+
+// one thread per flag; the kernel (and with it the stream) proceeds when every flag has reached `seq`. A peer that never
+// arrives must not hang the GPU: after `timeoutNs` the thread gives up and bumps *status.
+__global__ void k_flag_wait(const uint32_t* flags, int n, uint32_t seq, unsigned long long timeoutNs, uint32_t* status)
+{
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (true) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+        if ((int32_t)(v - seq) >= 0) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeoutNs) {
+            if (status) atomicAdd(status, 1u);
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+void launchFlagSignal(uint32_t* const* flags, int n, uint32_t seq, cudaStream_t st)
+{
+    FlagPtrs f;
+    for (int i = 0; i < CGRT_MAX_PEERS; i++) f.p[i] = i < n ? flags[i] : nullptr;
+    if (n > 0) k_flag_signal<<<1, CGRT_MAX_PEERS, 0, st>>>(f, n, seq);
+}
+
+void launchFlagWait(const uint32_t* flags, int n, uint32_t seq, unsigned long long timeoutNs, uint32_t* status, cudaStream_t st)
+{
+    if (n > 0) k_flag_wait<<<1, 32 * ((n + 31) / 32), 0, st>>>(flags, n, seq, timeoutNs, status);
+}
+
 #ifdef CGRT_INSTRUMENT
 void readInstrumentation(unsigned long long* out, bool reset)
 {
@@ -1180,6 +1282,16 @@ void readInstrumentation(unsigned long long* out, bool reset)
     if (reset) {
         unsigned long long z[16] = {0};
         cudaMemcpyToSymbol(g_instr, z, sizeof z);
+    }
+}
+void readTimeline(unsigned int* out, bool reset)
+{
+    cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned int) * 2 * 128 * 2);
+    if (reset) {
+        static unsigned int z[2 * 128 * 2];
+        cudaMemcpyToSymbol(g_tl, z, sizeof z);
+        unsigned long long m[2] = {~0ull, ~0ull};
+        cudaMemcpyToSymbol(g_t0, m, sizeof m);
     }
 }
 #endif

@@ -56,6 +56,7 @@ namespace cgrt {
 #define CGRT_CNT_HITS (CGRT_CNT_PATHS + 1)                      // path pipeline: hit records of all levels
 #define CGRT_CNT_BOUNCES (CGRT_CNT_PATHS + 2)                   // path pipeline: reflection rays traced
 #define CGRT_CNT_TOTAL (CGRT_CNT_PATHS + 3)
+#define CGRT_MAX_PEERS 32                       // flags one signal launch can write (GPUs of one box)
 #define CGRT_PARAM_BLOCK_HEADER 128             // bytes reserved for FrameParams in the per-frame block; lights follow
 
 // Per-frame constants, evaluated on the host with libm exactly as Trackball does (framework/src/trackball.cpp:70-73, 92-103)
@@ -70,6 +71,7 @@ struct FrameParams {
     int nSlots;             // local pixel slots = owned tiles * tileW * tileH
     int tileW, tileH, tilesX;
     int world, rank;
+    int screenLayout;       // 1: pixels are written at their Screen position (row H-1-y); 0: tile-major buffer of this rank
 };
 
 // Queues of the wavefront (all sized for the worst case `cap` = nSlots; only the used prefix is ever touched).
@@ -125,10 +127,12 @@ int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams&
                     const WaveBuffers& B, const int* dTileList, float* fb, int numSMs, bool countTests, WaveTrace* tr,
                     cudaStream_t st);
 int launchPathPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
-                       const PathBuffers& B, const int* dTileList, float* fb, int numSMs, WaveTrace* tr, cudaStream_t st);
+                       const PathBuffers& B, const int2* dTileSeq, float* fb, int numSMs, WaveTrace* tr, cudaStream_t st);
 void launchAssemble(const float* gathered, size_t perRankFloats, const int* tileLists, const int* tileCounts, int maxTiles,
                     int world, int tileW, int tileH, int tilesX, int width, int height, float* frame, int numSMs,
                     cudaStream_t st);
+void launchFlagSignal(uint32_t* const* flags, int n, uint32_t seq, cudaStream_t st);
+void launchFlagWait(const uint32_t* flags, int n, uint32_t seq, unsigned long long timeoutNs, uint32_t* status, cudaStream_t st);
 void launchQuantize(const float* frame, size_t nPixels, uint8_t* rgba, cudaStream_t st);
 
 } // namespace cgrt

@@ -67,12 +67,28 @@ def gather_tiles(local, rank, world):
     return out
 
 
-class TiledRenderer:
-    """Render frames of one scene on `world` GPUs. Rank r renders its interleaved tiles on its own B200; rank 0 receives all
-    tile buffers (NCCL gather over NVLink), de-interleaves them into the Screen layout and, for the end-to-end form, copies
-    the frame to pinned host memory."""
+class _DevicePtr:
+    """A raw device allocation of the library presented to torch through __cuda_array_interface__ (no copy)."""
 
-    def __init__(self, scene, width, height, trace_limit, rank=0, world=1, device=0, tile=(0, 0)):
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+
+class TiledRenderer:
+    """Render frames of one scene on `world` GPUs: full scene replica per rank, interleaved screen tiles, one exchange step.
+
+    mode "p2p" (default for world > 1): rank 0 owns the frame in device memory it exports over CUDA IPC; every other rank maps
+    it (NVLink / NVSwitch peer memory) and the kernels of cgrt_render_device store that rank's pixels straight at their final
+    Screen position (CGRT_RENDER_SCREEN_LAYOUT) - the gather is fused into the shading stores. What is left of the collective
+    is two sequence-number flags per rank: "my pixels of frame k have landed" (rank r -> rank 0, cgrt_flag_signal on the
+    peer-mapped flag, cgrt_flag_wait on rank 0) and "frame k-1 has been consumed" (rank 0 -> rank r) so a fast rank cannot
+    overwrite a frame that rank 0 is still copying out.
+    mode "nccl": every rank renders into a tile-major buffer, NCCL gather to rank 0, cgrt_assemble_tiles de-interleaves.
+    torch.distributed is the plumbing in both modes (handle exchange / gather); all compute is inside libcgrt_b200.so."""
+
+    TIMEOUT_MS = 4000
+
+    def __init__(self, scene, width, height, trace_limit, rank=0, world=1, device=0, tile=(0, 0), mode=None):
         import torch
         self.torch = torch
         self.scene = scene
@@ -82,26 +98,117 @@ class TiledRenderer:
         self.tile = tile
         self.dev = torch.device(f"cuda:{device}")
         self.params = _capi.render_params(width, height, trace_limit, rank, world, tile[0], tile[1])
-        n = _capi.tile_buffer_floats(self.params)
-        self.local = torch.empty(n, dtype=torch.float32, device=self.dev)
-        self.frame = torch.empty(height * width * 3, dtype=torch.float32, device=self.dev) if rank == 0 else None
-        self.gathered = torch.empty(n * world, dtype=torch.float32, device=self.dev) if (rank == 0 and world > 1) else None
         self.host_frame = None
         self.launches_last = 0
+        self.seq = 0
+        self.mode = "single" if world == 1 else (mode or "p2p")
+        self.fallback_reason = None
+        if self.mode == "p2p":
+            try:
+                self._init_p2p()
+            except Exception as e:  # no peer mapping between these processes: the NCCL gather is the other GPU path
+                self.fallback_reason = f"{type(e).__name__}: {e}"
+                self.mode = "nccl"
+            # all ranks must agree on the mode
+            import torch.distributed as dist
+            ok = torch.tensor([1 if self.mode == "p2p" else 0], dtype=torch.int32, device=self.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                self.mode = "nccl"
+        if self.mode != "p2p":
+            n = _capi.tile_buffer_floats(self.params)
+            self.local = torch.empty(n, dtype=torch.float32, device=self.dev)
+            self.frame = torch.empty(height * width * 3, dtype=torch.float32, device=self.dev) if rank == 0 else None
+            self.gathered = torch.empty(n * world, dtype=torch.float32, device=self.dev) if (rank == 0 and world > 1) else None
+
+    # ---- p2p set-up: rank 0 exports frame + arrival flags, every rank exports its "consumed" flag ------------------------
+    def _malloc(self, nbytes):
+        p = C.c_void_p()
+        _capi.check(self.lib.cgrt_device_malloc(self.device, nbytes, C.byref(p)))
+        _capi.check(self.lib.cgrt_memset_device(self.device, p, 0, nbytes, None))
+        return p
+
+    def _export(self, ptr):
+        h = (C.c_uint8 * _capi.IPC_HANDLE_BYTES)()
+        _capi.check(self.lib.cgrt_peer_export(self.device, ptr, h))
+        return bytes(h)
+
+    def _open(self, handle):
+        h = (C.c_uint8 * _capi.IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        p = C.c_void_p()
+        _capi.check(self.lib.cgrt_peer_open(self.device, h, C.byref(p)))
+        return p
+
+    def _init_p2p(self):
+        torch = self.torch
+        import torch.distributed as dist
+        nfl = self.H * self.W * 3
+        HB = _capi.IPC_HANDLE_BYTES
+        self.consumed = self._malloc(256)  # [0] consumed sequence number of this rank, [64] wait-timeout counter
+        self.status = C.c_void_p(self.consumed.value + 64)  # same allocation, 64 bytes in
+        mine = [self._export(self.consumed), bytes(HB), bytes(HB)]
+        if self.rank == 0:
+            self.frame_ptr = self._malloc(nfl * 4)
+            self.arrive = self._malloc(4 * max(self.world, 64))
+            mine[1], mine[2] = self._export(self.frame_ptr), self._export(self.arrive)
+        _capi.check(self.lib.cgrt_device_synchronize(self.device))
+        t = torch.tensor(list(b"".join(mine)), dtype=torch.uint8, device=self.dev)
+        allh = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(allh, t)
+        allh = [bytes(x.cpu().tolist()) for x in allh]
+        if self.rank == 0:
+            self.peer_consumed = [None] + [self._open(allh[r][0:HB]) for r in range(1, self.world)]
+            self.frame = torch.as_tensor(_DevicePtr(self.frame_ptr.value, nfl), device=self.dev)
+            self.out_ptr = self.frame_ptr
+        else:
+            self.frame = None
+            self.out_ptr = self._open(allh[0][HB:2 * HB])
+            self.peer_arrive = self._open(allh[0][2 * HB:3 * HB])
+        dist.barrier(device_ids=[self.device])
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _render_p2p(self, cam, flags):
+        p = self.params
+        p.flags = flags | _capi.RENDER_SCREEN_LAYOUT
+        st = C.c_void_p(self._stream())
+        lib, dv = self.lib, self.device
+        self.seq += 1
+        seq = self.seq
+        if self.rank == 0:
+            # everything enqueued on this stream so far (the consumer of frame seq-1) precedes this signal
+            ptrs = (C.c_void_p * (self.world - 1))(*[q.value for q in self.peer_consumed[1:]])
+            _capi.check(lib.cgrt_flag_signal(dv, ptrs, self.world - 1, seq - 1, st))
+            self.scene.render_device(cam, p, self.out_ptr.value, st.value)
+            _capi.check(lib.cgrt_flag_wait(dv, C.c_void_p(self.arrive.value + 4), self.world - 1, seq, self.TIMEOUT_MS, self.status, st))
+            return self.frame
+        _capi.check(lib.cgrt_flag_wait(dv, self.consumed, 1, seq - 1, self.TIMEOUT_MS, self.status, st))
+        self.scene.render_device(cam, p, self.out_ptr.value, st.value)
+        ptrs = (C.c_void_p * 1)(self.peer_arrive.value + 4 * self.rank)
+        _capi.check(lib.cgrt_flag_signal(dv, ptrs, 1, seq, st))
+        return None
+
+    def timeouts(self):
+        """Number of hand-off waits that gave up (0 in a healthy run); synchronises the device."""
+        if self.mode != "p2p":
+            return 0
+        v = C.c_uint32(0)
+        _capi.check(self.lib.cgrt_memcpy_d2h(self.device, C.byref(v), self.status, 4))
+        return int(v.value)
 
     def render_device(self, cam, flags=0):
         """Enqueue one frame on the current torch stream; returns the device frame tensor on rank 0 (None elsewhere).
         No host synchronisation."""
         p = self.params
-        p.flags = flags
         st = self._stream()
         if self.world == 1:
+            p.flags = flags
             self.scene.render_device(cam, p, self.frame.data_ptr(), st)
-            self.launches_last = 3 * self.L
             return self.frame
+        if self.mode == "p2p":
+            return self._render_p2p(cam, flags)
+        p.flags = flags
         import torch.distributed as dist
         self.scene.render_device(cam, p, self.local.data_ptr(), st)
         if self.rank == 0:
@@ -112,6 +219,24 @@ class TiledRenderer:
             return self.frame
         dist.gather(self.local, gather_list=None, dst=0)
         return None
+
+    def count_pass(self, cam):
+        """One frame through the counting variants (reference test counts for the roofline arithmetic) into a private
+        tile-major buffer: no exchange step, no effect on the shared frame. Returns the scene's stats."""
+        if getattr(self, "_count_buf", None) is None:
+            self._count_buf = self.torch.empty(_capi.tile_buffer_floats(self.params), dtype=self.torch.float32, device=self.dev)
+        p = self.params
+        p.flags = _capi.RENDER_COUNT
+        self.scene.render_device(cam, p, self._count_buf.data_ptr(), self._stream())
+        return self.scene.collect_stats()
+
+    def extra_launches_per_frame(self):
+        """Library kernels of the exchange step per frame on this rank (flag signal + wait, or the assemble kernel)."""
+        if self.world == 1:
+            return 0
+        if self.mode == "p2p":
+            return 2
+        return 1 if self.rank == 0 else 0
 
     def render_to_host(self, cam):
         """End to end: per-frame inputs (camera + lights) go host->device inside the call, the finished frame comes back to

@@ -116,6 +116,10 @@ enum { CGRT_K_PRIMARY = 0, CGRT_K_BOUNCE = 1, CGRT_K_SHADOW = 2, CGRT_K_SHADE = 
  * ray/triangle tests the REFERENCE traversal performs for the primary, bounce and shadow rays of the frame (shadow rays are
  * charged the reference's full closest-hit work, src/main.cpp:115). Same image; slower; meant for the roofline arithmetic. */
 #define CGRT_RENDER_COUNT 0x100
+/* world > 1 only: d_out of cgrt_render_device is a full [H][W][3] frame in Screen layout (typically the frame of rank 0,
+ * mapped into this process with cgrt_peer_open) and the kernels store this rank's pixels straight at their final position -
+ * the framebuffer "gather" is fused into the shading stores, no tile-major staging buffer, no assemble pass. */
+#define CGRT_RENDER_SCREEN_LAYOUT 0x200
 
 typedef struct cgrt_render_stats {
     uint64_t primary, primary_hit, shadow, bounce; /* logical rays, SURVEY.md §8(d) (shadow rays counted once) */
@@ -216,6 +220,24 @@ int cgrt_assemble_tiles(int device, const cgrt_render_params* p, const float* d_
 /* Screen::writeBitmapToFile quantisation (src/screen.cpp:38-49): clamp to [0,1], *255, truncate; rgba8[H*W*4], alpha 255 */
 int cgrt_quantize_rgba8(int device, const float* d_frame, size_t n_pixels, uint8_t* d_rgba8, void* stream);
 
+/* ---- multi-GPU frame hand-off over NVLink peer memory (one process per GPU) ------------------------------------------
+ * The path shards by pixels (src/main.cpp:656-697 has no inter-pixel dependence); its single exchange step is the
+ * framebuffer. Instead of a gather collective, every rank renders with CGRT_RENDER_SCREEN_LAYOUT into the frame of rank 0,
+ * which rank 0 exports and the others map:
+ *   rank 0 : cgrt_device_malloc(frame), cgrt_peer_export -> 64-byte handle, sent to the peers by the host's own plumbing
+ *   rank r : cgrt_peer_open(handle) -> device pointer valid in this process (NVLink / NVSwitch peer mapping)
+ * Completion and buffer reuse are 32-bit sequence numbers in device memory (local or peer-mapped):
+ *   cgrt_flag_signal : after everything enqueued on `stream` so far, store `seq` to each of the n flags (system-scope release)
+ *   cgrt_flag_wait   : `stream` does not proceed until all n consecutive flags are >= seq (wrap-safe); gives up after
+ *                      timeout_ms and increments *d_status (optional) so that a lost peer cannot hang the GPU. */
+#define CGRT_IPC_HANDLE_BYTES 64
+int cgrt_peer_export(int device, void* d_ptr, uint8_t* handle /* [CGRT_IPC_HANDLE_BYTES] */);
+int cgrt_peer_open(int device, const uint8_t* handle, void** out);
+int cgrt_peer_close(int device, void* p);
+int cgrt_flag_signal(int device, uint32_t* const* d_flags, int32_t n, uint32_t seq, void* stream);
+int cgrt_flag_wait(int device, const uint32_t* d_flags, int32_t n, uint32_t seq, uint32_t timeout_ms, uint32_t* d_status,
+                   void* stream);
+
 /* ---- device memory helpers for hosts that do not link the CUDA runtime themselves (ctypes / C callers) ---------------- */
 int cgrt_device_malloc(int device, size_t bytes, void** out);
 int cgrt_device_free(int device, void* p);
@@ -224,6 +246,8 @@ int cgrt_host_free_pinned(void* p);
 int cgrt_memcpy_h2d(int device, void* dst, const void* src, size_t bytes);
 int cgrt_memcpy_d2h(int device, void* dst, const void* src, size_t bytes);
 int cgrt_device_synchronize(int device);
+int cgrt_memset_device(int device, void* p, int value, size_t bytes, void* stream);
+int cgrt_memcpy_d2h_async(int device, void* dst, const void* src, size_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

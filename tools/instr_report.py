@@ -13,6 +13,8 @@ cam = capi.make_camera(W, H)
 s.render(cam, W, H, trace_limit=L)
 out = (C.c_ulonglong * 16)()
 lib.cgrt_debug_instrumentation(out, 1)
+tl = (C.c_uint * 512)()
+lib.cgrt_debug_timeline(tl, 1)
 _, st = s.render(cam, W, H, trace_limit=L)
 lib.cgrt_debug_instrumentation(out, 1)
 v = [int(x) for x in out]
@@ -23,3 +25,10 @@ for k, name in enumerate(("REF", "WIDE", "LEAF")):
 print("refill rounds %d lanes %d (%.1f/round); retire rounds %d lanes %d (%.1f/round)" % (v[8], v[9], v[9] / max(v[8], 1), v[10], v[11], v[11] / max(v[10], 1)))
 tot = v[12] + v[13] + v[14]
 print("cycles: steps %.1f%% refill %.1f%% retire %.1f%%; per warp total %.0f cycles; per iteration %.0f cycles" % (100.0 * v[12] / tot, 100.0 * v[13] / tot, 100.0 * v[14] / tot, tot / max(v[15], 1), v[12] / max(v[0], 1)))
+
+lib.cgrt_debug_timeline(tl, 1)
+tl = np.array(list(tl)).reshape(2, 128, 2)
+for k, name in enumerate(("k_paths", "k_shadow_all")):
+    print(name, "timeline (25 us buckets): bursts | avg running lanes per bursting warp")
+    last = max([b for b in range(128) if tl[k, b, 0] > 0] + [0])
+    print("  " + " ".join("%d:%d|%.0f" % (b, tl[k, b, 0], tl[k, b, 1] / max(tl[k, b, 0], 1)) for b in range(last + 1)))
