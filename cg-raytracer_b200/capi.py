@@ -56,13 +56,14 @@ class RenderStats(C.Structure):
     _fields_ = [("primary", C.c_uint64), ("primary_hit", C.c_uint64), ("shadow", C.c_uint64), ("bounce", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("box_tests", C.c_uint64 * 3), ("tri_tests", C.c_uint64 * 3),
                 ("device_ms", C.c_float), ("class_ms", C.c_float * 4), ("class_launches", C.c_uint32 * 4),
-                ("reserved", C.c_float * 3)]
+                ("replayed_closest", C.c_uint32), ("replayed_shadow", C.c_uint32), ("reserved", C.c_float * 1)]
 
     def as_dict(self):
         return dict(primary=int(self.primary), primary_hit=int(self.primary_hit), shadow=int(self.shadow),
                     bounce=int(self.bounce), kernel_launches=int(self.kernel_launches), device_ms=float(self.device_ms),
                     box_tests=[int(v) for v in self.box_tests], tri_tests=[int(v) for v in self.tri_tests],
-                    class_ms=[float(v) for v in self.class_ms], class_launches=[int(v) for v in self.class_launches])
+                    class_ms=[float(v) for v in self.class_ms], class_launches=[int(v) for v in self.class_launches],
+                    replayed_closest=int(self.replayed_closest), replayed_shadow=int(self.replayed_shadow))
 
 
 EXPORTS = [
@@ -198,7 +199,7 @@ class Scene:
     """Device-resident scene + BVH (cgrt_scene). `flat` needs the attributes of oracle.bindings.FlatScene /
     host loader output: vcount, tcount, vertices[.,6], triangles[.,3], materials[.,8], spheres[.,12]."""
 
-    def __init__(self, flat, lights=None, device=0, bvh_max_depth=12, host_only=False, no_subtrees=False):
+    def __init__(self, flat, lights=None, device=0, bvh_max_depth=12, host_only=False, no_subtrees=False, exact_only=None):
         self.lib = load_library()
         self.device = device
         self._keep = (np.ascontiguousarray(flat.vcount, np.int32), np.ascontiguousarray(flat.tcount, np.int32),
@@ -217,7 +218,10 @@ class Scene:
         o = SceneOptions()
         o.device = device
         o.bvh_max_depth = bvh_max_depth
-        o.flags = (1 if host_only else 0) | (2 if no_subtrees else 0)  # CGRT_SCENE_HOST_ONLY | CGRT_SCENE_NO_SUBTREES
+        if exact_only is None:  # CGRT_EXACT_ONLY=1: run everything through the exact traversal (A/B for tests / profiling)
+            exact_only = os.environ.get("CGRT_EXACT_ONLY", "0") == "1"
+        # CGRT_SCENE_HOST_ONLY | CGRT_SCENE_NO_SUBTREES | CGRT_SCENE_EXACT_ONLY
+        o.flags = (1 if host_only else 0) | (2 if no_subtrees else 0) | (4 if exact_only else 0)
         h = C.c_void_p()
         check(self.lib.cgrt_scene_create(C.byref(d), C.byref(o), C.byref(h)))
         self.h = h

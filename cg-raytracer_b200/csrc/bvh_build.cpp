@@ -12,6 +12,7 @@
 #include "bvh_build.h"
 
 #include <algorithm>
+#include <functional>
 #include <cfloat>
 #include <cmath>
 #include <cstddef>
@@ -402,6 +403,99 @@ void buildLeafSubTrees(const std::vector<MeshView>& meshes, BuiltBVH& bvh, int m
         }
     }
     bvh.leafTris.swap(permuted);
+}
+
+// =================================================================================================================
+// Fast tree: the reference tree collapsed into 8-wide conservative nodes on top of the leaf sub-trees
+// =================================================================================================================
+void buildFastTree(const std::vector<MeshView>& meshes, BuiltBVH& bvh)
+{
+    const size_t NN = bvh.nodes.size();
+    bvh.fastRoot = 0u;
+    bvh.parent.assign(NN, -1);
+    bvh.triLeafNode.assign(bvh.leafTris.size(), 0);
+    if (NN == 0) return;
+    if (bvh.wideRoot.size() != NN) bvh.wideRoot.assign(NN, -1);
+    // conservative box of every reference node, bottom-up (children always have larger indices: BFS numbering)
+    std::vector<TriBox> cons(NN);
+    for (size_t i = NN; i-- > 0;) {
+        const HostNode& n = bvh.nodes[i];
+        TriBox& b = cons[i];
+        for (int k = 0; k < 3; k++) { b.lo[k] = FLT_MAX; b.hi[k] = -FLT_MAX; b.c[k] = 0.0f; }
+        if (n.isLeaf) {
+            for (int t = 0; t < n.triCount; t++) {
+                const LeafTri lt = bvh.leafTris[n.firstTri + t];
+                bvh.triLeafNode[n.firstTri + t] = (int32_t)i;
+                const MeshView& mv = meshes[lt.mesh];
+                const uint32_t* tri = mv.triangles + 3 * (size_t)lt.tri;
+                const TriBox tb = conservativeBox(mv.vertices + 6 * (size_t)tri[0], mv.vertices + 6 * (size_t)tri[1],
+                                                  mv.vertices + 6 * (size_t)tri[2]);
+                for (int k = 0; k < 3; k++) { b.lo[k] = std::min(b.lo[k], tb.lo[k]); b.hi[k] = std::max(b.hi[k], tb.hi[k]); }
+            }
+        } else {
+            bvh.parent[n.child0] = (int32_t)i;
+            bvh.parent[n.child1] = (int32_t)i;
+            for (int c = 0; c < 2; c++) {
+                const TriBox& cb = cons[c == 0 ? n.child0 : n.child1];
+                for (int k = 0; k < 3; k++) { b.lo[k] = std::min(b.lo[k], cb.lo[k]); b.hi[k] = std::max(b.hi[k], cb.hi[k]); }
+            }
+        }
+    }
+    const uint32_t ID_TRI = 0x20000000u, ID_SUB = 0x40000000u;
+    // id of a reference leaf in the fast tree: its sub-tree root, or its triangles directly (leaves without a sub-tree hold at
+    // most 7 triangles, buildLeafSubTrees), or nothing when it is empty. 0xffffffff = cannot be represented.
+    auto leafId = [&](int ni) -> uint32_t {
+        const HostNode& n = bvh.nodes[ni];
+        if (bvh.wideRoot[ni] >= 0) return ID_SUB | (uint32_t)bvh.wideRoot[ni];
+        if (n.triCount <= 0) return 0u;
+        if (n.triCount > 8) return 0xffffffffu;
+        return ID_SUB | ID_TRI | ((uint32_t)(n.triCount - 1) << 26) | (uint32_t)n.firstTri;
+    };
+    auto area = [&](int ni) -> double {
+        const TriBox& b = cons[ni];
+        const double dx = std::max(0.0, (double)b.hi[0] - b.lo[0]), dy = std::max(0.0, (double)b.hi[1] - b.lo[1]),
+                     dz = std::max(0.0, (double)b.hi[2] - b.lo[2]);
+        const double a = dx * dy + dy * dz + dz * dx;
+        return std::isfinite(a) ? a : 1e300;
+    };
+    bool ok = true;
+    // wide node for reference inner node `ni`: open the child with the largest box until eight slots are used
+    std::function<uint32_t(int)> build = [&](int ni) -> uint32_t {
+        const HostNode& n = bvh.nodes[ni];
+        if (n.isLeaf) {
+            const uint32_t id = leafId(ni);
+            if (id == 0xffffffffu) ok = false;
+            return id;
+        }
+        std::vector<int> slots{n.child0, n.child1};
+        while (slots.size() < 8) {
+            int best = -1;
+            double bestA = -1.0;
+            for (size_t c = 0; c < slots.size(); c++)
+                if (!bvh.nodes[slots[c]].isLeaf && area(slots[c]) > bestA) { bestA = area(slots[c]); best = (int)c; }
+            if (best < 0) break;
+            const HostNode& o = bvh.nodes[slots[best]];
+            slots[best] = o.child0;
+            slots.push_back(o.child1);
+        }
+        const int self = (int)bvh.wide.size();
+        bvh.wide.push_back(WideNode());
+        WideNode w;
+        for (int c = 0; c < 8; c++) {
+            for (int k = 0; k < 3; k++) { w.lo[c][k] = FLT_MAX; w.hi[c][k] = -FLT_MAX; }
+            w.id[c] = 0u;
+        }
+        for (size_t c = 0; c < slots.size(); c++) {
+            const uint32_t id = build(slots[c]);
+            if (id == 0u || id == 0xffffffffu) continue; // empty leaf: slot stays unused
+            for (int k = 0; k < 3; k++) { w.lo[c][k] = cons[slots[c]].lo[k]; w.hi[c][k] = cons[slots[c]].hi[k]; }
+            w.id[c] = id;
+        }
+        bvh.wide[self] = w;
+        return ID_SUB | (uint32_t)self;
+    };
+    const uint32_t root = build(0);
+    bvh.fastRoot = (ok && root != 0xffffffffu) ? root : 0u;
 }
 
 } // namespace cgrt

@@ -44,6 +44,11 @@ struct BuiltBVH {
     std::vector<LeafTri> leafTrisReferenceOrder; // the reference's visiting order (intersectLeaf), kept for introspection
     std::vector<WideNode> wide;
     std::vector<int32_t> wideRoot;   // per reference node: root of its sub-tree in `wide`, -1 = scan the leaf
+    // speculative ("fast") traversal, buildFastTree: one 8-wide conservative tree over ALL triangles (top = the reference tree
+    // collapsed three levels at a time, bottom = the leaf sub-trees above) + what certification of its result needs
+    uint32_t fastRoot = 0;             // id of the root in the traversal's encoding, 0 = no fast tree
+    std::vector<int32_t> parent;       // per reference node: parent index (-1 for the root)
+    std::vector<int32_t> triLeafNode;  // per position: reference leaf that holds the triangle
     int numLevels = 0;
 };
 
@@ -57,5 +62,10 @@ void buildReferenceBVH(const std::vector<MeshView>& meshes, int maxDepth, BuiltB
 // test. Triangles whose accept region cannot be bounded tightly (non-finite coordinates, minimum angle below ~0.01 rad) get
 // an unbounded box, i.e. they are always tested.
 void buildLeafSubTrees(const std::vector<MeshView>& meshes, BuiltBVH& bvh, int minLeafForSubTree = 8, int subLeafSize = 6);
+
+// The speculative traversal's tree (after buildLeafSubTrees): appends the collapsed top levels to bvh.wide and fills
+// fastRoot / parent / triLeafNode. Boxes are unions of the triangles' conservative boxes, so the tolerant slab test can never
+// cull a triangle the reference could accept, wherever it sits in the reference tree.
+void buildFastTree(const std::vector<MeshView>& meshes, BuiltBVH& bvh);
 
 } // namespace cgrt

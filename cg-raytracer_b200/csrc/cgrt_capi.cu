@@ -178,7 +178,7 @@ struct cgrt_scene {
     int nMeshes = 0;
 
     DevBuf<float4> nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, pairs, wide;
-    DevBuf<int> origToLeaf;
+    DevBuf<int> origToLeaf, refParent;
     DevScene dev{};
 
     std::vector<cgrt_point_light> lights;
@@ -196,7 +196,8 @@ struct cgrt_scene {
     DevBuf<int> pathPix, counts, tileList;
     DevBuf<unsigned long long> tests;
     DevBuf<float4> hitRec;
-    DevBuf<int> hitList, pathDepth;
+    DevBuf<int> hitList, pathDepth, replayShadow;
+    DevBuf<float4> replayQ;
     bool lastPathPipeline = false;
     std::vector<cudaEvent_t> traceEvents;
     WaveTrace trace{};
@@ -235,9 +236,9 @@ static void destroyScene(cgrt_scene* s)
     cudaSetDevice(s->device);
     s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
     s->triN0.release(); s->triN1.release(); s->triN2.release(); s->mats.release(); s->spheres.release();
-    s->origToLeaf.release(); s->pairs.release(); s->wide.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
+    s->origToLeaf.release(); s->refParent.release(); s->pairs.release(); s->wide.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->tileSeq.release(); s->frame.release();
-    s->tests.release(); s->hitRec.release(); s->hitList.release(); s->pathDepth.release();
+    s->tests.release(); s->hitRec.release(); s->hitList.release(); s->pathDepth.release(); s->replayShadow.release(); s->replayQ.release();
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->hParamRing) cudaFreeHost(s->hParamRing);
     if (s->hFramePinned) cudaFreeHost(s->hFramePinned);
@@ -330,6 +331,7 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     s->leafGlobalId.resize(T); // the reference's own leaf order (introspection); device arrays may be permuted inside leaves
     for (size_t i = 0; i < T; i++) s->leafGlobalId[i] = views[s->bvh.leafTris[i].mesh].triOffset + s->bvh.leafTris[i].tri;
     const bool subTrees = !(opt && (opt->flags & CGRT_SCENE_NO_SUBTREES));
+    const bool fastTree = subTrees && !(opt && (opt->flags & CGRT_SCENE_EXACT_ONLY));
     if (subTrees) buildLeafSubTrees(views, s->bvh);
     else {
         s->bvh.leafRank.assign(T, 0);
@@ -337,6 +339,7 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
             if (n.isLeaf)
                 for (int i = 0; i < n.triCount; i++) s->bvh.leafRank[n.firstTri + i] = i;
     }
+    if (fastTree) buildFastTree(views, s->bvh);
     if (hostOnly) { // BVH introspection only (builder tests on machines without a GPU); every query entry refuses it
         *out = s;
         return CGRT_OK;
@@ -370,7 +373,9 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
             if (k == 1) std::memcpy(&w, &lt.mesh, 4);
             if (k == 2) std::memcpy(&w, &s->bvh.leafRank[i], 4);
             hv[k][i] = make_float4(vtx[0], vtx[1], vtx[2], w);
-            hn[k][i] = make_float4(vtx[3], vtx[4], vtx[5], 0.0f);
+            float nw = 0.0f; // triN0.w: reference leaf of the triangle (certification of the speculative traversal)
+            if (k == 0 && i < s->bvh.triLeafNode.size()) std::memcpy(&nw, &s->bvh.triLeafNode[i], 4);
+            hn[k][i] = make_float4(vtx[3], vtx[4], vtx[5], nw);
         }
     }
     std::vector<float4> hMats((size_t)d->n_meshes * 2);
@@ -394,6 +399,9 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     UP(triN0, hn[0]); UP(triN1, hn[1]); UP(triN2, hn[2]);
     UP(mats, hMats);
     UP(origToLeaf, hOrigToLeaf);
+    std::vector<int> hParent(s->bvh.parent.begin(), s->bvh.parent.end());
+    if (hParent.empty()) hParent.assign(std::max<size_t>(NN, 1), -1);
+    UP(refParent, hParent);
     // ---- the production traversal's node array: one 4 x float4 entry per inner node (reference or sub-tree) holding both
     // children with their visit ids (encoding documented in cgrt_device.cuh)
     const uint32_t ID_MASK = 0x03ffffffu, ID_REFLEAF = 0x10000000u, ID_TRI = 0x20000000u, ID_SUB = 0x40000000u,
@@ -468,6 +476,8 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     s->dev.origToLeaf = s->origToLeaf.p;
     s->dev.pairs = s->pairs.p;
     s->dev.wide = s->wide.p;
+    s->dev.refParent = s->refParent.p;
+    s->dev.fastRoot = s->bvh.fastRoot;
     s->dev.nNodes = (int)NN;
     s->dev.nTris = (int)T;
     s->dev.nMeshes = d->n_meshes;
@@ -875,6 +885,10 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
         RC(s->hitList.ensure(cap * pathLevels));
         RC(s->pathDepth.ensure(cap));
         RC(s->lit.ensure(cap * pathLevels * nL));
+        if (s->dev.fastRoot != 0u) { // replay queues of the speculative kernels
+            RC(s->replayQ.ensure(cap * 3));
+            RC(s->replayShadow.ensure(cap * pathLevels * nL));
+        }
     }
     RC(s->pathPix.ensure(cap));
     RC(s->counts.ensure(CGRT_CNT_TOTAL));
@@ -951,6 +965,8 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
         PB.lit = s->lit.p;
         PB.pathPix = s->pathPix.p;
         PB.pathDepth = s->pathDepth.p;
+        PB.replayQ = s->replayQ.p;
+        PB.replayShadow = s->replayShadow.p;
         PB.counts = s->counts.p;
         PB.cap = B.cap;
         PB.levels = std::max(P.traceLimit, 1);
@@ -987,6 +1003,8 @@ int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
         stats->primary_hit = (uint64_t)counts[CGRT_CNT_PATHS];
         stats->shadow = (uint64_t)counts[CGRT_CNT_HITS] * (uint64_t)P.nLights;
         stats->bounce = (uint64_t)counts[CGRT_CNT_BOUNCES];
+        stats->replayed_closest = (uint32_t)counts[CGRT_CNT_REPLAY_PATHS];
+        stats->replayed_shadow = (uint32_t)counts[CGRT_CNT_REPLAY_SHADOW];
     } else {
         stats->primary_hit = (uint64_t)counts[CGRT_CNT_HIT + 0];
         for (int l = 0; l < P.traceLimit; l++) {

@@ -128,7 +128,7 @@ struct TravStack {
     int r[CGRT_STACK + CGRT_SUBSTACK]; // reference node index of a reference entry (exact re-evaluation of its key)
 };
 
-enum { TRAV_CONTINUE = 0, TRAV_DONE = 1, TRAV_FIRED = 2 };
+enum { TRAV_CONTINUE = 0, TRAV_DONE = 1, TRAV_FIRED = 2, TRAV_DEFER = 3 };
 enum { CLS_REF = 0, CLS_WIDE = 1, CLS_LEAF = 2, CLS_NONE = 3 };
 RT_DEV int travClass(uint32_t node)
 {
@@ -465,6 +465,266 @@ RT_DEV bool traverseFast(const DevScene& S, const V3& o, const V3& d, float tIn,
         } while (state == TRAV_CONTINUE);
     }
     return travFinish<ANY>(S, T, state, eps, maxDist, R);
+}
+
+// ---- the speculative traversal ------------------------------------------------------------------------------------------------
+// The exact traversal above pays for reproducing the reference's visiting ORDER (two exact box decisions per reference node,
+// three node classes). For almost every ray the order is irrelevant: the reference's result is simply the acceptable
+// triangle with the smallest distance, where "acceptable" means that the reference's own arithmetic (leafCandidate: plane
+// distance in [0, ray.t at entry), point inside) accepts it. The speculative traversal therefore
+//   1. searches ONE conservative 8-wide tree over all triangles (DevScene::fastRoot, bvh_build.cpp buildFastTree) for the
+//      acceptable triangle of smallest distance t* - tolerant box tests that can never cull an acceptable triangle, the
+//      reference's exact triangle arithmetic, plain nearest-first order with pruning against t*;
+//   2. CERTIFIES that the reference finds the same triangle (certifyChain): the reference reaches a leaf unless one of the
+//      boxes on the way from the root is rejected (`currentT >= ray.t`, or a miss) or pruned as a pending sibling
+//      (`ray.t < tSecond`). Before tri* is accepted ray.t is the distance of some other acceptable triangle or the initial
+//      bound, i.e. > t*. So if for every node on the path root -> leaf(tri*) the origin is strictly inside the box
+//      (startsInBox: visited unconditionally, bvh.cpp:685-696) or the reference's own slabTest with ray.t := t* reports a hit
+//      with distance < t*, every one of those decisions comes out "descend" whatever the order of the visits, the leaf scan
+//      accepts tri* (its distance is below the current ray.t) and nothing accepted later can replace it (nothing acceptable is
+//      closer). A miss needs no certificate: the reference only ever accepts acceptable triangles.
+//   3. DEFERS the ray to the exact traversal whenever the outcome could depend on the visiting order: two acceptable triangles
+//      at exactly the same distance, a candidate through the in-plane shortcut (ray_tracing.cpp:43-47, accepted regardless of
+//      ray.t), a box on the chain that is entered exactly at t* (axis-aligned geometry lying in a box face), or a ray the
+//      tolerant tests are not safe for (useSub). Deferred rays are replayed by the exact kernels; results are identical to
+//      the reference's in every case, only the cost differs.
+// Any-hit (pointInShadow): an acceptable triangle X with !(t_X + eps >= maxDist) whose chain certifies with t* := t_X proves
+// "shadowed" - the reference either visits leaf(X) with ray.t > t_X and accepts X, or its ray.t is already below t_X; its
+// final distance is <= t_X either way and the predicate is monotone. No such X among ALL acceptable triangles proves that
+// the tree does not shadow; the search may prune with min(t*, maxDist) because eps > 0.
+struct FastTrav {
+    V3 o, d, inv;
+    float t;     // distance of the best acceptable triangle so far (initially the ray's bound)
+    int hitTri;  // its position, -1 none
+    int sp;
+    uint32_t node;
+};
+#define CGRT_FASTSTACK 64
+struct FastStack {
+    uint32_t n[CGRT_FASTSTACK];
+    float t[CGRT_FASTSTACK];
+};
+
+// intersectDataStructure (bvh.cpp:831-844) evaluated exactly, then the fast tree's root.
+// TRAV_DONE: the reference does not enter the tree (certain miss); TRAV_DEFER: this ray must take the exact traversal.
+RT_DEV int fastBegin(const DevScene& S, FastTrav& T, const V3& o, const V3& d, float tIn)
+{
+    T.o = o;
+    T.d = d;
+    T.t = tIn;
+    T.hitTri = -1;
+    T.sp = 0;
+    T.node = 0u;
+    if (S.nNodes <= 0) return TRAV_DONE;
+    const float4 rq0 = __ldg(S.nodes + 0), rq1 = __ldg(S.nodes + 1);
+    bool enter = startsInBox(o, mk3(rq0), mk3(rq1));
+    if (!enter) {
+        float tmp;
+        enter = slabTest(mk3(rq0), mk3(rq1), o, d, tIn, tmp);
+    }
+    if (!enter) return TRAV_DONE;
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    const bool okx = (ax == 0.0f) || (ax >= 1e-20f && ax <= 1e20f);
+    const bool oky = (ay == 0.0f) || (ay >= 1e-20f && ay <= 1e20f);
+    const bool okz = (az == 0.0f) || (az >= 1e-20f && az <= 1e20f);
+    const bool fin = fabsf(o.x) <= 1e30f && fabsf(o.y) <= 1e30f && fabsf(o.z) <= 1e30f; // false for NaN
+    if (!(okx && oky && okz && fin) || S.fastRoot == 0u) return TRAV_DEFER;
+    T.inv.x = ax == 0.0f ? 1e30f : 1.0f / d.x;
+    T.inv.y = ay == 0.0f ? 1e30f : 1.0f / d.y;
+    T.inv.z = az == 0.0f ? 1e30f : 1.0f / d.z;
+    T.node = S.fastRoot;
+    return TRAV_CONTINUE;
+}
+
+RT_DEV int fastPop(FastTrav& T, FastStack& K, float bound)
+{
+    while (T.sp > 0) {
+        T.sp--;
+        if (K.t[T.sp] > bound) continue;
+        T.node = K.n[T.sp];
+        return TRAV_CONTINUE;
+    }
+    return TRAV_DONE;
+}
+
+// search bound: boxes entered beyond it cannot hold a closer acceptable triangle (ANY: nor one within maxDist)
+template <bool ANY>
+RT_DEV float fastBound(const FastTrav& T, float maxDist)
+{
+    const float slack = 1.000001f;
+    return (ANY ? fminf(T.t, maxDist) : T.t) * slack;
+}
+
+template <bool ANY>
+RT_DEV int fastStepWide(const DevScene& S, FastTrav& T, FastStack& K, float maxDist)
+{
+    const float4* w = S.wide + 14 * (size_t)(T.node & CGRT_IDX_MASK);
+    const float slack = 1.000001f;
+    const float bt = fastBound<ANY>(T, maxDist);
+    const V3 o = T.o, inv = T.inv;
+    float tin[8];
+    uint32_t cid[8];
+    unsigned hitMask = 0u;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const float4 lx = __ldg(w + 0 + h), ly = __ldg(w + 2 + h), lz = __ldg(w + 4 + h);
+        const float4 hx = __ldg(w + 6 + h), hy = __ldg(w + 8 + h), hz = __ldg(w + 10 + h);
+        const float4 ci = __ldg(w + 12 + h);
+        const float lox[4] = {lx.x, lx.y, lx.z, lx.w}, loy[4] = {ly.x, ly.y, ly.z, ly.w}, loz[4] = {lz.x, lz.y, lz.z, lz.w};
+        const float hix[4] = {hx.x, hx.y, hx.z, hx.w}, hiy[4] = {hy.x, hy.y, hy.z, hy.w}, hiz[4] = {hz.x, hz.y, hz.z, hz.w};
+        const float cw[4] = {ci.x, ci.y, ci.z, ci.w};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float q0x = (lox[c] - o.x) * inv.x, q1x = (hix[c] - o.x) * inv.x;
+            const float q0y = (loy[c] - o.y) * inv.y, q1y = (hiy[c] - o.y) * inv.y;
+            const float q0z = (loz[c] - o.z) * inv.z, q1z = (hiz[c] - o.z) * inv.z;
+            const float ti = fmaxf(fmaxf(fminf(q0x, q1x), fminf(q0y, q1y)), fminf(q0z, q1z));
+            const float to = fminf(fminf(fmaxf(q0x, q1x), fmaxf(q0y, q1y)), fmaxf(q0z, q1z));
+            const uint32_t ii = (uint32_t)f2i(cw[c]);
+            const bool hit = ii != 0u && !(to < 0.0f || ti > to * slack || ti > bt);
+            tin[4 * h + c] = ti;
+            cid[4 * h + c] = ii;
+            if (hit) hitMask |= 1u << (4 * h + c);
+        }
+    }
+    if (hitMask == 0u) return fastPop(T, K, bt);
+    if (T.sp + 7 > CGRT_FASTSTACK) return TRAV_DEFER; // pathological depth: let the exact traversal handle the ray
+    int best = -1;
+    float bestT = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        if ((hitMask >> c & 1u) && (best < 0 || tin[c] < bestT)) { best = c; bestT = tin[c]; }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        if ((hitMask >> c & 1u) && c != best) {
+            K.n[T.sp] = cid[c];
+            K.t[T.sp] = tin[c];
+            T.sp++;
+        }
+    }
+    T.node = cid[best];
+    return TRAV_CONTINUE;
+}
+
+// the triangles of one fast-tree leaf with the reference's accept arithmetic (same expression trees as leafCandidate)
+template <bool ANY>
+RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps, float maxDist)
+{
+    const uint32_t id = T.node;
+    const int first = (int)(id & CGRT_IDX_MASK);
+    const int count = (int)((id >> CGRT_TRICNT_SHIFT) & 7u) + 1;
+    const V3 o = T.o, d = T.d;
+#pragma unroll 1
+    for (int i = first; i < first + count; i++) {
+        const float4 pl = __ldg(S.triPl + i);
+        const V3 n = mk3(pl);
+        const float on = dot3(o, n);
+        float tt = 0.0f;
+        const bool shortcut = (on == pl.w);
+        if (!shortcut) {
+            const float denominator = dot3(d, n);
+            if (denominator == 0) continue;
+            tt = (pl.w - on) / denominator;
+            if (tt < 0) continue;
+            if (!(tt <= T.t)) continue;                    // farther than the best (or NaN)
+            if (tt == T.t && T.hitTri < 0) continue;       // equals the ray's own bound: rejected by `t >= ray.t`
+        }
+        const float4 v0 = __ldg(S.triV0 + i), v1 = __ldg(S.triV1 + i), v2 = __ldg(S.triV2 + i);
+        const V3 p = o + d * tt;
+        if (!pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), n, p)) continue;
+        if (shortcut || tt == T.t) return TRAV_DEFER;      // the outcome depends on the reference's visiting order
+        T.t = tt;
+        T.hitTri = i;
+        if (ANY && !(tt + eps >= maxDist)) return TRAV_FIRED;
+    }
+    return fastPop(T, K, fastBound<ANY>(T, maxDist));
+}
+
+// does the reference reach the leaf of triangle `pos` while ray.t is still above tStar? (see the block comment above)
+RT_DEV bool certifyChain(const DevScene& S, const V3& o, const V3& d, int pos, float tStar)
+{
+    int node = f2i(__ldg(S.triN0 + pos).w);
+#pragma unroll 1
+    while (true) {
+        const float4 q0 = __ldg(S.nodes + 2 * node), q1 = __ldg(S.nodes + 2 * node + 1);
+        if (!startsInBox(o, mk3(q0), mk3(q1))) {
+            float te = 0.0f;
+            if (!slabTest(mk3(q0), mk3(q1), o, d, tStar, te)) return false;
+            if (!(te < tStar)) return false; // NaN distances are not certificates
+        }
+        if (node == 0) return true;
+        node = __ldg(S.refParent + node);
+    }
+}
+
+RT_DEV bool travIsLeaf(uint32_t node) { return (node & CGRT_TRI) != 0u; }
+
+template <bool ANY>
+RT_DEV int fastStep(const DevScene& S, FastTrav& T, FastStack& K, float eps, float maxDist)
+{
+    if (travIsLeaf(T.node)) return fastStepLeaf<ANY>(S, T, K, eps, maxDist);
+    return fastStepWide<ANY>(S, T, K, maxDist);
+}
+
+// After the search: certificate, then the sphere loop of BoundingVolumeHierarchy::intersect (bvh.cpp:878-879).
+// Returns false with `defer` set when the ray has to be replayed by the exact traversal.
+template <bool ANY>
+RT_DEV bool fastFinish(const DevScene& S, const FastTrav& T, int state, float eps, float maxDist, TraceResult& R, bool& defer)
+{
+    R.sphere = -1;
+    R.t = T.t;
+    R.tri = T.hitTri;
+    defer = false;
+    if (state == TRAV_DEFER) {
+        defer = true;
+        return false;
+    }
+    if (ANY) {
+        if (state == TRAV_FIRED) {
+            if (!certifyChain(S, T.o, T.d, T.hitTri, T.t)) defer = true;
+            return !defer;
+        }
+    } else if (T.hitTri >= 0) {
+        if (!certifyChain(S, T.o, T.d, T.hitTri, T.t)) {
+            defer = true;
+            return false;
+        }
+    }
+    float t = T.t;
+    for (int s = 0; s < S.nSpheres; s++) {
+        const float4 c = __ldg(S.spheres + 3 * s);
+        float ts;
+        V3 nn;
+        if (sphereTest(mk3(c), c.w, T.o, T.d, t, ts, nn)) {
+            t = ts;
+            R.sphere = s;
+            R.sphereN = nn;
+            if (ANY && !(ts + eps >= maxDist)) {
+                R.t = t;
+                return true;
+            }
+        }
+    }
+    R.t = t;
+    if (ANY) return false;
+    return T.hitTri >= 0 || R.sphere >= 0;
+}
+
+// one ray, start to finish: speculative search first, exact replay when it cannot be certified
+template <bool ANY>
+RT_DEV bool traverseSpec(const DevScene& S, const V3& o, const V3& d, float tIn, float eps, float maxDist, TraceResult& R)
+{
+    {
+        FastTrav T;
+        FastStack K;
+        int state = fastBegin(S, T, o, d, tIn);
+        while (state == TRAV_CONTINUE) state = fastStep<ANY>(S, T, K, eps, maxDist);
+        bool defer;
+        const bool r = fastFinish<ANY>(S, T, state, eps, maxDist, R, defer);
+        if (!defer) return r;
+    }
+    return traverseFast<ANY>(S, o, d, tIn, eps, maxDist, R);
 }
 
 // Closest-hit traversal in the reference's exact visiting order:

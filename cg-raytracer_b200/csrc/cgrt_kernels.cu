@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128) k_closest_batch(DevScene S, const float4*
         TraceResult R;
         uint32_t nBox = 0, nTri = 0;
         const bool hit = COUNT ? traverseStrict<false, true>(S, o, d, r0.w, 0.0f, 0.0f, R, nBox, nTri)
-                               : traverseFast<false>(S, o, d, r0.w, 0.0f, 0.0f, R);
+                               : traverseSpec<false>(S, o, d, r0.w, 0.0f, 0.0f, R);
         writeHit(S, o, d, r0.w, hit, R, hits + 2 * i);
         if (COUNT) {
             counts[2 * i] = nBox;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128) k_any_batch(DevScene S, const float4* __r
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float4 r0 = __ldg(rays + 2 * i), r1 = __ldg(rays + 2 * i + 1);
         TraceResult R;
-        const bool sh = traverseFast<true>(S, mk3(r0), mk3(r1), r0.w, eps, __ldg(maxDist + i), R);
+        const bool sh = traverseSpec<true>(S, mk3(r0), mk3(r1), r0.w, eps, __ldg(maxDist + i), R);
         occluded[i] = sh ? 1 : 0;
     }
 }
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(128) k_shadow(DevScene S, const FrameParams* _
 // keeps its lanes busy instead of idling until its slowest ray is done; rays that miss the root box (most primary rays)
 // cost one converged refill round. A Policy supplies the rays and consumes the results:
 //     bool load(int idx, V3& o, V3& d, float& tIn, float& eps, float& maxDist)   false = nothing to trace for this index
-//     bool retire(bool fin, int idx, bool traced, bool result, const TraceResult& R, const Trav& T, V3& o, V3& d, float& tIn)
+//     bool retire(bool fin, int idx, bool traced, bool result, const TraceResult& R, const V3& ro, const V3& rd, V3& o, V3& d, float& tIn)
 //          called by ALL lanes; returns true when the lane continues with a follow-up ray (o, d, tIn) of the same item
 // =================================================================================================================
 // Scheduling knobs of the persistent warps (environment CGRT_TUNE="steps=6,idle=6,vote=1,wref=4,wsub=16,wleaf=8,blocks=8"
@@ -548,7 +548,7 @@ RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCou
                 bool result = false;
                 if (fin && traced) result = travFinish<ANY>(S, T, state, eps, maxDist, R);
                 V3 no, nd;
-                const bool again = P.retire(fin, idx, traced, result, R, T, no, nd, tIn);
+                const bool again = P.retire(fin, idx, traced, result, R, T.o, T.d, no, nd, tIn);
                 if (fin) {
                     if (again) {
                         state = travBegin(S, T, no, nd, tIn) ? TRAV_CONTINUE : TRAV_DONE;
@@ -641,7 +641,7 @@ struct PrimaryPolicy {
         maxDist = 0.0f;
         return true;
     }
-    RT_DEV bool retire(bool fin, int slot, bool traced, bool hit, const TraceResult& R, const Trav& T, V3&, V3&, float&)
+    RT_DEV bool retire(bool fin, int slot, bool traced, bool hit, const TraceResult& R, const V3& ro, const V3& rd, V3&, V3&, float&)
     {
         if (fin) {
             if (!traced) {
@@ -650,7 +650,7 @@ struct PrimaryPolicy {
                 storeRGB(fb, outIdx, mk3(0.0f, 0.0f, 0.0f)); // trace(): miss -> black, src/main.cpp:288-294
             }
         }
-        pushHitRecord(S, B, 0, fin && traced && hit, R, T.o, T.d, outIdx, -1);
+        pushHitRecord(S, B, 0, fin && traced && hit, R, ro, rd, outIdx, -1);
         return false;
     }
 };
@@ -673,11 +673,11 @@ struct BouncePolicy {
         maxDist = 0.0f;
         return true;
     }
-    RT_DEV bool retire(bool fin, int, bool, bool hit, const TraceResult& R, const Trav& T, V3&, V3&, float&)
+    RT_DEV bool retire(bool fin, int, bool, bool hit, const TraceResult& R, const V3& ro, const V3& rd, V3&, V3&, float&)
     {
         if (fin && !hit) // reflected colour is black; unwind the levels above (src/main.cpp:288-294 then :263)
             storeRGB(fb, outIdx, foldPath(B.pathState, B.cap, level, pathId, mk3(0.0f, 0.0f, 0.0f)));
-        pushHitRecord(S, B, level, fin && hit, R, T.o, T.d, outIdx, pathId);
+        pushHitRecord(S, B, level, fin && hit, R, ro, rd, outIdx, pathId);
         return false;
     }
 };
@@ -700,7 +700,7 @@ struct ShadowPolicy {
         maxDist = length3(fromPosToLight);
         return true;
     }
-    RT_DEV bool retire(bool fin, int i, bool, bool shadowed, const TraceResult&, const Trav&, V3&, V3&, float&)
+    RT_DEV bool retire(bool fin, int i, bool, bool shadowed, const TraceResult&, const V3&, const V3&, V3&, V3&, float&)
     {
         if (fin) B.lit[i] = shadowed ? 0 : 1;
         return false;
@@ -736,6 +736,9 @@ __global__ void __launch_bounds__(128) k_shadow_p(DevScene S, const FrameParams*
 // mirror hit while level + 1 < trace limit. A lane of k_paths follows that chain itself (the follow-up ray of shade(),
 // main.cpp:252-256, is handed straight back to the traversal), so the chain costs no kernel boundary; the shadow rays
 // (pointInShadow) do not influence the chain and are traced afterwards for all levels at once.
+// FROMQ = false: work items are pixel slots (primary rays); FROMQ = true: work items are records of the replay queue, i.e.
+// rays of any level that the speculative kernel could not certify (the chain continues from there in the same lane).
+template <bool FROMQ>
 struct PathsPolicy {
     const DevScene& S;
     const FrameParams& P;
@@ -745,6 +748,18 @@ struct PathsPolicy {
     int outIdx, level, path; // per lane
     RT_DEV bool load(int slot, V3& o, V3& d, float& tIn, float& eps, float& maxDist)
     {
+        eps = 0.0f;
+        maxDist = 0.0f;
+        if (FROMQ) {
+            const float4 a = B.replayQ[3 * (size_t)slot], b = B.replayQ[3 * (size_t)slot + 1], c = B.replayQ[3 * (size_t)slot + 2];
+            o = mk3(a);
+            tIn = a.w;
+            d = mk3(b);
+            level = f2i(b.w);
+            path = f2i(c.x);
+            outIdx = f2i(c.y);
+            return true;
+        }
         int x, y, local;
         level = 0;
         path = -1;
@@ -755,11 +770,18 @@ struct PathsPolicy {
         o = mk3(P.camX, P.camY, P.camZ);
         d = primaryDirection(P, x, y);
         tIn = FLT_MAX;
-        eps = 0.0f;
-        maxDist = 0.0f;
         return true;
     }
-    RT_DEV bool retire(bool fin, int slot, bool traced, bool hit, const TraceResult& R, const Trav& T, V3& no, V3& nd, float& nt)
+    // the speculative kernel hands a ray it cannot certify to the exact kernel (rare: one atomic per ray is fine)
+    RT_DEV void defer(const V3& o, const V3& d, float tIn)
+    {
+        const int q = atomicAdd(B.counts + CGRT_CNT_REPLAY_PATHS, 1);
+        float4* r = B.replayQ + 3 * (size_t)q;
+        r[0] = make_float4(o.x, o.y, o.z, tIn);
+        r[1] = make_float4(d.x, d.y, d.z, i2f(level));
+        r[2] = make_float4(i2f(path), i2f(outIdx), 0.0f, 0.0f);
+    }
+    RT_DEV bool retire(bool fin, int slot, bool traced, bool hit, const TraceResult& R, const V3& ro, const V3& rd, V3& no, V3& nd, float& nt)
     {
         const bool isHit = fin && traced && hit;
         const int newPath = warpPush(B.counts + CGRT_CNT_PATHS, isHit && level == 0);
@@ -786,21 +808,21 @@ struct PathsPolicy {
                     const float4 n0 = __ldg(S.triN0 + i), n1 = __ldg(S.triN1 + i), n2 = __ldg(S.triN2 + i);
                     const float4 pl = __ldg(S.triPl + i);
                     float al, be, ga;
-                    hitEpilogue(mk3(v0), mk3(v1), mk3(v2), mk3(n0), mk3(n1), mk3(n2), mk3(pl), T.o, T.d, R.t, al, be, ga, nn);
+                    hitEpilogue(mk3(v0), mk3(v1), mk3(v2), mk3(n0), mk3(n1), mk3(n2), mk3(pl), ro, rd, R.t, al, be, ga, nn);
                     mat = f2i(v1.w);
                 }
-                const V3 pointOn = T.o + T.d * R.t; // main.cpp:164
+                const V3 pointOn = ro + rd * R.t; // main.cpp:164
                 const int rec = path * B.levels + level;
                 float4* r = B.hitRec + 3 * (size_t)rec;
                 r[0] = make_float4(pointOn.x, pointOn.y, pointOn.z, i2f(mat));
                 r[1] = make_float4(nn.x, nn.y, nn.z, 0.0f);
-                r[2] = make_float4(T.d.x, T.d.y, T.d.z, 0.0f);
+                r[2] = make_float4(rd.x, rd.y, rd.z, 0.0f);
                 B.hitList[listPos] = rec;
                 B.pathDepth[path] = level + 1;
                 const float ksz = mat >= 0 ? __ldg(S.mats + 2 * mat + 1).z : 0.0f;
                 if (!(ksz <= 0.01f) && level + 1 < P.traceLimit) { // shade(): mirror test main.cpp:246, trace limit :267
-                    const V3 reflected = normalize3(reflect3(T.d, nn)); // ComputeReflectedRay, main.cpp:252-256
-                    nt = length3(T.d);
+                    const V3 reflected = normalize3(reflect3(rd, nn)); // ComputeReflectedRay, main.cpp:252-256
+                    nt = length3(rd);
                     const float epsilon = 0.001f;
                     no = pointOn + epsilon * reflected;
                     nd = reflected;
@@ -815,12 +837,138 @@ struct PathsPolicy {
     }
 };
 
+// =================================================================================================================
+// Persistent warps over the SPECULATIVE traversal (cgrt_device.cuh): same refill / retire skeleton as persistentTraverse,
+// two node classes (8-wide conservative node, triangle leaf), and a third way for a ray to end - "defer": the lane hands
+// the ray to the Policy's replay queue, which the exact kernel drains afterwards.
+// =================================================================================================================
+#ifndef CGRT_FAST_STEPS
+#define CGRT_FAST_STEPS 8
+#endif
+#ifndef CGRT_FAST_MINBLOCKS
+#define CGRT_FAST_MINBLOCKS 8
+#endif
+#ifndef CGRT_FAST_W_LEAF
+#define CGRT_FAST_W_LEAF 1
+#endif
+template <bool ANY, class Policy>
+RT_DEV void persistentFast(const DevScene& S, Policy& P, int n, int* workCounter)
+{
+    FastTrav T;
+    FastStack K;
+    int idx = -1;
+    int state = TRAV_DONE;
+    bool traced = false;
+    float tIn = 0.0f, eps = 0.0f, maxDist = 0.0f;
+    bool exhausted = false;
+    const int lane = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    INSTR_ADD(15, 1);
+    while (true) {
+        // ---- refill
+        const unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
+        const int nIdle = __popc(idle);
+        if (!exhausted && (nIdle >= CGRT_REFILL_MIN_IDLE || idle == 0xffffffffu)) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(workCounter, nIdle);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + nIdle >= n) exhausted = true;
+            if (idx < 0) {
+                const int mine = base + __popc(idle & ltMask);
+                if (mine < n) {
+                    idx = mine;
+                    V3 o, d;
+                    traced = P.load(idx, o, d, tIn, eps, maxDist);
+                    state = traced ? fastBegin(S, T, o, d, tIn) : TRAV_DONE;
+                }
+            }
+            INSTR_ADD(8, 1); INSTR_ADD(9, nIdle);
+        }
+        // ---- retire finished lanes (collective)
+        {
+            const bool fin = idx >= 0 && state != TRAV_CONTINUE;
+            if (__ballot_sync(0xffffffffu, fin) != 0u) {
+                INSTR_ADD(10, 1); INSTR_ADD(11, __popc(__ballot_sync(0xffffffffu, fin)));
+                TraceResult R;
+                R.sphere = -1; R.tri = -1; R.t = tIn;
+                bool result = false, defer = false;
+                if (fin && traced) result = fastFinish<ANY>(S, T, state, eps, maxDist, R, defer);
+                if (fin && defer) P.defer(T.o, T.d, tIn);
+                V3 no, nd;
+                const bool again = P.retire(fin && !defer, idx, traced, result, R, T.o, T.d, no, nd, tIn);
+                if (fin) {
+                    if (again) state = fastBegin(S, T, no, nd, tIn);
+                    else idx = -1;
+                }
+                continue;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, idx >= 0) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- a burst of steps: each iteration runs the node class most running lanes wait in
+#ifdef CGRT_INSTRUMENT
+        {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            const int nRun = __popc(__ballot_sync(0xffffffffu, idx >= 0 && state == TRAV_CONTINUE));
+            if (lane == 0) {
+                const unsigned long long old = atomicMin(&g_t0[ANY ? 1 : 0], now);
+                const unsigned long long t0 = old < now ? old : now;
+                int b = (int)((now - t0) / 25000ull);
+                if (b > 127) b = 127;
+                atomicAdd(&g_tl[ANY ? 1 : 0][b][0], 1u);
+                atomicAdd(&g_tl[ANY ? 1 : 0][b][1], (unsigned)nRun);
+            }
+        }
+#endif
+#pragma unroll 1
+        for (int it = 0; it < CGRT_FAST_STEPS; it++) {
+            const bool run = idx >= 0 && state == TRAV_CONTINUE;
+            const bool leaf = run && travIsLeaf(T.node);
+            const int sAll = __popc(__ballot_sync(0xffffffffu, run));
+            const int sLeaf = __popc(__ballot_sync(0xffffffffu, leaf));
+            INSTR_ADD(0, 1); INSTR_ADD(1, sAll);
+            if (sAll == 0) break;
+            if (sAll - sLeaf >= sLeaf * CGRT_FAST_W_LEAF) {
+                INSTR_ADD(2, 1); INSTR_ADD(5, sAll - sLeaf);
+                if (run && !leaf) state = fastStepWide<ANY>(S, T, K, maxDist);
+            } else {
+                INSTR_ADD(4, 1); INSTR_ADD(7, sLeaf);
+                if (leaf) state = fastStepLeaf<ANY>(S, T, K, eps, maxDist);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128, CGRT_FAST_MINBLOCKS) k_paths_fast(DevScene S, const FrameParams* __restrict__ Pp, PathBuffers B,
+                                                    const int2* __restrict__ tileSeq, float* __restrict__ fb, int* work)
+{
+    const FrameParams P = *Pp;
+    PathsPolicy<false> pol{S, P, B, tileSeq, fb, -1, 0, -1};
+    persistentFast<false>(S, pol, P.nSlots, work);
+}
+
+// exact traversal: all pixels (scenes without a fast tree) ...
 __global__ void __launch_bounds__(128, CGRT_MINBLOCKS) k_paths(DevScene S, const FrameParams* __restrict__ Pp, PathBuffers B,
                                                const int2* __restrict__ tileSeq, float* __restrict__ fb, int* work, Tuning U)
 {
     const FrameParams P = *Pp;
-    PathsPolicy pol{S, P, B, tileSeq, fb, -1, 0, -1};
+    PathsPolicy<false> pol{S, P, B, tileSeq, fb, -1, 0, -1};
     persistentTraverse<false>(S, pol, P.nSlots, work, U);
+}
+
+// ... or the rays k_paths_fast deferred
+__global__ void __launch_bounds__(128, CGRT_MINBLOCKS) k_paths_replay(DevScene S, const FrameParams* __restrict__ Pp, PathBuffers B,
+                                                      float* __restrict__ fb, int* work, Tuning U)
+{
+    const int n = B.counts[CGRT_CNT_REPLAY_PATHS];
+    if (n == 0) return;
+    const FrameParams P = *Pp;
+    PathsPolicy<true> pol{S, P, B, nullptr, fb, -1, 0, -1};
+    persistentTraverse<false>(S, pol, n, work, U);
 }
 
 // trace limit 0 with direct writes into a shared frame: black for this rank's pixels only
@@ -833,16 +981,25 @@ __global__ void k_clear_tiles(const FrameParams* __restrict__ Pp, const int2* __
     }
 }
 
+template <bool FROMQ>
 struct ShadowAllPolicy {
     const PathBuffers& B;
     const float4* lights;
     int nL;
-    int out; // per lane: index of the lit flag
+    int item; // per lane: (hit record, light) work item = index of the lit flag
     RT_DEV bool load(int i, V3& o, V3& d, float& tIn, float& eps, float& maxDist)
     { // pointInShadow, src/main.cpp:104-135
-        const int h = i / nL, l = i - h * nL;
-        const int rec = B.hitList[h];
-        out = rec * nL + l;
+        int rec, l;
+        if (FROMQ) {
+            item = B.replayShadow[i];
+            rec = item / nL;
+            l = item - rec * nL;
+        } else {
+            const int h = i / nL;
+            l = i - h * nL;
+            rec = B.hitList[h];
+            item = rec * nL + l;
+        }
         const V3 pointOn = mk3(B.hitRec[3 * (size_t)rec]);
         const V3 lightPos = mk3(__ldg(lights + 2 * l));
         const V3 fromPosToLight = lightPos - pointOn;
@@ -853,19 +1010,37 @@ struct ShadowAllPolicy {
         maxDist = length3(fromPosToLight);
         return true;
     }
-    RT_DEV bool retire(bool fin, int, bool, bool shadowed, const TraceResult&, const Trav&, V3&, V3&, float&)
+    RT_DEV void defer(const V3&, const V3&, float) { B.replayShadow[atomicAdd(B.counts + CGRT_CNT_REPLAY_SHADOW, 1)] = item; }
+    RT_DEV bool retire(bool fin, int, bool, bool shadowed, const TraceResult&, const V3&, const V3&, V3&, V3&, float&)
     {
-        if (fin) B.lit[out] = shadowed ? 0 : 1;
+        if (fin) B.lit[item] = shadowed ? 0 : 1;
         return false;
     }
 };
+
+__global__ void __launch_bounds__(128, CGRT_FAST_MINBLOCKS) k_shadow_fast(DevScene S, const FrameParams* __restrict__ Pp,
+                                                     const float4* __restrict__ lights, PathBuffers B, int* work)
+{
+    const int nL = Pp->nLights;
+    ShadowAllPolicy<false> pol{B, lights, nL, 0};
+    persistentFast<true>(S, pol, B.counts[CGRT_CNT_HITS] * nL, work);
+}
 
 __global__ void __launch_bounds__(128, CGRT_MINBLOCKS) k_shadow_all(DevScene S, const FrameParams* __restrict__ Pp,
                                                     const float4* __restrict__ lights, PathBuffers B, int* work, Tuning U)
 {
     const int nL = Pp->nLights;
-    ShadowAllPolicy pol{B, lights, nL, 0};
+    ShadowAllPolicy<false> pol{B, lights, nL, 0};
     persistentTraverse<true>(S, pol, B.counts[CGRT_CNT_HITS] * nL, work, U);
+}
+
+__global__ void __launch_bounds__(128, CGRT_MINBLOCKS) k_shadow_replay(DevScene S, const FrameParams* __restrict__ Pp,
+                                                       const float4* __restrict__ lights, PathBuffers B, int* work, Tuning U)
+{
+    const int n = B.counts[CGRT_CNT_REPLAY_SHADOW];
+    if (n == 0) return;
+    ShadowAllPolicy<true> pol{B, lights, Pp->nLights, 0};
+    persistentTraverse<true>(S, pol, n, work, U);
 }
 
 // direct colour of one hit record: shading(), src/main.cpp:160-235 (point-light loop :220-232)
@@ -1193,16 +1368,31 @@ int launchPathPipeline(const DevScene& S, const FrameParams* dP, const FramePara
     }
     int launches = 0;
     const int persistent = numSMs * tuning().blocks;
+    const int gPaths = min(gridFor((size_t)hP.nSlots, 128, 1 << 30), persistent);
+    int* work = B.counts + CGRT_CNT_WORK;
     traceBegin(tr, 0, st);
-    k_paths<<<min(gridFor((size_t)hP.nSlots, 128, 1 << 30), persistent), 128, 0, st>>>(S, dP, B, dTileSeq, fb,
-                                                                                        B.counts + CGRT_CNT_WORK, tuning());
+    if (S.fastRoot != 0u) { // speculative search + certificate; what cannot be certified is replayed exactly
+        k_paths_fast<<<gPaths, 128, 0, st>>>(S, dP, B, dTileSeq, fb, work + 0);
+        k_paths_replay<<<gPaths, 128, 0, st>>>(S, dP, B, fb, work + 2, tuning());
+        launches += 2;
+        if (tr) tr->launches[0]++;
+    } else {
+        k_paths<<<gPaths, 128, 0, st>>>(S, dP, B, dTileSeq, fb, work + 0, tuning());
+        launches++;
+    }
     traceEnd(tr, 0, st);
-    launches++;
     if (hP.nLights > 0) {
         traceBegin(tr, 2, st);
-        k_shadow_all<<<persistent, 128, 0, st>>>(S, dP, dLights, B, B.counts + CGRT_CNT_WORK + 1, tuning());
+        if (S.fastRoot != 0u) {
+            k_shadow_fast<<<persistent, 128, 0, st>>>(S, dP, dLights, B, work + 1);
+            k_shadow_replay<<<persistent, 128, 0, st>>>(S, dP, dLights, B, work + 3, tuning());
+            launches += 2;
+            if (tr) tr->launches[2]++;
+        } else {
+            k_shadow_all<<<persistent, 128, 0, st>>>(S, dP, dLights, B, work + 1, tuning());
+            launches++;
+        }
         traceEnd(tr, 2, st);
-        launches++;
     }
     traceBegin(tr, 3, st);
     k_shade_paths<<<gridFor((size_t)hP.nSlots, 128, numSMs * 16), 128, 0, st>>>(S, dP, dLights, B, fb);

@@ -19,7 +19,9 @@
 //             in cgrt_device.cuh), w1 = reference node index of the child. rootId = id of the root.
 // wide      : 8-wide nodes of the culling sub-trees that refine the reference leaves, 14 x float4 each:
 //             lo.x[0..3] lo.x[4..7] lo.y.. lo.z.. hi.x.. hi.y.. hi.z.. id[0..3] id[4..7]; boxes pre-expanded (bvh_build.cpp)
-// triN0/1/2 : float4 per triangle: vertex normal.xyz (read only for the final hit)
+// triN0/1/2 : float4 per triangle: vertex normal.xyz (read only for the final hit); triN0.w = reference leaf node of the triangle
+//             The top of `wide` also holds the FAST TREE (bvh_build.cpp buildFastTree): the reference tree collapsed into
+//             8-wide conservative nodes whose leaves are the sub-tree roots above - one tree over all triangles.
 // mats      : 2 x float4 per mesh:  [kd.xyz | shininess] [ks.xyz | transparency]        (src/mesh.h:17-23)
 // spheres   : 3 x float4 per sphere: [center | radius] [kd | shininess] [ks | transparency]  (src/scene.h:36-40)
 struct DevScene {
@@ -36,6 +38,8 @@ struct DevScene {
     const float4* pairs;
     const float4* wide;
     const int* origToLeaf; // global triangle id -> leaf-order index (brute-force path only)
+    const int* refParent;  // reference node -> parent (-1 for the root): certification of the speculative traversal
+    uint32_t fastRoot;     // id of the root of the fast tree in `wide` (0 = none: exact traversal only)
     int nNodes;
     int nTris;
     int nSpheres;
@@ -55,7 +59,9 @@ namespace cgrt {
 #define CGRT_CNT_PATHS (CGRT_CNT_WORK + 2 * CGRT_MAX_LEVELS + 2) // path pipeline: pixels whose primary ray hit (= paths)
 #define CGRT_CNT_HITS (CGRT_CNT_PATHS + 1)                      // path pipeline: hit records of all levels
 #define CGRT_CNT_BOUNCES (CGRT_CNT_PATHS + 2)                   // path pipeline: reflection rays traced
-#define CGRT_CNT_TOTAL (CGRT_CNT_PATHS + 3)
+#define CGRT_CNT_REPLAY_PATHS (CGRT_CNT_PATHS + 3)              // rays the speculative closest-hit kernel deferred to the exact one
+#define CGRT_CNT_REPLAY_SHADOW (CGRT_CNT_PATHS + 4)             // shadow rays deferred to the exact any-hit kernel
+#define CGRT_CNT_TOTAL (CGRT_CNT_PATHS + 5)
 #define CGRT_MAX_PEERS 32                       // flags one signal launch can write (GPUs of one box)
 #define CGRT_PARAM_BLOCK_HEADER 128             // bytes reserved for FrameParams in the per-frame block; lights follow
 
@@ -95,6 +101,8 @@ struct PathBuffers {
     uint8_t* lit;      // [(path * levels + level) * nLights + light] 1 = light reaches the point
     int* pathPix;      // [path] output index of the path's pixel
     int* pathDepth;    // [path] number of levels that recorded a hit
+    float4* replayQ;   // 3 x float4 per deferred ray: [origin | tmax] [direction | level] [path, outIdx, -, -]
+    int* replayShadow; // deferred shadow work items (index of the lit flag)
     int* counts;       // shared with WaveBuffers::counts
     size_t cap;        // paths the buffers can hold (= local pixel slots)
     int levels;        // trace limit the buffers are laid out for

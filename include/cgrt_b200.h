@@ -84,6 +84,9 @@ typedef struct cgrt_scene_options {
 /* Do not refine the reference leaves with culling sub-trees: every visited leaf is scanned triangle by triangle exactly as
  * intersectLeaf does (A/B switch for tests and profiling; results are identical either way). */
 #define CGRT_SCENE_NO_SUBTREES 2
+/* Do not use the speculative traversal (fast conservative tree + certification): every ray takes the exact
+ * reference-order traversal. A/B switch for tests and profiling; results are identical either way. */
+#define CGRT_SCENE_EXACT_ONLY 4
 
 /* PointLight, src/scene.h:42-45 */
 typedef struct cgrt_point_light {
@@ -128,7 +131,9 @@ typedef struct cgrt_render_stats {
     float device_ms;                               /* CUDA-event time of the whole wavefront on its stream */
     float class_ms[4];                             /* CGRT_RENDER_PROFILE only: summed device time per kernel class */
     uint32_t class_launches[4];                    /* kernels launched per class */
-    float reserved[3];
+    uint32_t replayed_closest, replayed_shadow;    /* rays the speculative traversal could not certify and handed to the
+                                                      exact reference-order traversal (same results, more work) */
+    float reserved[1];
 } cgrt_render_stats;
 
 typedef struct cgrt_scene cgrt_scene; /* opaque: flattened scene + BVH resident in HBM */

@@ -360,3 +360,66 @@ def test_cpp_host_mirror_cli(capi, oracle, gpu, tmp_path):
     assert f"hit={int(g['tri'] >= 0)}" in line
     if g["tri"] >= 0:
         assert f"t={g['t']:.9g}" in line
+
+
+# ---- speculative traversal (fast conservative tree + certificate + exact replay) vs the exact reference-order traversal --------
+def _axis_aligned_box_scene():
+    """Cornell-like: walls lying exactly in the faces of their bounding boxes (the case the certificate must refuse)."""
+    q = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], np.float32) * 0.7
+    faces = [(0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 5, 4), (3, 2, 6, 7), (0, 3, 7, 4)]
+    V, T, vc, tc = [], [], [], []
+    for f in faces:  # one mesh per wall, two triangles each
+        n = np.cross(q[f[1]] - q[f[0]], q[f[2]] - q[f[0]])
+        n = n / np.linalg.norm(n)
+        V.append(np.concatenate([q[list(f)], np.tile(n, (4, 1))], axis=1))
+        T.append(np.array([[0, 1, 2], [0, 2, 3]], np.uint32))
+        vc.append(4)
+        tc.append(2)
+    mats = np.tile(np.array([0.7, 0.7, 0.7, 0.5, 0.5, 0.5, 8.0, 1.0], np.float32), (len(faces), 1))
+    return ob.FlatScene(np.array(vc, np.int32), np.array(tc, np.int32), np.concatenate(V).astype(np.float32),
+                        np.concatenate(T), mats, np.zeros((0, 12), np.float32))
+
+
+@pytest.mark.parametrize("kind", ["soup", "soup_meshes", "boxes", "golden", "dragon"])
+def test_speculative_equals_exact_traversal(capi, oracle, gpu, golden, kind):
+    if kind == "soup":
+        flat = ob.random_soup(30000, seed=77, scale=0.04)
+    elif kind == "soup_meshes":
+        flat = ob.random_soup(4000, seed=78, scale=0.15, n_meshes=40)
+    elif kind == "boxes":
+        flat = _axis_aligned_box_scene()
+    elif kind == "golden":
+        flat = golden.flat
+    else:
+        flat = capi.dragon_standin()
+    fast, exact = capi.Scene(flat, exact_only=False), capi.Scene(flat, exact_only=True)
+    rays = ob.random_rays(200000, seed=31)
+    rays["t"][::7] = np.float32(0.8)
+    # axis-parallel and grid-aligned rays: zero direction components, origins on box faces
+    k = 20000
+    rays["d"][:k] = np.eye(3, dtype=np.float32)[np.arange(k) % 3] * np.where(np.arange(k) % 2, 1, -1)[:, None].astype(np.float32)
+    rays["o"][:k] = np.round(rays["o"][:k] * 10) / 10 * np.float32(0.7)
+    hf, he = fast.intersect(rays), exact.intersect(rays)
+    for f in ("t", "tri", "alpha", "beta", "gamma", "n"):
+        assert same_bits(hf[f], he[f]), f
+    if kind != "dragon":
+        g = oracle.scene(flat).bvh().intersect(rays[:40000])
+        assert hits_equal(hf[:40000], g, flat.canonical_ids())
+    rng = np.random.default_rng(3)
+    far = rays.copy()
+    far["t"] = np.float32(np.finfo(np.float32).max)
+    for md in (np.full(len(rays), np.inf, np.float32), rng.uniform(0, 2, len(rays)).astype(np.float32)):
+        assert np.array_equal(fast.intersect_any(far, md), exact.intersect_any(far, md))
+    # frames: same pixels bit for bit, same ray counts; the replay share is reported, not asserted (scene dependent)
+    W, H, L = 320, 200, 4
+    lights = np.array([[-1, 1, -1, 1, 1, 1], [0.3, 0.2, 0.1, 0.5, 0.5, 0.5]], np.float32)
+    fast.set_lights(lights)
+    exact.set_lights(lights)
+    cam = capi.make_camera(W, H)
+    a, sa = fast.render(cam, W, H, trace_limit=L)
+    b, sb = exact.render(cam, W, H, trace_limit=L)
+    assert np.array_equal(bits(a), bits(b))
+    for key in ("primary", "primary_hit", "shadow", "bounce"):
+        assert sa[key] == sb[key], key
+    assert sb["replayed_closest"] == 0 and sb["replayed_shadow"] == 0
+    print(f"[{kind}] rays {sa['primary'] + sa['shadow'] + sa['bounce']}: replayed closest {sa['replayed_closest']}, shadow {sa['replayed_shadow']}")
