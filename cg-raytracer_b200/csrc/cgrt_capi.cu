@@ -177,7 +177,7 @@ struct cgrt_scene {
     int64_t nTris = 0;
     int nMeshes = 0;
 
-    DevBuf<float4> nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, pairs, wide;
+    DevBuf<float4> tri4, nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, pairs, wide;
     DevBuf<int> origToLeaf, refParent;
     DevScene dev{};
 
@@ -234,7 +234,7 @@ static void destroyScene(cgrt_scene* s)
         return;
     }
     cudaSetDevice(s->device);
-    s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
+    s->tri4.release(); s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
     s->triN0.release(); s->triN1.release(); s->triN2.release(); s->mats.release(); s->spheres.release();
     s->origToLeaf.release(); s->refParent.release(); s->pairs.release(); s->wide.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->tileSeq.release(); s->frame.release();
@@ -457,19 +457,22 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
 #undef UP
     rc = s->triPl.ensure(T);
     if (rc) { destroyScene(s); return rc; }
+    rc = s->tri4.ensure(4 * T);
+    if (rc) { destroyScene(s); return rc; }
 
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
     if (e != cudaSuccess) { destroyScene(s); return fail(CGRT_ERR_CUDA, cudaGetErrorString(e)); }
 
-    launchSetupPlanes(s->triV0.p, s->triV1.p, s->triV2.p, s->triPl.p, (int)T, s->stream);
+    launchSetupPlanes(s->triV0.p, s->triV1.p, s->triV2.p, s->triPl.p, s->tri4.p, (int)T, s->stream);
     e = cudaStreamSynchronize(s->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { destroyScene(s); return fail(CGRT_ERR_CUDA, std::string("plane set-up kernel: ") + cudaGetErrorString(e)); }
 
     s->dev.nodes = s->nodes.p;
     s->dev.triPl = s->triPl.p;
+    s->dev.tri4 = s->tri4.p;
     s->dev.triV0 = s->triV0.p; s->dev.triV1 = s->triV1.p; s->dev.triV2 = s->triV2.p;
     s->dev.triN0 = s->triN0.p; s->dev.triN1 = s->triN1.p; s->dev.triN2 = s->triN2.p;
     s->dev.mats = s->mats.p;

@@ -34,7 +34,8 @@ struct LeafBest {
 // Returns true iff the triangle became the new best.
 RT_DEV bool leafCandidate(const DevScene& S, int i, const V3& o, const V3& d, LeafBest& best)
 {
-    const float4 pl = __ldg(S.triPl + i);
+    const float4* tr = S.tri4 + 4 * (size_t)i;
+    const float4 pl = __ldg(tr);
     const V3 n = mk3(pl);
     const float on = dot3(o, n);
     float tt;
@@ -53,7 +54,7 @@ RT_DEV bool leafCandidate(const DevScene& S, int i, const V3& o, const V3& d, Le
         if (best.shortcut) return false;
         if (tt == best.t && best.pos < 0) return false;
     }
-    const float4 v0 = __ldg(S.triV0 + i), v1 = __ldg(S.triV1 + i), v2 = __ldg(S.triV2 + i);
+    const float4 v0 = __ldg(tr + 1), v1 = __ldg(tr + 2), v2 = __ldg(tr + 3);
     const int rank = f2i(v2.w);
     if (shortcut) {
         if (best.shortcut && rank < best.rank) return false; // the last shortcut candidate in leaf order wins
@@ -617,7 +618,9 @@ RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps,
     const V3 o = T.o, d = T.d;
 #pragma unroll 1
     for (int i = first; i < first + count; i++) {
-        const float4 pl = __ldg(S.triPl + i);
+        // the whole 64-byte record at once: one memory round trip per triangle
+        const float4* tr = S.tri4 + 4 * (size_t)i;
+        const float4 pl = __ldg(tr), v0 = __ldg(tr + 1), v1 = __ldg(tr + 2), v2 = __ldg(tr + 3);
         const V3 n = mk3(pl);
         const float on = dot3(o, n);
         float tt = 0.0f;
@@ -630,7 +633,6 @@ RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps,
             if (!(tt <= T.t)) continue;                    // farther than the best (or NaN)
             if (tt == T.t && T.hitTri < 0) continue;       // equals the ray's own bound: rejected by `t >= ray.t`
         }
-        const float4 v0 = __ldg(S.triV0 + i), v1 = __ldg(S.triV1 + i), v2 = __ldg(S.triV2 + i);
         const V3 p = o + d * tt;
         if (!pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), n, p)) continue;
         if (shortcut || tt == T.t) return TRAV_DEFER;      // the outcome depends on the reference's visiting order

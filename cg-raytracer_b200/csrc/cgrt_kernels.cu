@@ -13,11 +13,17 @@ namespace cgrt {
 // Scene set-up: planes of all triangles (trianglePlane, src/ray_tracing.cpp:74-82) computed once, on the device.
 // =================================================================================================================
 __global__ void k_setup_planes(const float4* __restrict__ v0, const float4* __restrict__ v1, const float4* __restrict__ v2,
-                               float4* __restrict__ pl, int n)
+                               float4* __restrict__ pl, float4* __restrict__ tri4, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    pl[i] = trianglePlaneDev(mk3(v0[i]), mk3(v1[i]), mk3(v2[i]));
+    const float4 a = v0[i], b = v1[i], c = v2[i];
+    const float4 p = trianglePlaneDev(mk3(a), mk3(b), mk3(c));
+    pl[i] = p;
+    tri4[4 * (size_t)i + 0] = p;
+    tri4[4 * (size_t)i + 1] = a;
+    tri4[4 * (size_t)i + 2] = b;
+    tri4[4 * (size_t)i + 3] = c;
 }
 
 // =================================================================================================================
@@ -1235,9 +1241,9 @@ static inline int gridFor(size_t n, int block, int maxBlocks)
     return (int)g;
 }
 
-void launchSetupPlanes(const float4* v0, const float4* v1, const float4* v2, float4* pl, int n, cudaStream_t st)
+void launchSetupPlanes(const float4* v0, const float4* v1, const float4* v2, float4* pl, float4* tri4, int n, cudaStream_t st)
 {
-    if (n > 0) k_setup_planes<<<(n + 255) / 256, 256, 0, st>>>(v0, v1, v2, pl, n);
+    if (n > 0) k_setup_planes<<<(n + 255) / 256, 256, 0, st>>>(v0, v1, v2, pl, tri4, n);
 }
 
 void launchClosestBatch(const DevScene& S, const float4* rays, size_t n, float4* hits, uint32_t* counts, int numSMs,
