@@ -232,7 +232,10 @@ def main():
     cls_rays = [st_count["primary"], st_count["bounce"], st_count["shadow"]]
     alg_bytes_class = [B_RAY * cls_rays[c] + B_BOX * st_count["box_tests"][c] + B_TRI * st_count["tri_tests"][c] for c in range(3)]
     alg_bytes_frame_local = sum(alg_bytes_class)
-    if st_prof["class_launches"][1] == 0:  # path pipeline: k_paths traces the primary AND the bounce rays
+    names = capi.class_names(st_prof)
+    if names is capi.ROUND_CLASS_NAMES:  # round pipeline: k_trace (class 2) searches every ray of the frame
+        alg_bytes_class = [0, 0, alg_bytes_frame_local]
+    elif st_prof["class_launches"][1] == 0:  # path pipeline: k_paths traces the primary AND the bounce rays
         alg_bytes_class = [alg_bytes_class[0] + alg_bytes_class[1], 0, alg_bytes_class[2]]
     tot = torch.tensor([rays_local, st_count["primary"], st_count["shadow"], st_count["bounce"], alg_bytes_frame_local],
                        dtype=torch.float64, device=dev)
@@ -290,7 +293,7 @@ def main():
         except Exception:
             pass
         peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-        dom_name = capi.KERNEL_CLASS_NAMES[dominant]
+        dom_name = names[dominant]
         dom_avg_s = dom_ms * 1e-3 / max(dom_launches, 1)
         # algorithmic bytes of the rays this rank's launches of the dominant kernel process, averaged per launch
         dom_bytes_per_launch = alg_bytes_class[dominant] / max(st_prof["class_launches"][dominant], 1) if dominant < 3 else 0.0
@@ -311,8 +314,8 @@ def main():
                                     "nccl": "NCCL gather of tile-major buffers + assemble kernel"}[R.mode],
                        "exchange_fallback_reason": R.fallback_reason, "handoff_timeouts": timeouts,
                        "rays_per_frame": {"primary": n_primary, "shadow": n_shadow, "bounce": n_bounce},
-                       "kernel_ms_per_frame_rank0": dict(zip(capi.KERNEL_CLASS_NAMES, [round(v, 4) for v in st_prof["class_ms"]])),
-                       "kernel_launches_per_frame": dict(zip(capi.KERNEL_CLASS_NAMES, st_prof["class_launches"])),
+                       "kernel_ms_per_frame_rank0": dict(zip(names, [round(v, 4) for v in st_prof["class_ms"]])),
+                       "kernel_launches_per_frame": dict(zip(names, st_prof["class_launches"])),
                        "frame_roofline": {"algorithmic_bytes_per_frame": alg_bytes_frame, "bytes_per_ray": alg_bytes_frame / rays_frame,
                                           "achieved_GBps": alg_bytes_frame * args.steps / (total_ms * 1e-3) / 1e9,
                                           "frac_of_hbm_peak": alg_bytes_frame * args.steps / (total_ms * 1e-3) / 1e9 / (peak * world)}},

@@ -183,7 +183,13 @@ def make_camera(W, H, fovy_deg=50.0, dist=3.0, look_at=(0.0, 0.0, 0.0), euler_de
 
 K_PRIMARY, K_BOUNCE, K_SHADOW, K_SHADE = 0, 1, 2, 3
 # production (path pipeline) kernels per class; class 1 is only launched by the level-by-level counting pipeline
-KERNEL_CLASS_NAMES = ["k_paths", "k_bounce_closest", "k_shadow_all", "k_shade_paths"]
+KERNEL_CLASS_NAMES = ["k_paths", "k_bounce_closest", "k_shadow_all", "k_shade_paths"]  # path pipeline (exact-only scenes)
+ROUND_CLASS_NAMES = ["k_gen", "k_finish", "k_trace", "k_shade_slots"]                   # round pipeline (production)
+
+
+def class_names(stats):
+    """Kernel names behind cgrt_render_stats.class_ms / class_launches for the pipeline that produced `stats`."""
+    return ROUND_CLASS_NAMES if stats["class_launches"][1] > 0 and stats["box_tests"] == [0, 0, 0] else KERNEL_CLASS_NAMES
 RENDER_PROFILE_ALL, RENDER_COUNT, RENDER_SCREEN_LAYOUT = 0xF, 0x100, 0x200
 IPC_HANDLE_BYTES = 64
 

@@ -17,7 +17,7 @@
 
 using namespace cgrt;
 #ifdef CGRT_INSTRUMENT
-namespace cgrt { void readInstrumentation(unsigned long long* out, bool reset); void readTimeline(unsigned int* out, bool reset); }
+namespace cgrt { void readInstrumentation(unsigned long long* out, bool reset); void readTimeline(unsigned int* out, bool reset); void readStepHist(unsigned int* out, bool reset); }
 #endif
 
 static thread_local std::string g_err;
@@ -198,6 +198,8 @@ struct cgrt_scene {
     DevBuf<float4> hitRec;
     DevBuf<int> hitList, pathDepth, replayShadow;
     DevBuf<float4> replayQ;
+    DevBuf<float4> cRay[2], cRes[2], sRay[2], sRes[2];
+    int lastPipeline = 0; // 0 counting wavefront, 1 path pipeline, 2 round pipeline
     bool lastPathPipeline = false;
     std::vector<cudaEvent_t> traceEvents;
     WaveTrace trace{};
@@ -239,6 +241,7 @@ static void destroyScene(cgrt_scene* s)
     s->origToLeaf.release(); s->refParent.release(); s->pairs.release(); s->wide.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->tileSeq.release(); s->frame.release();
     s->tests.release(); s->hitRec.release(); s->hitList.release(); s->pathDepth.release(); s->replayShadow.release(); s->replayQ.release();
+    for (int k = 0; k < 2; k++) { s->cRay[k].release(); s->cRes[k].release(); s->sRay[k].release(); s->sRes[k].release(); }
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->hParamRing) cudaFreeHost(s->hParamRing);
     if (s->hFramePinned) cudaFreeHost(s->hFramePinned);
@@ -436,10 +439,10 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
         pack(l.lo, l.hi, refId(n.child0), (uint32_t)n.child0, out);
         pack(r.lo, r.hi, refId(n.child1), (uint32_t)n.child1, out + 2);
     }
-    std::vector<float4> hWide(s->bvh.wide.size() * 14);
+    std::vector<float4> hWide(s->bvh.wide.size() * 16, make_float4(0.0f, 0.0f, 0.0f, 0.0f)); // 256-byte nodes (cgrt_device.cuh CGRT_WIDE_STRIDE)
     for (size_t j = 0; j < s->bvh.wide.size(); j++) {
         const WideNode& n = s->bvh.wide[j];
-        float4* out = hWide.data() + 14 * j;
+        float4* out = hWide.data() + 16 * j;
         for (int k = 0; k < 3; k++)
             for (int h = 0; h < 2; h++) {
                 out[2 * k + h] = make_float4(n.lo[4 * h][k], n.lo[4 * h + 1][k], n.lo[4 * h + 2][k], n.lo[4 * h + 3][k]);
@@ -824,6 +827,14 @@ int cgrt_tile_list(const cgrt_render_params* p, int32_t rank, int32_t* out, int3
     return (int)l.size();
 }
 
+// the round pipeline needs the fast tree and lit-flag indices that fit the ray record's 30 bits
+static bool useRounds(const cgrt_scene* s, const FrameParams& P)
+{
+    if (s->dev.fastRoot == 0u) return false;
+    const uint64_t flags = (uint64_t)std::max(P.nSlots, 1) * (uint64_t)std::max(P.traceLimit, 1) * (uint64_t)std::max(P.nLights, 1);
+    return flags < ((uint64_t)1 << 30);
+}
+
 static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, FrameParams& P,
                         const int** dTileList, const int2** dTileSeq)
 {
@@ -883,6 +894,16 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
         RC(s->bounceQ.ensure(cap * 2));
         RC(s->lit.ensure(cap * nL));
         RC(s->pathState.ensure(cap * 2 * levels));
+    } else if (useRounds(s, P)) { // round pipeline: records indexed by (pixel slot, level), two ray lists per kind
+        RC(s->hitRec.ensure(cap * pathLevels * 3));
+        RC(s->pathDepth.ensure(cap));
+        RC(s->lit.ensure(cap * pathLevels * nL));
+        for (int k = 0; k < 2; k++) {
+            RC(s->cRay[k].ensure(cap * 3));
+            RC(s->cRes[k].ensure(cap));
+            RC(s->sRay[k].ensure(cap * nL * 3));
+            RC(s->sRes[k].ensure(cap * nL));
+        }
     } else { // path pipeline: one record per (path, level)
         RC(s->hitRec.ensure(cap * pathLevels * 3));
         RC(s->hitList.ensure(cap * pathLevels));
@@ -961,7 +982,23 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
         launches = launchWavefront(s->dev, (const FrameParams*)s->dParamBlock.p, P,
                                    (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), B, dTiles, d_out,
                                    s->di.numSMs, true, &s->trace, st);
+    } else if (useRounds(s, P)) {
+        RoundBuffers RB;
+        for (int k = 0; k < 2; k++) {
+            RB.cRay[k] = s->cRay[k].p; RB.cRes[k] = s->cRes[k].p;
+            RB.sRay[k] = s->sRay[k].p; RB.sRes[k] = s->sRes[k].p;
+        }
+        RB.hitRec = s->hitRec.p;
+        RB.lit = s->lit.p;
+        RB.pathDepth = s->pathDepth.p;
+        RB.counts = s->counts.p;
+        RB.levels = std::max(P.traceLimit, 1);
+        launches = launchRoundPipeline(s->dev, (const FrameParams*)s->dParamBlock.p, P,
+                                       (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), RB, dSeq, d_out,
+                                       s->di.numSMs, &s->trace, st);
+        s->lastPipeline = 2;
     } else {
+        s->lastPipeline = 1;
         PathBuffers PB;
         PB.hitRec = s->hitRec.p;
         PB.hitList = s->hitList.p;
@@ -978,6 +1015,7 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
                                       s->di.numSMs, &s->trace, st);
     }
     s->lastPathPipeline = !countTests;
+    if (countTests) s->lastPipeline = 0;
     CK(cudaEventRecord(s->ev1, st));
     s->lastCounted = countTests;
     CK(cudaGetLastError());
@@ -1002,7 +1040,15 @@ int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
     // logical rays: primary = pixels of this rank inside the image
     const uint64_t primary = s->primaryPixels;
     stats->primary = primary;
-    if (s->lastPathPipeline) {
+    if (s->lastPipeline == 2) {
+        stats->primary_hit = (uint64_t)counts[CGRT_CNT_PATHS];
+        for (int l = 0; l < P.traceLimit; l++) {
+            stats->shadow += (uint64_t)counts[CGRT_CNT_HIT + l] * (uint64_t)P.nLights;
+            if (l >= 1) stats->bounce += (uint64_t)counts[CGRT_CNT_BOUNCE + l];
+        }
+        stats->replayed_closest = (uint32_t)counts[CGRT_CNT_REPLAY_PATHS];
+        stats->replayed_shadow = (uint32_t)counts[CGRT_CNT_REPLAY_SHADOW];
+    } else if (s->lastPathPipeline) {
         stats->primary_hit = (uint64_t)counts[CGRT_CNT_PATHS];
         stats->shadow = (uint64_t)counts[CGRT_CNT_HITS] * (uint64_t)P.nLights;
         stats->bounce = (uint64_t)counts[CGRT_CNT_BOUNCES];
@@ -1136,6 +1182,7 @@ int cgrt_quantize_rgba8(int device, const float* d_frame, size_t n_pixels, uint8
 #ifdef CGRT_INSTRUMENT
 void cgrt_debug_instrumentation(unsigned long long* out, int reset) { cgrt::readInstrumentation(out, reset != 0); }
 void cgrt_debug_timeline(unsigned int* out, int reset) { cgrt::readTimeline(out, reset != 0); }
+void cgrt_debug_step_hist(unsigned int* out, int reset) { cgrt::readStepHist(out, reset != 0); }
 #endif
 
 // ---- peer memory + frame hand-off flags (multi-GPU, one process per GPU) ---------------------------------------------

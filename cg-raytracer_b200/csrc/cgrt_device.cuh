@@ -107,6 +107,11 @@ RT_DEV bool leafCandidate(const DevScene& S, int i, const V3& o, const V3& d, Le
 #define CGRT_SUB 0x40000000u
 #define CGRT_REFSCAN 0x80000000u
 
+#define CGRT_WIDE_STRIDE 16 // float4 per 8-wide node: 14 used, padded to 256 B = exactly two 128-byte lines
+
+// L1 prefetch hint: starts the fetch of a line the next step will read, without tying up a register
+RT_DEV void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 #define CGRT_RHO 1e-6f
 #define CGRT_TAU 1e-30f
 RT_DEV float errBound(float x) { return fabsf(x) * CGRT_RHO + CGRT_TAU; }
@@ -335,7 +340,7 @@ RT_DEV int travStepWide(const DevScene& S, Trav& T, TravStack& K)
         T.inLeaf = true;
         T.subBase = T.sp;
     }
-    const float4* w = S.wide + 14 * (size_t)(id & CGRT_IDX_MASK);
+    const float4* w = S.wide + CGRT_WIDE_STRIDE * (size_t)(id & CGRT_IDX_MASK);
     const float slack = 1.000001f;
     const float bt = T.best.t * slack;
     const V3 o = T.o, inv = T.inv;
@@ -501,10 +506,15 @@ struct FastTrav {
     uint32_t node;
 };
 #define CGRT_FASTSTACK 64
+#ifndef CGRT_PREFETCH
+#define CGRT_PREFETCH 1
+#endif
 struct FastStack {
     uint32_t n[CGRT_FASTSTACK];
     float t[CGRT_FASTSTACK];
 };
+
+RT_DEV void fastPrefetch(const DevScene& S, uint32_t id);
 
 // intersectDataStructure (bvh.cpp:831-844) evaluated exactly, then the fast tree's root.
 // TRAV_DONE: the reference does not enter the tree (certain miss); TRAV_DEFER: this ray must take the exact traversal.
@@ -534,15 +544,33 @@ RT_DEV int fastBegin(const DevScene& S, FastTrav& T, const V3& o, const V3& d, f
     T.inv.y = ay == 0.0f ? 1e30f : 1.0f / d.y;
     T.inv.z = az == 0.0f ? 1e30f : 1.0f / d.z;
     T.node = S.fastRoot;
+    fastPrefetch(S, T.node);
     return TRAV_CONTINUE;
 }
 
-RT_DEV int fastPop(FastTrav& T, FastStack& K, float bound)
+// start fetching what the next step on `id` reads: both lines of an 8-wide node, or the 64-byte records of a leaf's triangles
+RT_DEV void fastPrefetch(const DevScene& S, uint32_t id)
+{
+#if CGRT_PREFETCH
+    if (id & CGRT_TRI) {
+        const float4* tr = S.tri4 + 4 * (size_t)(id & CGRT_IDX_MASK);
+        const int count = (int)((id >> CGRT_TRICNT_SHIFT) & 7u) + 1;
+        for (int k = 0; k < count; k++) prefetchL1(tr + 4 * k);
+    } else {
+        const float4* w = S.wide + CGRT_WIDE_STRIDE * (size_t)(id & CGRT_IDX_MASK);
+        prefetchL1(w);
+        prefetchL1(w + 8);
+    }
+#endif
+}
+
+RT_DEV int fastPop(const DevScene& S, FastTrav& T, FastStack& K, float bound)
 {
     while (T.sp > 0) {
         T.sp--;
         if (K.t[T.sp] > bound) continue;
         T.node = K.n[T.sp];
+        fastPrefetch(S, T.node);
         return TRAV_CONTINUE;
     }
     return TRAV_DONE;
@@ -559,7 +587,7 @@ RT_DEV float fastBound(const FastTrav& T, float maxDist)
 template <bool ANY>
 RT_DEV int fastStepWide(const DevScene& S, FastTrav& T, FastStack& K, float maxDist)
 {
-    const float4* w = S.wide + 14 * (size_t)(T.node & CGRT_IDX_MASK);
+    const float4* w = S.wide + CGRT_WIDE_STRIDE * (size_t)(T.node & CGRT_IDX_MASK);
     const float slack = 1.000001f;
     const float bt = fastBound<ANY>(T, maxDist);
     const V3 o = T.o, inv = T.inv;
@@ -588,7 +616,7 @@ RT_DEV int fastStepWide(const DevScene& S, FastTrav& T, FastStack& K, float maxD
             if (hit) hitMask |= 1u << (4 * h + c);
         }
     }
-    if (hitMask == 0u) return fastPop(T, K, bt);
+    if (hitMask == 0u) return fastPop(S, T, K, bt);
     if (T.sp + 7 > CGRT_FASTSTACK) return TRAV_DEFER; // pathological depth: let the exact traversal handle the ray
     int best = -1;
     float bestT = 0.0f;
@@ -605,6 +633,7 @@ RT_DEV int fastStepWide(const DevScene& S, FastTrav& T, FastStack& K, float maxD
         }
     }
     T.node = cid[best];
+    fastPrefetch(S, T.node);
     return TRAV_CONTINUE;
 }
 
@@ -640,7 +669,7 @@ RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps,
         T.hitTri = i;
         if (ANY && !(tt + eps >= maxDist)) return TRAV_FIRED;
     }
-    return fastPop(T, K, fastBound<ANY>(T, maxDist));
+    return fastPop(S, T, K, fastBound<ANY>(T, maxDist));
 }
 
 // does the reference reach the leaf of triangle `pos` while ray.t is still above tStar? (see the block comment above)

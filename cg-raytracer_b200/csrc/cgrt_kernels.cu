@@ -492,6 +492,7 @@ __device__ unsigned long long g_instr[16];
 // timeline: per kernel kind (0 closest, 1 any) and 25 us bucket since the first burst of the launch: [warps bursting, lanes running]
 __device__ unsigned long long g_t0[2];
 __device__ unsigned int g_tl[2][128][2];
+__device__ unsigned int g_stepHist[64]; // k_trace: rays by number of steps (bucket = steps / 8, last bucket open)
 // the value is evaluated by ALL lanes (it may contain warp collectives); lane 0 adds it
 #define INSTR_ADD(i, v) do { const unsigned long long v_ = (unsigned long long)(v); if ((threadIdx.x & 31) == 0) atomicAdd(&g_instr[i], v_); } while (0)
 #else
@@ -1103,6 +1104,317 @@ __global__ void __launch_bounds__(128) k_shade_paths(DevScene S, const FramePara
     }
 }
 
+// =================================================================================================================
+// Round pipeline (production for scenes with a fast tree): k_gen -> { k_trace -> k_finish } per level -> k_shade_slots
+// =================================================================================================================
+// Measurements of the path pipeline above (profiles/r01_tuning.md) showed that its traversal kernels spent two thirds of their
+// issued instructions outside traversal steps: ray set-up, certificate, fp64 hit epilogue and record keeping executed inside
+// the persistent loop with a dozen of 32 lanes active. Here the persistent kernel does nothing but search steps; everything
+// per-ray runs in flat, converged kernels before and after it, and rays of one warp are neighbours on the screen.
+#ifndef CGRT_TRACE_STEPS
+#define CGRT_TRACE_STEPS 8
+#endif
+#ifndef CGRT_TRACE_MINBLOCKS
+#define CGRT_TRACE_MINBLOCKS 8
+#endif
+#ifndef CGRT_TRACE_REFILL
+#define CGRT_TRACE_REFILL 4
+#endif
+#define CGRT_RAY_ANY 0x40000000 // ray record c.y: any-hit ray (value & 0x3fffffff = index of its lit flag); else the level
+
+RT_DEV void writeRay(float4* q, const V3& o, float tIn, const V3& d, float maxDist, int slot, int meta, float eps)
+{
+    q[0] = make_float4(o.x, o.y, o.z, tIn);
+    q[1] = make_float4(d.x, d.y, d.z, maxDist);
+    q[2] = make_float4(i2f(slot), i2f(meta), eps, 0.0f);
+}
+
+// ---- level 0: ray generation + intersectDataStructure's root test; rays that enter are compacted in slot order ------------
+__global__ void __launch_bounds__(128) k_gen(DevScene S, const FrameParams* __restrict__ Pp, RoundBuffers B,
+                                             const int2* __restrict__ tileSeq, float* __restrict__ fb)
+{
+    const FrameParams P = *Pp;
+    const int n = P.nSlots;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int slot = base + threadIdx.x;
+        bool push = false;
+        V3 o = mk3(P.camX, P.camY, P.camZ), d = mk3(0.0f, 0.0f, 0.0f);
+        if (slot < n) {
+            int x, y, outIdx, local;
+            B.pathDepth[slot] = 0;
+            if (seqToPixel(P, tileSeq, slot, x, y, outIdx, local)) {
+                d = primaryDirection(P, x, y);
+                // a ray that does not enter the tree (bvh.cpp:831-844) can only hit spheres
+                bool enter = S.nSpheres > 0;
+                if (!enter && S.nNodes > 0) {
+                    const float4 q0 = __ldg(S.nodes + 0), q1 = __ldg(S.nodes + 1);
+                    enter = startsInBox(o, mk3(q0), mk3(q1));
+                    if (!enter) {
+                        float tmp;
+                        enter = slabTest(mk3(q0), mk3(q1), o, d, FLT_MAX, tmp);
+                    }
+                }
+                push = enter;
+                if (!enter) storeRGB(fb, outIdx, mk3(0.0f, 0.0f, 0.0f)); // trace(): miss -> black, src/main.cpp:288-294
+            } else if (!P.screenLayout) {
+                storeRGB(fb, local, mk3(0.0f, 0.0f, 0.0f)); // padding pixels of edge tiles in the tile-major buffer
+            }
+        }
+        const int q = warpPush(B.counts + CGRT_CNT_BOUNCE + 0, push);
+        if (push) writeRay(B.cRay[0] + 3 * (size_t)q, o, FLT_MAX, d, __int_as_float(0x7f800000), slot, 0, 0.0f);
+    }
+}
+
+// ---- the search: persistent warps, nothing but steps ------------------------------------------------------------------------
+// Work items [0, nA) are the shadow rays of list A, [nA, nA + nB) the closest-hit rays of list B. A finished lane stores
+// (state, t, tri) and takes the next ray as soon as CGRT_TRACE_REFILL lanes of its warp are idle.
+RT_DEV int fastStepAny(const DevScene& S, FastTrav& T, FastStack& K, bool any, float eps, float maxDist)
+{
+    if (travIsLeaf(T.node)) return any ? fastStepLeaf<true>(S, T, K, eps, maxDist) : fastStepLeaf<false>(S, T, K, eps, maxDist);
+    return any ? fastStepWide<true>(S, T, K, maxDist) : fastStepWide<false>(S, T, K, maxDist);
+}
+
+__global__ void __launch_bounds__(128, CGRT_TRACE_MINBLOCKS) k_trace(DevScene S, const float4* __restrict__ raysA, float4* __restrict__ resA,
+                                                const int* __restrict__ nAp, int mulA, const float4* __restrict__ raysB,
+                                                float4* __restrict__ resB, const int* __restrict__ nBp, int* work)
+{
+    const int nA = nAp ? *nAp * mulA : 0, nB = nBp ? *nBp : 0; // list A holds mulA (= lights) rays per counted hit
+    const int n = nA + nB;
+    // a block whose first wave would find the list already handed out has nothing to do (small late rounds)
+    if ((long long)blockIdx.x * blockDim.x >= (long long)n) return;
+    FastTrav T;
+    FastStack K;
+    int idx = -1;
+    int state = TRAV_DONE;
+    float eps = 0.0f, maxDist = 0.0f;
+    bool exhausted = false;
+    const int lane = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+#ifdef CGRT_INSTRUMENT
+    int nSteps = 0;
+#define TRACE_DONE_INSTR() do { int b_ = nSteps / 8; if (b_ > 63) b_ = 63; atomicAdd(&g_stepHist[b_], 1u); nSteps = 0; } while (0)
+#define TRACE_STEP_INSTR() nSteps++
+#else
+#define TRACE_DONE_INSTR() do { } while (0)
+#define TRACE_STEP_INSTR() do { } while (0)
+#endif
+    INSTR_ADD(15, 1);
+    while (true) {
+        const unsigned idle = __ballot_sync(0xffffffffu, idx < 0);
+        const int nIdle = __popc(idle);
+        if (!exhausted && nIdle >= CGRT_TRACE_REFILL) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(work, nIdle);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + nIdle >= n) exhausted = true;
+            if (idx < 0) {
+                const int mine = base + __popc(idle & ltMask);
+                if (mine < n) {
+                    idx = mine;
+                    const float4* r = mine < nA ? raysA + 3 * (size_t)mine : raysB + 3 * (size_t)(mine - nA);
+                    const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
+                    maxDist = b.w;
+                    eps = c.z;
+                    state = fastBegin(S, T, mk3(a), mk3(b), a.w);
+                }
+            }
+            INSTR_ADD(8, 1); INSTR_ADD(9, nIdle);
+        } else if (idle == 0xffffffffu) {
+            break; // exhausted and every lane is done
+        }
+#pragma unroll 1
+        for (int it = 0; it < CGRT_TRACE_STEPS; it++) {
+            if (idx >= 0 && state != TRAV_CONTINUE) { // finished (possibly right at fastBegin): hand in the result
+                float4* out = idx < nA ? resA + idx : resB + (idx - nA);
+                *out = make_float4(i2f(state), T.t, i2f(T.hitTri), 0.0f);
+                idx = -1;
+                TRACE_DONE_INSTR();
+            }
+            const bool run = idx >= 0;
+            const bool leaf = run && travIsLeaf(T.node);
+            const int sAll = __popc(__ballot_sync(0xffffffffu, run));
+            const int sLeaf = __popc(__ballot_sync(0xffffffffu, leaf));
+            INSTR_ADD(0, 1); INSTR_ADD(1, sAll);
+            if (sAll == 0 || (!exhausted && 32 - sAll >= CGRT_TRACE_REFILL && it > 0)) break;
+            const bool any = idx >= 0 && idx < nA;
+            if (sAll - sLeaf >= sLeaf * CGRT_FAST_W_LEAF) {
+                INSTR_ADD(2, 1); INSTR_ADD(5, sAll - sLeaf);
+                if (run && !leaf) { state = any ? fastStepWide<true>(S, T, K, maxDist) : fastStepWide<false>(S, T, K, maxDist); TRACE_STEP_INSTR(); }
+            } else {
+                INSTR_ADD(4, 1); INSTR_ADD(7, sLeaf);
+                if (leaf) { state = any ? fastStepLeaf<true>(S, T, K, eps, maxDist) : fastStepLeaf<false>(S, T, K, eps, maxDist); TRACE_STEP_INSTR(); }
+            }
+        }
+        if (idx >= 0 && state != TRAV_CONTINUE) {
+            float4* out = idx < nA ? resA + idx : resB + (idx - nA);
+            *out = make_float4(i2f(state), T.t, i2f(T.hitTri), 0.0f);
+            idx = -1;
+            TRACE_DONE_INSTR();
+        }
+    }
+}
+
+// ---- after the search: one thread per ray ------------------------------------------------------------------------------------
+// Shadow rays (list A, produced by the hits of level `level - 1`): certificate or exact replay, sphere loop, lit flag.
+// Closest-hit rays (list B, level `level`): certificate or exact replay, sphere loop, hit epilogue, hit record; emits the
+// shadow rays of the hit (pointInShadow, main.cpp:104-135) and its reflection ray (shade(), main.cpp:246-256).
+__global__ void __launch_bounds__(128) k_finish(DevScene S, const FrameParams* __restrict__ Pp, const float4* __restrict__ lights,
+                                                RoundBuffers B, int level, const float4* __restrict__ raysA,
+                                                const float4* __restrict__ resA, const int* __restrict__ nAp,
+                                                const float4* __restrict__ raysB, const float4* __restrict__ resB,
+                                                const int* __restrict__ nBp, float4* __restrict__ nextC, float4* __restrict__ nextS,
+                                                float* __restrict__ fb, const int2* __restrict__ tileSeq)
+{
+    const FrameParams P = *Pp;
+    const int nL = P.nLights;
+    const int nA = nAp ? *nAp * nL : 0, nB = nBp ? *nBp : 0;
+    const int n = nA + nB;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        bool hit = false, bounce = false, replayC = false, replayS = false;
+        V3 pointOn = mk3(0.0f, 0.0f, 0.0f), nn = pointOn, rd = pointOn;
+        int slot = 0, rec = 0;
+        if (i < nA) { // ---- shadow ray
+            const float4* r = raysA + 3 * (size_t)i;
+            const float4 a = r[0], b = r[1], c = r[2], res = resA[i];
+            const V3 o = mk3(a), d = mk3(b);
+            const int state = f2i(res.x), tri = f2i(res.z);
+            const float eps = c.z, maxDist = b.w;
+            bool shadowed = false, settled = false;
+            if (state == TRAV_FIRED) {
+                if (certifyChain(S, o, d, tri, res.y)) { shadowed = true; settled = true; }
+            } else if (state == TRAV_DONE) { // the tree does not shadow; spheres may (bvh.cpp:878-879)
+                settled = true;
+                float t = res.y;
+                for (int sp = 0; sp < S.nSpheres; sp++) {
+                    const float4 sc = __ldg(S.spheres + 3 * sp);
+                    float ts;
+                    V3 sn;
+                    if (sphereTest(mk3(sc), sc.w, o, d, t, ts, sn)) {
+                        t = ts;
+                        if (!(ts + eps >= maxDist)) { shadowed = true; break; }
+                    }
+                }
+            }
+            if (!settled) { // not certifiable: the exact reference-order traversal decides
+                TraceResult R;
+                shadowed = traverseFast<true>(S, o, d, a.w, eps, maxDist, R);
+                replayS = true;
+            }
+            B.lit[f2i(c.y) & 0x3fffffff] = shadowed ? 0 : 1;
+        } else if (i < n) { // ---- closest-hit ray of `level`
+            const float4* r = raysB + 3 * (size_t)(i - nA);
+            const float4 a = r[0], b = r[1], c = r[2], res = resB[i - nA];
+            const V3 o = mk3(a), d = mk3(b);
+            slot = f2i(c.x);
+            const int state = f2i(res.x);
+            TraceResult R;
+            R.sphere = -1;
+            R.tri = f2i(res.z);
+            R.t = res.y;
+            bool settled = state == TRAV_DONE && (R.tri < 0 || certifyChain(S, o, d, R.tri, R.t));
+            if (settled) {
+                float t = R.t;
+                for (int sp = 0; sp < S.nSpheres; sp++) {
+                    const float4 sc = __ldg(S.spheres + 3 * sp);
+                    float ts;
+                    V3 sn;
+                    if (sphereTest(mk3(sc), sc.w, o, d, t, ts, sn)) {
+                        t = ts;
+                        R.sphere = sp;
+                        R.sphereN = sn;
+                    }
+                }
+                R.t = t;
+                hit = R.tri >= 0 || R.sphere >= 0;
+            } else {
+                hit = traverseFast<false>(S, o, d, a.w, 0.0f, 0.0f, R);
+                replayC = true;
+            }
+            if (!hit) {
+                if (level == 0) { // trace(): miss -> black, src/main.cpp:288-294
+                    int x, y, outIdx, local;
+                    if (seqToPixel(P, tileSeq, slot, x, y, outIdx, local)) storeRGB(fb, outIdx, mk3(0.0f, 0.0f, 0.0f));
+                }
+            } else {
+                int mat;
+                if (R.sphere >= 0) {
+                    nn = R.sphereN;
+                    mat = R.tri >= 0 ? f2i(__ldg(S.triV1 + R.tri).w) : -1;
+                } else {
+                    const int k = R.tri;
+                    const float4 v0 = __ldg(S.triV0 + k), v1 = __ldg(S.triV1 + k), v2 = __ldg(S.triV2 + k);
+                    const float4 n0 = __ldg(S.triN0 + k), n1 = __ldg(S.triN1 + k), n2 = __ldg(S.triN2 + k);
+                    const float4 pl = __ldg(S.triPl + k);
+                    float al, be, ga;
+                    hitEpilogue(mk3(v0), mk3(v1), mk3(v2), mk3(n0), mk3(n1), mk3(n2), mk3(pl), o, d, R.t, al, be, ga, nn);
+                    mat = f2i(v1.w);
+                }
+                pointOn = o + d * R.t; // main.cpp:164
+                rd = d;
+                rec = slot * B.levels + level;
+                float4* h = B.hitRec + 3 * (size_t)rec;
+                h[0] = make_float4(pointOn.x, pointOn.y, pointOn.z, i2f(mat));
+                h[1] = make_float4(nn.x, nn.y, nn.z, 0.0f);
+                h[2] = make_float4(d.x, d.y, d.z, 0.0f);
+                B.pathDepth[slot] = level + 1;
+                const float ksz = mat >= 0 ? __ldg(S.mats + 2 * mat + 1).z : 0.0f;
+                bounce = !(ksz <= 0.01f) && level + 1 < P.traceLimit; // shade(): mirror test main.cpp:246, trace limit :267
+            }
+        }
+        // ---- emission (warp-aggregated, slots stay in screen order within the warp)
+        if (level == 0) warpPush(B.counts + CGRT_CNT_PATHS, hit);
+        const int sBase = warpPush(B.counts + CGRT_CNT_HIT + level, hit && nL > 0);
+        const int cPos = warpPush(B.counts + CGRT_CNT_BOUNCE + level + 1, bounce);
+        const unsigned rc = __ballot_sync(0xffffffffu, replayC), rs = __ballot_sync(0xffffffffu, replayS);
+        if ((threadIdx.x & 31) == 0) {
+            if (rc) atomicAdd(B.counts + CGRT_CNT_REPLAY_PATHS, __popc(rc));
+            if (rs) atomicAdd(B.counts + CGRT_CNT_REPLAY_SHADOW, __popc(rs));
+        }
+        if (hit && nL > 0) {
+            for (int l = 0; l < nL; l++) { // pointInShadow, src/main.cpp:104-135
+                const V3 lightPos = mk3(__ldg(lights + 2 * l));
+                const V3 fromPosToLight = lightPos - pointOn;
+                const V3 dir = normalize3(fromPosToLight);
+                const float epsilon = 0.001f;
+                const V3 org = pointOn + epsilon * dir;
+                writeRay(nextS + 3 * ((size_t)sBase * nL + l), org, FLT_MAX, dir, length3(fromPosToLight), slot,
+                         CGRT_RAY_ANY | (rec * nL + l), epsilon);
+            }
+        }
+        if (bounce) { // ComputeReflectedRay, main.cpp:252-256: t = |incoming direction|, origin offset along the reflection
+            const V3 reflected = normalize3(reflect3(rd, nn));
+            const float epsilon = 0.001f;
+            writeRay(nextC + 3 * (size_t)cPos, pointOn + epsilon * reflected, length3(rd), reflected, __int_as_float(0x7f800000),
+                     slot, level + 1, 0.0f);
+        }
+    }
+}
+
+// one thread per pixel slot: direct colour of every level, then the recursion unwound innermost first (main.cpp:241-264)
+__global__ void __launch_bounds__(128) k_shade_slots(DevScene S, const FrameParams* __restrict__ Pp, const float4* __restrict__ lights,
+                                                     RoundBuffers B, const int2* __restrict__ tileSeq, float* __restrict__ fb)
+{
+    const FrameParams P = *Pp;
+    const int nL = P.nLights;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < P.nSlots; slot += gridDim.x * blockDim.x) {
+        const int depth = B.pathDepth[slot];
+        if (depth <= 0) continue; // the pixel is already final (black)
+        V3 direct[CGRT_MAX_LEVELS], ksv[CGRT_MAX_LEVELS];
+        for (int k = 0; k < depth; k++) {
+            const int rec = slot * B.levels + k;
+            const float4* r = B.hitRec + 3 * (size_t)rec;
+            direct[k] = directColour(S, lights, nL, r[0], r[1], r[2], B.lit + (size_t)rec * nL, ksv[k]);
+        }
+        int k = depth - 1;
+        V3 colour = (ksv[k].z <= 0.01f) ? direct[k] : direct[k] + mk3(0.0f, 0.0f, 0.0f) * ksv[k];
+        for (k = depth - 2; k >= 0; k--) colour = direct[k] + colour * ksv[k];
+        int x, y, outIdx, local;
+        if (seqToPixel(P, tileSeq, slot, x, y, outIdx, local)) storeRGB(fb, outIdx, colour);
+    }
+}
+
 // ---- shading + bounce emission: one thread per hit.  shading/shade, src/main.cpp:61-98, 220-264 ---------------------------
 __global__ void __launch_bounds__(128) k_shade(DevScene S, const FrameParams* __restrict__ Pp,
                                                const float4* __restrict__ lights, WaveBuffers B, int level,
@@ -1407,6 +1719,54 @@ int launchPathPipeline(const DevScene& S, const FrameParams* dP, const FramePara
     return launches;
 }
 
+int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
+                        const RoundBuffers& B, const int2* dTileSeq, float* fb, int numSMs, WaveTrace* tr, cudaStream_t st)
+{
+    cudaMemsetAsync(B.counts, 0, sizeof(int) * CGRT_CNT_TOTAL, st);
+    if (hP.traceLimit <= 0) { // trace(0, ...) returns black for every pixel without casting a ray, src/main.cpp:267-272
+        if (hP.world > 1 && hP.screenLayout) {
+            k_clear_tiles<<<gridFor((size_t)hP.nSlots, 128, numSMs * 16), 128, 0, st>>>(dP, dTileSeq, fb);
+            return 1;
+        }
+        const size_t px = hP.world == 1 ? (size_t)hP.width * hP.height : (size_t)hP.nSlots;
+        cudaMemsetAsync(fb, 0, px * 3 * sizeof(float), st);
+        return 0;
+    }
+    int launches = 0;
+    const int persistent = numSMs * tuning().blocks;
+    const int flat = gridFor((size_t)hP.nSlots, 128, numSMs * 16);
+    int* counts = B.counts;
+    traceBegin(tr, 0, st);
+    k_gen<<<flat, 128, 0, st>>>(S, dP, B, dTileSeq, fb);
+    traceEnd(tr, 0, st);
+    launches++;
+    const bool shadows = hP.nLights > 0;
+    const int rounds = hP.traceLimit + (shadows ? 1 : 0);
+    for (int r = 0; r < rounds; r++) {
+        // closest-hit rays of level r (list B) + shadow rays of the hits of level r-1 (list A)
+        const bool haveC = r < hP.traceLimit, haveS = shadows && r >= 1;
+        const float4* raysB = haveC ? B.cRay[r & 1] : nullptr;
+        float4* resB = haveC ? B.cRes[r & 1] : nullptr;
+        const int* nB = haveC ? counts + CGRT_CNT_BOUNCE + r : nullptr;
+        const float4* raysA = haveS ? B.sRay[(r - 1) & 1] : nullptr;
+        float4* resA = haveS ? B.sRes[(r - 1) & 1] : nullptr;
+        const int* nA = haveS ? counts + CGRT_CNT_HIT + (r - 1) : nullptr;
+        traceBegin(tr, 2, st);
+        k_trace<<<persistent, 128, 0, st>>>(S, raysA, resA, nA, hP.nLights, raysB, resB, nB, counts + CGRT_CNT_WORK + r);
+        traceEnd(tr, 2, st);
+        traceBegin(tr, 1, st);
+        k_finish<<<flat, 128, 0, st>>>(S, dP, dLights, B, r, raysA, resA, nA, raysB, resB, nB, B.cRay[(r + 1) & 1], B.sRay[r & 1],
+                                      fb, dTileSeq);
+        traceEnd(tr, 1, st);
+        launches += 2;
+    }
+    traceBegin(tr, 3, st);
+    k_shade_slots<<<flat, 128, 0, st>>>(S, dP, dLights, B, dTileSeq, fb);
+    traceEnd(tr, 3, st);
+    launches++;
+    return launches;
+}
+
 void launchAssemble(const float* gathered, size_t perRankFloats, const int* tileLists, const int* tileCounts, int maxTiles,
                     int world, int tileW, int tileH, int tilesX, int width, int height, float* frame, int numSMs,
                     cudaStream_t st)
@@ -1478,6 +1838,14 @@ void readInstrumentation(unsigned long long* out, bool reset)
     if (reset) {
         unsigned long long z[16] = {0};
         cudaMemcpyToSymbol(g_instr, z, sizeof z);
+    }
+}
+void readStepHist(unsigned int* out, bool reset)
+{
+    cudaMemcpyFromSymbol(out, g_stepHist, sizeof(unsigned int) * 64);
+    if (reset) {
+        static unsigned int z[64];
+        cudaMemcpyToSymbol(g_stepHist, z, sizeof z);
     }
 }
 void readTimeline(unsigned int* out, bool reset)

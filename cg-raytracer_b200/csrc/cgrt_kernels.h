@@ -110,6 +110,26 @@ struct PathBuffers {
     int levels;        // trace limit the buffers are laid out for
 };
 
+// Buffers of the ROUND pipeline (production when the scene has a fast tree; cgrt_kernels.cu "round pipeline"):
+//   k_gen      : one thread per pixel slot: primary ray, the reference's root-box test, compacted list of rays that enter
+//   round r    : k_trace  - persistent warps, speculative search ONLY (no prologue / epilogue code in the hot loop) over the
+//                           closest-hit rays of level r and the shadow rays of the hits of level r-1
+//                k_finish - one thread per traced ray, converged: certificate (or exact replay), sphere loop, hit epilogue,
+//                           hit record, emission of the next level's reflection ray and of the shadow rays
+//   k_shade_slots : one thread per pixel slot folds the levels back to the pixel
+// Ray record: 3 x float4  [origin | tmax] [direction | maxDist] [slot, level / lit index, eps, -]; result: [state, t, tri, -]
+struct RoundBuffers {
+    float4* cRay[2];   // closest-hit rays, double-buffered by level parity
+    float4* cRes[2];
+    float4* sRay[2];   // shadow rays, double-buffered by level parity
+    float4* sRes[2];
+    float4* hitRec;    // [slot * levels + level] 3 x float4: [P | matId] [N | -] [D | -]
+    uint8_t* lit;      // [(slot * levels + level) * nLights + light]
+    int* pathDepth;    // [slot] number of levels that recorded a hit (0: the pixel is already final)
+    int* counts;
+    int levels;
+};
+
 // optional per-kernel event trace of one wavefront (classes: 0 primary, 1 bounce closest-hit, 2 shadow, 3 shade)
 struct WaveTrace {
     cudaEvent_t* ev;   // 2 * maxKernels events
@@ -138,6 +158,8 @@ int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams&
                     cudaStream_t st);
 int launchPathPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
                        const PathBuffers& B, const int2* dTileSeq, float* fb, int numSMs, WaveTrace* tr, cudaStream_t st);
+int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
+                        const RoundBuffers& B, const int2* dTileSeq, float* fb, int numSMs, WaveTrace* tr, cudaStream_t st);
 void launchAssemble(const float* gathered, size_t perRankFloats, const int* tileLists, const int* tileCounts, int maxTiles,
                     int world, int tileW, int tileH, int tilesX, int width, int height, float* frame, int numSMs,
                     cudaStream_t st);

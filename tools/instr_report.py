@@ -15,6 +15,8 @@ out = (C.c_ulonglong * 16)()
 lib.cgrt_debug_instrumentation(out, 1)
 tl = (C.c_uint * 512)()
 lib.cgrt_debug_timeline(tl, 1)
+sh = (C.c_uint * 64)()
+lib.cgrt_debug_step_hist(sh, 1)
 _, st = s.render(cam, W, H, trace_limit=L)
 lib.cgrt_debug_instrumentation(out, 1)
 v = [int(x) for x in out]
@@ -23,7 +25,11 @@ print("warps %d iterations %d avg running lanes/iter %.2f" % (v[15], v[0], v[1] 
 for k, name in enumerate(("REF", "WIDE", "LEAF")):
     print("  class %-8s chosen %9d iterations (%.1f%%), avg lanes stepped %.2f" % (name, v[2 + k], 100.0 * v[2 + k] / max(v[0], 1), v[5 + k] / max(v[2 + k], 1)))
 print("refill rounds %d lanes %d (%.1f/round); retire rounds %d lanes %d (%.1f/round)" % (v[8], v[9], v[9] / max(v[8], 1), v[10], v[11], v[11] / max(v[10], 1)))
-tot = v[12] + v[13] + v[14]
+lib.cgrt_debug_step_hist(sh, 1)
+sh = np.array(list(sh)); cum = np.cumsum(sh) / max(sh.sum(), 1)
+print("k_trace steps per ray (bucket of 8 steps: rays): " + " ".join("%d:%d" % (8 * b, sh[b]) for b in range(64) if sh[b]))
+print("  mean steps (bucket mid) %.1f; 50/90/99/99.9%% below %s steps" % (float((sh * (np.arange(64) * 8 + 4)).sum() / max(sh.sum(), 1)), [int(8 * (np.searchsorted(cum, q) + 1)) for q in (0.5, 0.9, 0.99, 0.999)]))
+tot = max(v[12] + v[13] + v[14], 1)
 print("cycles: steps %.1f%% refill %.1f%% retire %.1f%%; per warp total %.0f cycles; per iteration %.0f cycles" % (100.0 * v[12] / tot, 100.0 * v[13] / tot, 100.0 * v[14] / tot, tot / max(v[15], 1), v[12] / max(v[0], 1)))
 
 lib.cgrt_debug_timeline(tl, 1)
