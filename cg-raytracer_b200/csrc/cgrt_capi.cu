@@ -177,7 +177,7 @@ struct cgrt_scene {
     int64_t nTris = 0;
     int nMeshes = 0;
 
-    DevBuf<float4> tri4, nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, pairs, wide;
+    DevBuf<float4> wide8, tri4, nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, pairs, wide;
     DevBuf<int> origToLeaf, refParent;
     DevScene dev{};
 
@@ -236,7 +236,7 @@ static void destroyScene(cgrt_scene* s)
         return;
     }
     cudaSetDevice(s->device);
-    s->tri4.release(); s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
+    s->wide8.release(); s->tri4.release(); s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
     s->triN0.release(); s->triN1.release(); s->triN2.release(); s->mats.release(); s->spheres.release();
     s->origToLeaf.release(); s->refParent.release(); s->pairs.release(); s->wide.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->tileSeq.release(); s->frame.release();
@@ -455,6 +455,17 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
         }
     }
     UP(wide, hWide);
+    std::vector<float4> hWide8(s->bvh.wide.size() * 16);
+    for (size_t jn = 0; jn < s->bvh.wide.size(); jn++) {
+        const WideNode& n = s->bvh.wide[jn];
+        for (int c = 0; c < 8; c++) {
+            float fid;
+            std::memcpy(&fid, &n.id[c], 4);
+            hWide8[16 * jn + 2 * c] = make_float4(n.lo[c][0], n.lo[c][1], n.lo[c][2], fid);
+            hWide8[16 * jn + 2 * c + 1] = make_float4(n.hi[c][0], n.hi[c][1], n.hi[c][2], 0.0f);
+        }
+    }
+    UP(wide8, hWide8);
     s->dev.rootId = NN > 0 ? (int)refId(0) : 0;
     UP(pairs, hPairs);
 #undef UP
@@ -482,6 +493,7 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     s->dev.origToLeaf = s->origToLeaf.p;
     s->dev.pairs = s->pairs.p;
     s->dev.wide = s->wide.p;
+    s->dev.wide8 = s->wide8.p;
     s->dev.refParent = s->refParent.p;
     s->dev.fastRoot = s->bvh.fastRoot;
     s->dev.nNodes = (int)NN;

@@ -450,6 +450,8 @@ struct Tuning {
     int vote = 1;    // 1: each step runs the node class picked by the warp vote; 0: every lane steps every iteration
     int wref = 4, wsub = 16, wleaf = 8;
     int blocks = 8;  // persistent CTAs (128 threads) per SM
+    int coop = 120000; // round pipeline: rounds with fewer rays than this are searched by k_trace8 (8 lanes per ray: low
+                       // latency), larger ones by k_trace (1 lane per ray: higher throughput)
 };
 static Tuning g_tune;
 static bool g_tuneLoaded = false;
@@ -476,6 +478,7 @@ static const Tuning& tuning()
                     else if (key == "wsub") g_tune.wsub = v;
                     else if (key == "wleaf") g_tune.wleaf = v;
                     else if (key == "blocks") g_tune.blocks = v;
+                    else if (key == "coop") g_tune.coop = v;
                 }
                 pos = c + 1;
             }
@@ -1176,10 +1179,11 @@ RT_DEV int fastStepAny(const DevScene& S, FastTrav& T, FastStack& K, bool any, f
 
 __global__ void __launch_bounds__(128, CGRT_TRACE_MINBLOCKS) k_trace(DevScene S, const float4* __restrict__ raysA, float4* __restrict__ resA,
                                                 const int* __restrict__ nAp, int mulA, const float4* __restrict__ raysB,
-                                                float4* __restrict__ resB, const int* __restrict__ nBp, int* work)
+                                                float4* __restrict__ resB, const int* __restrict__ nBp, int* work, int coopMax)
 {
     const int nA = nAp ? *nAp * mulA : 0, nB = nBp ? *nBp : 0; // list A holds mulA (= lights) rays per counted hit
     const int n = nA + nB;
+    if (n < coopMax) return; // small round: k_trace8 searches it
     // a block whose first wave would find the list already handed out has nothing to do (small late rounds)
     if ((long long)blockIdx.x * blockDim.x >= (long long)n) return;
     FastTrav T;
@@ -1252,6 +1256,204 @@ __global__ void __launch_bounds__(128, CGRT_TRACE_MINBLOCKS) k_trace(DevScene S,
             idx = -1;
             TRACE_DONE_INSTR();
         }
+    }
+}
+
+// ---- the search, cooperative form: EIGHT lanes per ray ----------------------------------------------------------------------
+// Profiling k_trace showed that every launch ends with a long tail: the warp that holds the longest rays runs ~140 dependent
+// iterations of ~350 instructions each with nothing to hide their latency (1.5 us per iteration, ~200 us per launch, six
+// launches per frame). Here a ray belongs to a group of 8 lanes: in an 8-wide node every lane tests ONE child box, in a leaf
+// every lane tests ONE triangle, and ballot / redux combine the group's answers. A step is ~60 instructions deep instead of
+// ~350, four rays of a warp diverge instead of thirty-two, and the node / triangle fetches of a group are single contiguous
+// 256 / 512-byte reads. The traversal stack of a group lives in shared memory. Same search (conservative boxes, the
+// reference's triangle arithmetic, smallest acceptable distance, defer on ties / in-plane shortcuts), so k_finish's
+// certificate applies unchanged.
+#ifndef CGRT_TRACE8
+#define CGRT_TRACE8 1
+#endif
+#ifndef CGRT_TRACE8_MINBLOCKS
+#define CGRT_TRACE8_MINBLOCKS 10
+#endif
+#define CGRT_STACK8 48
+
+__global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene S, const float4* __restrict__ raysA, float4* __restrict__ resA,
+                                                  const int* __restrict__ nAp, int mulA, const float4* __restrict__ raysB,
+                                                  float4* __restrict__ resB, const int* __restrict__ nBp, int* work, int coopMax)
+{
+    __shared__ uint2 stk[16][CGRT_STACK8]; // per group: (node id, entry distance bits)
+    const int nA = nAp ? *nAp * mulA : 0, nB = nBp ? *nBp : 0;
+    const int n = nA + nB;
+    if (n >= coopMax) return; // large round: k_trace searches it
+    // rays per global fetch of a warp: small rounds are spread over all warps (latency), large ones fetch 16 at a time
+    const int totalWarps = gridDim.x * 4;
+    int chunk = (n + totalWarps - 1) / totalWarps;
+    chunk = chunk < 4 ? 4 : (chunk > 16 ? 16 : chunk);
+    if ((long long)blockIdx.x * 4 * chunk >= (long long)n) return;
+    const int lane = threadIdx.x & 31, g = lane >> 3, j = lane & 7;
+    const unsigned gmask = 0xFFu << (8 * g);
+    uint2* K = stk[threadIdx.x >> 3];
+    const float slack = 1.000001f;
+    // group-uniform ray state (every lane of the group holds the same values)
+    V3 o = mk3(0.0f, 0.0f, 0.0f), d = o, inv = o;
+    float t = 0.0f, eps = 0.0f, maxDist = 0.0f;
+    int hitTri = -1, idx = -1, state = TRAV_DONE, sp = 0;
+    uint32_t node = 0u;
+    bool any = false;
+    int cur = 0, end = 0; // warp-uniform: the warp's current chunk of the work list
+    bool exhausted = false;
+    while (true) {
+        // ---- finished groups hand in their result, then the warp hands out rays (converged)
+        if (idx >= 0 && state != TRAV_CONTINUE) {
+            if (j == 0) {
+                float4* out = idx < nA ? resA + idx : resB + (idx - nA);
+                *out = make_float4(i2f(state), t, i2f(hitTri), 0.0f);
+            }
+            idx = -1;
+        }
+        const unsigned needy = __ballot_sync(0xffffffffu, idx < 0 && j == 0);
+        if (needy != 0u && !exhausted) {
+#pragma unroll
+            for (int gg = 0; gg < 4; gg++) {
+                if (!((needy >> (8 * gg)) & 1u) || exhausted) continue;
+                if (cur == end) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(work, chunk);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    cur = base;
+                    end = base + chunk < n ? base + chunk : n;
+                    if (cur >= n) {
+                        exhausted = true;
+                        continue;
+                    }
+                }
+                const int mine = cur++;
+                if (g == gg) {
+                    idx = mine;
+                    any = mine < nA;
+                    const float4* r = any ? raysA + 3 * (size_t)mine : raysB + 3 * (size_t)(mine - nA);
+                    const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
+                    o = mk3(a);
+                    d = mk3(b);
+                    maxDist = b.w;
+                    eps = c.z;
+                    FastTrav T0;
+                    state = fastBegin(S, T0, o, d, a.w);
+                    inv = T0.inv;
+                    t = a.w;
+                    hitTri = -1;
+                    sp = 0;
+                    node = T0.node;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, idx >= 0) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- one step of every active group. The per-lane tests run in divergent code WITHOUT collectives; the group results
+        // are then combined with full-warp ballots / shuffles that all 32 lanes execute together (per-group masks would split
+        // the warp into four separately scheduled quarters - measured 4x slower).
+        const bool active = idx >= 0 && state == TRAV_CONTINUE;
+        const bool isLeaf = (node & CGRT_TRI) != 0u;
+        const float bound = (any ? fminf(t, maxDist) : t) * slack;
+        bool p = false, amb = false;     // p: this lane's child box is hit / this lane's triangle is an acceptable candidate
+        unsigned key = 0xffffffffu;      // ordering key of the lane's result (entry distance | child, or candidate distance)
+        uint32_t id = 0u;
+        float ti = 0.0f;
+        if (active) {
+            if (isLeaf) {
+                // leaf: lane j tests triangle j with the reference's accept arithmetic (cgrt_device.cuh fastStepLeaf)
+                const int first = (int)(node & CGRT_IDX_MASK), count = (int)((node >> CGRT_TRICNT_SHIFT) & 7u) + 1;
+                if (j < count) {
+                    const float4* tr = S.tri4 + 4 * (size_t)(first + j);
+                    const float4 pl = __ldg(tr), v0 = __ldg(tr + 1), v1 = __ldg(tr + 2), v2 = __ldg(tr + 3);
+                    const V3 nrm = mk3(pl);
+                    const float on = dot3(o, nrm);
+                    const bool shortcut = (on == pl.w);
+                    bool cand = true;
+                    float tt = 0.0f;
+                    if (!shortcut) {
+                        const float denominator = dot3(d, nrm);
+                        if (denominator == 0) cand = false;
+                        else {
+                            tt = (pl.w - on) / denominator;
+                            if (tt < 0) cand = false;
+                            else if (!(tt <= t)) cand = false;               // farther than the best (or NaN)
+                            else if (tt == t && hitTri < 0) cand = false;    // equals the ray's own bound: `t >= ray.t`
+                        }
+                    }
+                    if (cand) {
+                        const V3 pt = o + d * tt;
+                        if (pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), nrm, pt)) {
+                            if (shortcut || tt == t) amb = true; // the outcome depends on the reference's visiting order
+                            else { p = true; key = __float_as_uint(tt + 0.0f); }
+                        }
+                    }
+                }
+            } else {
+                // 8-wide node: lane j tests child j against its pre-expanded box
+                const float4* c = S.wide8 + 16 * (size_t)(node & CGRT_IDX_MASK) + 2 * j;
+                const float4 lo = __ldg(c), hi = __ldg(c + 1);
+                id = (uint32_t)f2i(lo.w);
+                const float q0x = (lo.x - o.x) * inv.x, q1x = (hi.x - o.x) * inv.x;
+                const float q0y = (lo.y - o.y) * inv.y, q1y = (hi.y - o.y) * inv.y;
+                const float q0z = (lo.z - o.z) * inv.z, q1z = (hi.z - o.z) * inv.z;
+                ti = fmaxf(fmaxf(fminf(q0x, q1x), fminf(q0y, q1y)), fminf(q0z, q1z));
+                const float to = fminf(fminf(fmaxf(q0x, q1x), fmaxf(q0y, q1y)), fmaxf(q0z, q1z));
+                p = id != 0u && !(to < 0.0f || ti > to * slack || ti > bound);
+                if (p) key = (__float_as_uint(fmaxf(ti, 0.0f)) & ~7u) | (unsigned)j; // nearest first, ties by child index
+            }
+        }
+        // ---- combine within each group of 8 (full-warp collectives, converged)
+        const unsigned pm = (__ballot_sync(0xffffffffu, p) >> (8 * g)) & 0xFFu;
+        const unsigned ambm = (__ballot_sync(0xffffffffu, amb) >> (8 * g)) & 0xFFu;
+        unsigned mn = key;
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 1));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 2));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 4));
+        const unsigned winm = (__ballot_sync(0xffffffffu, p && key == mn) >> (8 * g)) & 0xFFu;
+        const uint32_t nextId = __shfl_sync(0xffffffffu, id, 8 * g + (int)(mn & 7u));
+        if (active) {
+            bool pop = false;
+            if (isLeaf) {
+                if (ambm != 0u || __popc(winm) > 1) {
+                    state = TRAV_DEFER; // ties at the smallest distance / in-plane shortcut
+                } else {
+                    if (pm != 0u) {
+                        t = __uint_as_float(mn);
+                        hitTri = (int)(node & CGRT_IDX_MASK) + (__ffs(winm) - 1);
+                    }
+                    if (any && pm != 0u && !(t + eps >= maxDist)) state = TRAV_FIRED;
+                    else pop = true;
+                }
+            } else if (pm == 0u) {
+                pop = true;
+            } else if (sp + 7 > CGRT_STACK8) {
+                state = TRAV_DEFER; // pathological depth: the exact traversal handles the ray
+            } else {
+                // nearest hit child next; the others go on the group's stack with their entry distance
+                const int best = (int)(mn & 7u);
+                if (p && j != best) {
+                    const unsigned before = pm & ((1u << j) - 1u) & ~(1u << best);
+                    K[sp + __popc(before)] = make_uint2(id, __float_as_uint(ti));
+                }
+                sp += __popc(pm) - 1;
+                node = nextId;
+            }
+            if (pop) {
+                const float b2 = (any ? fminf(t, maxDist) : t) * slack;
+                state = TRAV_DONE;
+                while (sp > 0) {
+                    sp--;
+                    const uint2 e = K[sp];
+                    if (__uint_as_float(e.y) > b2) continue;
+                    node = e.x;
+                    state = TRAV_CONTINUE;
+                    break;
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -1752,7 +1954,14 @@ int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FramePar
         float4* resA = haveS ? B.sRes[(r - 1) & 1] : nullptr;
         const int* nA = haveS ? counts + CGRT_CNT_HIT + (r - 1) : nullptr;
         traceBegin(tr, 2, st);
-        k_trace<<<persistent, 128, 0, st>>>(S, raysA, resA, nA, hP.nLights, raysB, resB, nB, counts + CGRT_CNT_WORK + r);
+        // the ray count of the round lives on the device: both searches are launched, the one that does not apply returns at once
+        const int coopMax = tuning().coop;
+        if (coopMax < (1 << 30))
+            k_trace<<<persistent, 128, 0, st>>>(S, raysA, resA, nA, hP.nLights, raysB, resB, nB, counts + CGRT_CNT_WORK + r, coopMax);
+        if (coopMax > 0)
+            k_trace8<<<numSMs * CGRT_TRACE8_MINBLOCKS, 128, 0, st>>>(S, raysA, resA, nA, hP.nLights, raysB, resB, nB,
+                                                                     counts + CGRT_CNT_WORK + r, coopMax);
+        launches++;
         traceEnd(tr, 2, st);
         traceBegin(tr, 1, st);
         k_finish<<<flat, 128, 0, st>>>(S, dP, dLights, B, r, raysA, resA, nA, raysB, resB, nB, B.cRay[(r + 1) & 1], B.sRay[r & 1],

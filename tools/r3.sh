@@ -1,4 +1,3 @@
-CGRT_LIB=$PWD/build_variants/lib_instr.so python tools/instr_report.py 2>&1 | tail -12 | cut -c1-1500
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_tmp.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 python - <<'PY'
 import csv
@@ -12,7 +11,6 @@ for r in rows[start+1:]:
     v=float(r[idx['Metric Value']].replace(',','')); u=r[idx['Metric Unit']]
     if u.startswith('n'): v/=1000
     elif u.startswith('m'): v*=1000
-    out.append((r[idx['Kernel Name']][:28], round(v,1)))
-# print the last frame's launches
-print(out[-16:])
+    out.append((r[idx['Kernel Name']].split('(')[0][-14:], round(v,1)))
+print(out[-15:])
 PY
