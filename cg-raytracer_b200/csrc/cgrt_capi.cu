@@ -200,6 +200,8 @@ struct cgrt_scene {
     DevBuf<float4> replayQ;
     DevBuf<float4> cRay[2], cRes[2], sRay[2], sRes[2];
     int lastPipeline = 0; // 0 counting wavefront, 1 path pipeline, 2 round pipeline
+    int lastChains = 1;
+    ChainSync chainSync{};
     bool lastPathPipeline = false;
     std::vector<cudaEvent_t> traceEvents;
     WaveTrace trace{};
@@ -245,6 +247,13 @@ static void destroyScene(cgrt_scene* s)
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->hParamRing) cudaFreeHost(s->hParamRing);
     if (s->hFramePinned) cudaFreeHost(s->hFramePinned);
+    if (s->chainSync.fork) {
+        cudaEventDestroy(s->chainSync.fork);
+        for (int c = 1; c < CGRT_MAX_CHAINS; c++) {
+            if (s->chainSync.streams[c]) cudaStreamDestroy(s->chainSync.streams[c]);
+            if (s->chainSync.join[c]) cudaEventDestroy(s->chainSync.join[c]);
+        }
+    }
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -910,11 +919,12 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
         RC(s->hitRec.ensure(cap * pathLevels * 3));
         RC(s->pathDepth.ensure(cap));
         RC(s->lit.ensure(cap * pathLevels * nL));
+        const size_t capR = cap + (size_t)CGRT_MAX_CHAINS * P.tileW * P.tileH; // per-chain rounding to whole tiles
         for (int k = 0; k < 2; k++) {
-            RC(s->cRay[k].ensure(cap * 3));
-            RC(s->cRes[k].ensure(cap));
-            RC(s->sRay[k].ensure(cap * nL * 3));
-            RC(s->sRes[k].ensure(cap * nL));
+            RC(s->cRay[k].ensure(capR * 3));
+            RC(s->cRes[k].ensure(capR));
+            RC(s->sRay[k].ensure(capR * nL * 3));
+            RC(s->sRes[k].ensure(capR * nL));
         }
     } else { // path pipeline: one record per (path, level)
         RC(s->hitRec.ensure(cap * pathLevels * 3));
@@ -927,7 +937,7 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
         }
     }
     RC(s->pathPix.ensure(cap));
-    RC(s->counts.ensure(CGRT_CNT_TOTAL));
+    RC(s->counts.ensure(CGRT_CNT_TOTAL * CGRT_MAX_CHAINS));
     RC(s->tests.ensure(6));
     // parameter block: FrameParams header + lights (2 x float4 each)
     const size_t need = CGRT_PARAM_BLOCK_HEADER + (size_t)nL * 32;
@@ -978,7 +988,7 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
     B.counts = s->counts.p;
     B.tests = s->tests.p;
     B.cap = (size_t)std::max(P.nSlots, 1);
-    const int maxKernels = 3 * CGRT_MAX_LEVELS + 1;
+    const int maxKernels = CGRT_TRACE_MAX_KERNELS;
     if ((p->flags & CGRT_RENDER_PROFILE_ALL) && s->traceEvents.empty()) {
         s->traceEvents.resize(2 * maxKernels);
         for (cudaEvent_t& e : s->traceEvents) CK(cudaEventCreate(&e));
@@ -995,19 +1005,34 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
                                    (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), B, dTiles, d_out,
                                    s->di.numSMs, true, &s->trace, st);
     } else if (useRounds(s, P)) {
-        RoundBuffers RB;
-        for (int k = 0; k < 2; k++) {
-            RB.cRay[k] = s->cRay[k].p; RB.cRes[k] = s->cRes[k].p;
-            RB.sRay[k] = s->sRay[k].p; RB.sRes[k] = s->sRes[k].p;
+        // chains: independent sub-frames (tiles dealt round-robin) on their own streams
+        const int nChains = roundPipelineChains();
+        if (nChains > 1 && !s->chainSync.fork) {
+            CK(cudaEventCreateWithFlags(&s->chainSync.fork, cudaEventDisableTiming));
+            for (int c = 1; c < CGRT_MAX_CHAINS; c++) {
+                CK(cudaStreamCreateWithFlags(&s->chainSync.streams[c], cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&s->chainSync.join[c], cudaEventDisableTiming));
+            }
         }
-        RB.hitRec = s->hitRec.p;
-        RB.lit = s->lit.p;
-        RB.pathDepth = s->pathDepth.p;
-        RB.counts = s->counts.p;
-        RB.levels = std::max(P.traceLimit, 1);
+        RoundBuffers RB[CGRT_MAX_CHAINS];
+        const size_t tpx = (size_t)P.tileW * P.tileH;
+        const size_t capC = ((size_t)std::max(P.nSlots, 1) / tpx / nChains + 1) * tpx; // slots one chain can own
+        const size_t nLc = (size_t)std::max(P.nLights, 1);
+        for (int c = 0; c < nChains; c++) {
+            for (int k = 0; k < 2; k++) {
+                RB[c].cRay[k] = s->cRay[k].p + c * capC * 3; RB[c].cRes[k] = s->cRes[k].p + c * capC;
+                RB[c].sRay[k] = s->sRay[k].p + c * capC * nLc * 3; RB[c].sRes[k] = s->sRes[k].p + c * capC * nLc;
+            }
+            RB[c].hitRec = s->hitRec.p;
+            RB[c].lit = s->lit.p;
+            RB[c].pathDepth = s->pathDepth.p;
+            RB[c].counts = s->counts.p + c * CGRT_CNT_TOTAL;
+            RB[c].levels = std::max(P.traceLimit, 1);
+        }
         launches = launchRoundPipeline(s->dev, (const FrameParams*)s->dParamBlock.p, P,
-                                       (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), RB, dSeq, d_out,
-                                       s->di.numSMs, &s->trace, st);
+                                       (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), RB, nChains, s->chainSync,
+                                       dSeq, d_out, s->di.numSMs, &s->trace, st);
+        s->lastChains = nChains;
         s->lastPipeline = 2;
     } else {
         s->lastPipeline = 1;
@@ -1047,7 +1072,15 @@ int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
     if (!s->haveLast) return fail(CGRT_ERR_INVALID, "no frame rendered yet");
     CK(cudaStreamSynchronize(s->lastStream));
     int counts[CGRT_CNT_TOTAL];
-    CK(cudaMemcpy(counts, s->counts.p, sizeof counts, cudaMemcpyDeviceToHost));
+    {
+        const int nc = s->lastPipeline == 2 ? s->lastChains : 1;
+        std::vector<int> all((size_t)CGRT_CNT_TOTAL * nc);
+        CK(cudaMemcpy(all.data(), s->counts.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < CGRT_CNT_TOTAL; k++) {
+            counts[k] = 0;
+            for (int c = 0; c < nc; c++) counts[k] += all[(size_t)c * CGRT_CNT_TOTAL + k];
+        }
+    }
     const FrameParams& P = s->lastParams;
     // logical rays: primary = pixels of this rank inside the image
     const uint64_t primary = s->primaryPixels;
@@ -1079,10 +1112,33 @@ int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
     CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     stats->device_ms = ms;
     for (int c = 0; c < 4; c++) stats->class_launches[c] = (uint32_t)s->trace.launches[c];
-    for (int k = 0; k < s->trace.n; k++) {
-        float kms = 0.0f;
-        CK(cudaEventElapsedTime(&kms, s->trace.ev[2 * k], s->trace.ev[2 * k + 1]));
-        stats->class_ms[s->trace.cls[k]] += kms;
+    // device time per kernel class = length of the UNION of its launches' intervals (launches of different chains overlap);
+    // timestamps are taken relative to the frame's first event, which works across streams
+    {
+        std::vector<std::pair<float, float>> iv[4];
+        for (int k = 0; k < s->trace.n; k++) {
+            float t0 = 0.0f, t1 = 0.0f;
+            CK(cudaEventElapsedTime(&t0, s->ev0, s->trace.ev[2 * k]));
+            CK(cudaEventElapsedTime(&t1, s->ev0, s->trace.ev[2 * k + 1]));
+            iv[s->trace.cls[k]].push_back(std::make_pair(t0, t1));
+        }
+        for (int c = 0; c < 4; c++) {
+            std::sort(iv[c].begin(), iv[c].end());
+            float total = 0.0f, curEnd = -1.0f, curBeg = 0.0f;
+            bool open = false;
+            for (const auto& x : iv[c]) {
+                if (!open || x.first > curEnd) {
+                    if (open) total += curEnd - curBeg;
+                    curBeg = x.first;
+                    curEnd = x.second;
+                    open = true;
+                } else if (x.second > curEnd) {
+                    curEnd = x.second;
+                }
+            }
+            if (open) total += curEnd - curBeg;
+            stats->class_ms[c] = total;
+        }
     }
     if (s->lastCounted) {
         unsigned long long t[6];

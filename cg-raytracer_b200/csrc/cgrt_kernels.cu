@@ -450,7 +450,9 @@ struct Tuning {
     int vote = 1;    // 1: each step runs the node class picked by the warp vote; 0: every lane steps every iteration
     int wref = 4, wsub = 16, wleaf = 8;
     int blocks = 8;  // persistent CTAs (128 threads) per SM
-    int coop = 120000; // round pipeline: rounds with fewer rays than this are searched by k_trace8 (8 lanes per ray: low
+    int chains = 4;    // round pipeline: independent pixel subsets rendered on separate streams so that the tail of one
+                       // subset's launch is filled by the other subsets' work
+    int coop = 15000;  // round pipeline: rounds with fewer rays than this are searched by k_trace8 (8 lanes per ray: low
                        // latency), larger ones by k_trace (1 lane per ray: higher throughput)
 };
 static Tuning g_tune;
@@ -479,6 +481,7 @@ static const Tuning& tuning()
                     else if (key == "wleaf") g_tune.wleaf = v;
                     else if (key == "blocks") g_tune.blocks = v;
                     else if (key == "coop") g_tune.coop = v;
+                    else if (key == "chains") g_tune.chains = v;
                 }
                 pos = c + 1;
             }
@@ -1133,16 +1136,22 @@ RT_DEV void writeRay(float4* q, const V3& o, float tIn, const V3& d, float maxDi
 }
 
 // ---- level 0: ray generation + intersectDataStructure's root test; rays that enter are compacted in slot order ------------
+// Chains: the tiles of the frame's sequence are dealt round-robin to `nChains` independent sub-frames (own ray lists, own
+// counters, own stream); this launch generates the rays of sub-frame `chain`.
 __global__ void __launch_bounds__(128) k_gen(DevScene S, const FrameParams* __restrict__ Pp, RoundBuffers B,
-                                             const int2* __restrict__ tileSeq, float* __restrict__ fb)
+                                             const int2* __restrict__ tileSeq, float* __restrict__ fb, int chain, int nChains)
 {
     const FrameParams P = *Pp;
-    const int n = P.nSlots;
+    const int tpx = P.tileW * P.tileH;
+    const int nTiles = P.nSlots / tpx;
+    const int myTiles = nTiles > chain ? (nTiles - chain + nChains - 1) / nChains : 0;
+    const int n = myTiles * tpx;
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const int slot = base + threadIdx.x;
+        const int i = base + threadIdx.x;
+        const int slot = i < n ? ((i / tpx) * nChains + chain) * tpx + i % tpx : 0;
         bool push = false;
         V3 o = mk3(P.camX, P.camY, P.camZ), d = mk3(0.0f, 0.0f, 0.0f);
-        if (slot < n) {
+        if (i < n) {
             int x, y, outIdx, local;
             B.pathDepth[slot] = 0;
             if (seqToPixel(P, tileSeq, slot, x, y, outIdx, local)) {
@@ -1921,10 +1930,17 @@ int launchPathPipeline(const DevScene& S, const FrameParams* dP, const FramePara
     return launches;
 }
 
-int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
-                        const RoundBuffers& B, const int2* dTileSeq, float* fb, int numSMs, WaveTrace* tr, cudaStream_t st)
+int roundPipelineChains()
 {
-    cudaMemsetAsync(B.counts, 0, sizeof(int) * CGRT_CNT_TOTAL, st);
+    const int c = tuning().chains;
+    return c < 1 ? 1 : (c > CGRT_MAX_CHAINS ? CGRT_MAX_CHAINS : c);
+}
+
+int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
+                        const RoundBuffers* chains, int nChains, const ChainSync& sync, const int2* dTileSeq, float* fb,
+                        int numSMs, WaveTrace* tr, cudaStream_t st)
+{
+    cudaMemsetAsync(chains[0].counts, 0, sizeof(int) * CGRT_CNT_TOTAL * nChains, st); // the chains' counters are contiguous
     if (hP.traceLimit <= 0) { // trace(0, ...) returns black for every pixel without casting a ray, src/main.cpp:267-272
         if (hP.world > 1 && hP.screenLayout) {
             k_clear_tiles<<<gridFor((size_t)hP.nSlots, 128, numSMs * 16), 128, 0, st>>>(dP, dTileSeq, fb);
@@ -1937,40 +1953,58 @@ int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FramePar
     int launches = 0;
     const int persistent = numSMs * tuning().blocks;
     const int flat = gridFor((size_t)hP.nSlots, 128, numSMs * 16);
-    int* counts = B.counts;
-    traceBegin(tr, 0, st);
-    k_gen<<<flat, 128, 0, st>>>(S, dP, B, dTileSeq, fb);
-    traceEnd(tr, 0, st);
-    launches++;
+    const int flatChain = gridFor((size_t)hP.nSlots / nChains + 1, 128, numSMs * 16);
     const bool shadows = hP.nLights > 0;
     const int rounds = hP.traceLimit + (shadows ? 1 : 0);
-    for (int r = 0; r < rounds; r++) {
-        // closest-hit rays of level r (list B) + shadow rays of the hits of level r-1 (list A)
-        const bool haveC = r < hP.traceLimit, haveS = shadows && r >= 1;
-        const float4* raysB = haveC ? B.cRay[r & 1] : nullptr;
-        float4* resB = haveC ? B.cRes[r & 1] : nullptr;
-        const int* nB = haveC ? counts + CGRT_CNT_BOUNCE + r : nullptr;
-        const float4* raysA = haveS ? B.sRay[(r - 1) & 1] : nullptr;
-        float4* resA = haveS ? B.sRes[(r - 1) & 1] : nullptr;
-        const int* nA = haveS ? counts + CGRT_CNT_HIT + (r - 1) : nullptr;
-        traceBegin(tr, 2, st);
-        // the ray count of the round lives on the device: both searches are launched, the one that does not apply returns at once
-        const int coopMax = tuning().coop;
-        if (coopMax < (1 << 30))
-            k_trace<<<persistent, 128, 0, st>>>(S, raysA, resA, nA, hP.nLights, raysB, resB, nB, counts + CGRT_CNT_WORK + r, coopMax);
-        if (coopMax > 0)
-            k_trace8<<<numSMs * CGRT_TRACE8_MINBLOCKS, 128, 0, st>>>(S, raysA, resA, nA, hP.nLights, raysB, resB, nB,
-                                                                     counts + CGRT_CNT_WORK + r, coopMax);
+    const int coopMax = tuning().coop;
+    // fork: every chain's stream starts after the frame's parameter upload / counter reset on `st`
+    if (nChains > 1) {
+        cudaEventRecord(sync.fork, st);
+        for (int c = 1; c < nChains; c++) cudaStreamWaitEvent(sync.streams[c], sync.fork, 0);
+    }
+    for (int c = 0; c < nChains; c++) {
+        cudaStream_t sc = c == 0 ? st : sync.streams[c];
+        traceBegin(tr, 0, sc);
+        k_gen<<<flatChain, 128, 0, sc>>>(S, dP, chains[c], dTileSeq, fb, c, nChains);
+        traceEnd(tr, 0, sc);
         launches++;
-        traceEnd(tr, 2, st);
-        traceBegin(tr, 1, st);
-        k_finish<<<flat, 128, 0, st>>>(S, dP, dLights, B, r, raysA, resA, nA, raysB, resB, nB, B.cRay[(r + 1) & 1], B.sRay[r & 1],
-                                      fb, dTileSeq);
-        traceEnd(tr, 1, st);
-        launches += 2;
+    }
+    for (int r = 0; r < rounds; r++) {
+        for (int c = 0; c < nChains; c++) {
+            const RoundBuffers& B = chains[c];
+            cudaStream_t sc = c == 0 ? st : sync.streams[c];
+            int* counts = B.counts;
+            // closest-hit rays of level r (list B) + shadow rays of the hits of level r-1 (list A)
+            const bool haveC = r < hP.traceLimit, haveS = shadows && r >= 1;
+            const float4* raysB = haveC ? B.cRay[r & 1] : nullptr;
+            float4* resB = haveC ? B.cRes[r & 1] : nullptr;
+            const int* nB = haveC ? counts + CGRT_CNT_BOUNCE + r : nullptr;
+            const float4* raysA = haveS ? B.sRay[(r - 1) & 1] : nullptr;
+            float4* resA = haveS ? B.sRes[(r - 1) & 1] : nullptr;
+            const int* nA = haveS ? counts + CGRT_CNT_HIT + (r - 1) : nullptr;
+            traceBegin(tr, 2, sc);
+            // the ray count of the round lives on the device: both searches are launched, the one that does not apply returns at once
+            if (coopMax < (1 << 30))
+                k_trace<<<persistent, 128, 0, sc>>>(S, raysA, resA, nA, hP.nLights, raysB, resB, nB, counts + CGRT_CNT_WORK + r, coopMax);
+            if (coopMax > 0)
+                k_trace8<<<numSMs * CGRT_TRACE8_MINBLOCKS, 128, 0, sc>>>(S, raysA, resA, nA, hP.nLights, raysB, resB, nB,
+                                                                         counts + CGRT_CNT_WORK + r, coopMax);
+            launches++;
+            traceEnd(tr, 2, sc);
+            traceBegin(tr, 1, sc);
+            k_finish<<<flatChain, 128, 0, sc>>>(S, dP, dLights, B, r, raysA, resA, nA, raysB, resB, nB, B.cRay[(r + 1) & 1],
+                                               B.sRay[r & 1], fb, dTileSeq);
+            traceEnd(tr, 1, sc);
+            launches++;
+        }
+    }
+    // join
+    for (int c = 1; c < nChains; c++) {
+        cudaEventRecord(sync.join[c], sync.streams[c]);
+        cudaStreamWaitEvent(st, sync.join[c], 0);
     }
     traceBegin(tr, 3, st);
-    k_shade_slots<<<flat, 128, 0, st>>>(S, dP, dLights, B, dTileSeq, fb);
+    k_shade_slots<<<flat, 128, 0, st>>>(S, dP, dLights, chains[0], dTileSeq, fb);
     traceEnd(tr, 3, st);
     launches++;
     return launches;

@@ -132,13 +132,14 @@ struct RoundBuffers {
     int levels;
 };
 
+#define CGRT_TRACE_MAX_KERNELS (8 * (2 * (CGRT_MAX_LEVELS + 1) + 1) + 2) // chains x (k_gen + 2 per round) + shade
 // optional per-kernel event trace of one wavefront (classes: 0 primary, 1 bounce closest-hit, 2 shadow, 3 shade)
 struct WaveTrace {
     cudaEvent_t* ev;   // 2 * maxKernels events
     int maxKernels;
     int classMask;
     int n;             // traced kernels
-    int cls[3 * CGRT_MAX_LEVELS + 1];
+    int cls[CGRT_TRACE_MAX_KERNELS];
     int launches[4];
 };
 
@@ -160,8 +161,16 @@ int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams&
                     cudaStream_t st);
 int launchPathPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
                        const PathBuffers& B, const int2* dTileSeq, float* fb, int numSMs, WaveTrace* tr, cudaStream_t st);
+#define CGRT_MAX_CHAINS 8
+// streams / events of the round pipeline's chains (chain 0 runs on the caller's stream)
+struct ChainSync {
+    cudaStream_t streams[CGRT_MAX_CHAINS];
+    cudaEvent_t fork, join[CGRT_MAX_CHAINS];
+};
+int roundPipelineChains(); // number of chains the round pipeline uses (CGRT_TUNE chains=N)
 int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
-                        const RoundBuffers& B, const int2* dTileSeq, float* fb, int numSMs, WaveTrace* tr, cudaStream_t st);
+                        const RoundBuffers* chains, int nChains, const ChainSync& sync, const int2* dTileSeq, float* fb,
+                        int numSMs, WaveTrace* tr, cudaStream_t st);
 void launchAssemble(const float* gathered, size_t perRankFloats, const int* tileLists, const int* tileCounts, int maxTiles,
                     int world, int tileW, int tileH, int tilesX, int width, int height, float* frame, int numSMs,
                     cudaStream_t st);
