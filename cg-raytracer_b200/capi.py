@@ -76,7 +76,7 @@ EXPORTS = [
     "cgrt_tile_buffer_floats", "cgrt_tile_list", "cgrt_assemble_tiles", "cgrt_quantize_rgba8", "cgrt_device_malloc", "cgrt_device_free",
     "cgrt_host_alloc_pinned", "cgrt_host_free_pinned", "cgrt_memcpy_h2d", "cgrt_memcpy_d2h", "cgrt_device_synchronize",
     "cgrt_memset_device", "cgrt_memcpy_d2h_async", "cgrt_peer_export", "cgrt_peer_open", "cgrt_peer_close",
-    "cgrt_flag_signal", "cgrt_flag_wait",
+    "cgrt_flag_signal", "cgrt_flag_wait", "cgrt_bvh_fast_tree_stats",
 ]
 
 _lib = None
@@ -140,6 +140,7 @@ def load_library(path=None):
         "cgrt_peer_close": (C.c_int, [C.c_int, vp]),
         "cgrt_flag_signal": (C.c_int, [C.c_int, C.POINTER(vp), i32, C.c_uint32, vp]),
         "cgrt_flag_wait": (C.c_int, [C.c_int, vp, i32, C.c_uint32, C.c_uint32, vp, vp]),
+        "cgrt_bvh_fast_tree_stats": (C.c_int, [vp, C.POINTER(C.c_int64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header/library drift
@@ -262,6 +263,12 @@ class Scene:
 
     def num_triangles(self):
         return int(self.lib.cgrt_scene_num_triangles(self.h))
+
+    def fast_tree_stats(self):
+        out = (C.c_int64 * 8)()
+        check(self.lib.cgrt_bvh_fast_tree_stats(self.h, out))
+        keys = ("wide_nodes", "triangles_reached", "coverage_errors", "containment_errors", "depth", "chain_errors", "present")
+        return dict(zip(keys, [int(v) for v in out]))
 
     def nodes(self):
         n = self.num_nodes()

@@ -164,6 +164,59 @@ static void cameraConstants(const cgrt_camera& c, FrameParams& P)
     P.halfW = c.aspect * P.halfH;        // :95
 }
 
+// ---- structural self-check of the fast tree (host, at build time; exported through cgrt_bvh_fast_tree_stats) ------------
+// out: [0] 8-wide nodes reachable from the root, [1] triangles reachable, [2] triangles reached more than once or never,
+//      [3] vertices outside the box of the child slot they hang under (boxes must CONTAIN their geometry), [4] depth in 8-wide
+//      levels, [5] parent-chain errors (a triangle's leaf must reach node 0 through `parent`), [6] 1 = tree present
+static void fastTreeSelfCheck(const std::vector<MeshView>& views, const BuiltBVH& bvh, int64_t out[8])
+{
+    for (int k = 0; k < 8; k++) out[k] = 0;
+    if (bvh.fastRoot == 0u) return;
+    out[6] = 1;
+    const uint32_t ID_MASK = 0x03ffffffu, ID_TRI = 0x20000000u;
+    std::vector<int> seen(bvh.leafTris.size(), 0);
+    struct Item { uint32_t id; int depth; float lo[3], hi[3]; };
+    std::vector<Item> stack;
+    Item root{bvh.fastRoot, 1, {-FLT_MAX, -FLT_MAX, -FLT_MAX}, {FLT_MAX, FLT_MAX, FLT_MAX}};
+    stack.push_back(root);
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        if (it.id & ID_TRI) {
+            const int first = (int)(it.id & ID_MASK), count = (int)((it.id >> 26) & 7u) + 1;
+            for (int t = first; t < first + count; t++) {
+                if (t < 0 || (size_t)t >= seen.size()) { out[2]++; continue; }
+                seen[t]++;
+                out[1]++;
+                const LeafTri lt = bvh.leafTris[t];
+                const MeshView& mv = views[lt.mesh];
+                for (int k = 0; k < 3; k++) {
+                    const float* v = mv.vertices + 6 * (size_t)mv.triangles[3 * (size_t)lt.tri + k];
+                    for (int a = 0; a < 3; a++)
+                        if (std::isfinite(v[a]) && (v[a] < it.lo[a] || v[a] > it.hi[a])) out[3]++;
+                }
+                // the certificate's chain: leaf -> ... -> root
+                int node = bvh.triLeafNode[t], guard = 0;
+                while (node > 0 && guard++ < 64) node = bvh.parent[node];
+                if (node != 0 || !bvh.nodes[bvh.triLeafNode[t]].isLeaf || t < bvh.nodes[bvh.triLeafNode[t]].firstTri ||
+                    t >= bvh.nodes[bvh.triLeafNode[t]].firstTri + bvh.nodes[bvh.triLeafNode[t]].triCount)
+                    out[5]++;
+            }
+            continue;
+        }
+        const WideNode& w = bvh.wide[it.id & ID_MASK];
+        out[0]++;
+        out[4] = std::max<int64_t>(out[4], it.depth);
+        for (int c = 0; c < 8; c++) {
+            if (w.id[c] == 0u) continue;
+            Item ch{w.id[c], it.depth + 1, {w.lo[c][0], w.lo[c][1], w.lo[c][2]}, {w.hi[c][0], w.hi[c][1], w.hi[c][2]}};
+            stack.push_back(ch);
+        }
+    }
+    for (int v : seen)
+        if (v != 1) out[2]++;
+}
+
 // ---- the scene object --------------------------------------------------------------------------------------------------
 struct cgrt_scene {
     int device = 0;
@@ -201,6 +254,7 @@ struct cgrt_scene {
     DevBuf<float4> cRay[2], cRes[2], sRay[2], sRes[2];
     int lastPipeline = 0; // 0 counting wavefront, 1 path pipeline, 2 round pipeline
     int lastChains = 1;
+    int64_t fastStats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     ChainSync chainSync{};
     bool lastPathPipeline = false;
     std::vector<cudaEvent_t> traceEvents;
@@ -351,7 +405,10 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
             if (n.isLeaf)
                 for (int i = 0; i < n.triCount; i++) s->bvh.leafRank[n.firstTri + i] = i;
     }
-    if (fastTree) buildFastTree(views, s->bvh);
+    if (fastTree) {
+        buildFastTree(views, s->bvh);
+        fastTreeSelfCheck(views, s->bvh, s->fastStats);
+    }
     if (hostOnly) { // BVH introspection only (builder tests on machines without a GPU); every query entry refuses it
         *out = s;
         return CGRT_OK;
@@ -953,6 +1010,13 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
 }
 
 static_assert(sizeof(FrameParams) <= CGRT_PARAM_BLOCK_HEADER, "FrameParams must fit the parameter block header");
+
+int cgrt_bvh_fast_tree_stats(const cgrt_scene* s, int64_t* out)
+{
+    if (!s || !out) return fail(CGRT_ERR_INVALID, "null argument");
+    for (int k = 0; k < 8; k++) out[k] = s->fastStats[k];
+    return CGRT_OK;
+}
 
 int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, float* d_out, void* stream)
 {

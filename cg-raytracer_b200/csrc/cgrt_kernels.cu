@@ -1293,10 +1293,11 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
     const int nA = nAp ? *nAp * mulA : 0, nB = nBp ? *nBp : 0;
     const int n = nA + nB;
     if (n >= coopMax) return; // large round: k_trace searches it
-    // rays per global fetch of a warp: small rounds are spread over all warps (latency), large ones fetch 16 at a time
+    // rays per global fetch of a warp: small rounds are spread over all warps, down to one ray per warp (latency: the four
+    // groups of a warp serialise when they sit in different node classes), large ones fetch 16 at a time
     const int totalWarps = gridDim.x * 4;
     int chunk = (n + totalWarps - 1) / totalWarps;
-    chunk = chunk < 4 ? 4 : (chunk > 16 ? 16 : chunk);
+    chunk = chunk < 1 ? 1 : (chunk > 16 ? 16 : chunk);
     if ((long long)blockIdx.x * 4 * chunk >= (long long)n) return;
     const int lane = threadIdx.x & 31, g = lane >> 3, j = lane & 7;
     const unsigned gmask = 0xFFu << (8 * g);

@@ -165,6 +165,12 @@ int cgrt_bvh_export_nodes(const cgrt_scene* s, int32_t* meta, float* aabb);
 /* global triangle ids of leaf `node` in the leaf's visiting order (intersectLeaf bvh.cpp:535-553); returns the count */
 int cgrt_bvh_leaf_triangles(const cgrt_scene* s, int32_t node, int32_t* out, int32_t cap);
 
+/* Structural self-check of the speculative traversal's tree (the conservative 8-wide tree over all triangles, see
+ * DESIGN.md), evaluated on the host at build time: out[8] = wide nodes reachable, triangles reachable, triangles not reached
+ * exactly once, vertices outside the box they hang under, depth in wide levels, certificate-chain errors, 1 if the scene has
+ * such a tree (0 with CGRT_SCENE_NO_SUBTREES / CGRT_SCENE_EXACT_ONLY), reserved. Callable without a GPU. */
+int cgrt_bvh_fast_tree_stats(const cgrt_scene* s, int64_t* out);
+
 /* ---- queries -------------------------------------------------------------------------------------------------------
  * cgrt_intersect_closest replaces BoundingVolumeHierarchy::intersect(Ray&, HitInfo&) const
  * (src/bounding_volume_hierarchy.cpp:850-881) for a batch of n rays: same visiting order, same pruning, same accept/reject

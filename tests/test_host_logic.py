@@ -200,3 +200,23 @@ def test_bmp_writer(capi, tmp_path):
     px = np.frombuffer(raw, np.uint8, offset=off).reshape(7, 5, 4)[::-1]  # bottom-up rows
     want = (np.clip(img, 0, 1) * np.float32(255.0)).astype(np.uint8)  # clamp, *255, truncate (screen.cpp:43-44)
     assert np.array_equal(px[..., [2, 1, 0]], want) and np.all(px[..., 3] == 255)
+
+
+@pytest.mark.parametrize("ntri,nmesh,depth", [(1, 1, 12), (7, 1, 12), (9, 3, 12), (3000, 1, 12), (3000, 300, 12), (3000, 1, 1),
+                                              (3000, 1, 20), (40000, 3, 12)])
+def test_fast_tree_covers_every_triangle_once(capi, ntri, nmesh, depth):
+    """the speculative traversal's tree: every triangle hangs under exactly one leaf, boxes contain their geometry, and every
+    triangle's certificate chain (reference leaf -> parent -> ... -> root) is intact"""
+    flat = ob.random_soup(ntri, seed=5 * ntri + nmesh, scale=0.1, n_meshes=nmesh)
+    st = capi.Scene(flat, host_only=True, bvh_max_depth=depth).fast_tree_stats()
+    assert st["present"] == 1
+    assert st["triangles_reached"] == ntri and st["coverage_errors"] == 0
+    assert st["containment_errors"] == 0 and st["chain_errors"] == 0
+    assert st["depth"] <= 40
+    assert capi.Scene(flat, host_only=True, exact_only=True).fast_tree_stats()["present"] == 0
+
+
+def test_fast_tree_on_bundled_scenes(capi, golden):
+    st = capi.Scene(golden.flat, host_only=True).fast_tree_stats()
+    assert st["present"] == 1 and st["triangles_reached"] == golden.flat.n_triangles
+    assert st["coverage_errors"] == 0 and st["containment_errors"] == 0 and st["chain_errors"] == 0
