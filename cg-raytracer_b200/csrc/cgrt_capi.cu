@@ -398,8 +398,13 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     for (size_t i = 0; i < T; i++) s->leafGlobalId[i] = views[s->bvh.leafTris[i].mesh].triOffset + s->bvh.leafTris[i].tri;
     const bool subTrees = !(opt && (opt->flags & CGRT_SCENE_NO_SUBTREES));
     const bool fastTree = subTrees && !(opt && (opt->flags & CGRT_SCENE_EXACT_ONLY));
-    if (subTrees) buildLeafSubTrees(views, s->bvh);
-    else {
+    if (subTrees) {
+        // sub-leaf size of the culling sub-trees (speed only; CGRT_SUBLEAF / CGRT_MINLEAF override for tuning)
+        int subLeaf = 6, minLeaf = 8;
+        if (const char* e = getenv("CGRT_SUBLEAF")) subLeaf = std::max(1, std::min(8, atoi(e)));
+        if (const char* e = getenv("CGRT_MINLEAF")) minLeaf = std::max(2, atoi(e));
+        buildLeafSubTrees(views, s->bvh, minLeaf, subLeaf);
+    } else {
         s->bvh.leafRank.assign(T, 0);
         for (const HostNode& n : s->bvh.nodes)
             if (n.isLeaf)
