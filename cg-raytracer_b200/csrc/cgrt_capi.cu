@@ -1075,7 +1075,7 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
                                    s->di.numSMs, true, &s->trace, st);
     } else if (useRounds(s, P)) {
         // chains: independent sub-frames (tiles dealt round-robin) on their own streams
-        const int nChains = roundPipelineChains();
+        const int nChains = roundPipelineChains(P.nSlots);
         if (nChains > 1 && !s->chainSync.fork) {
             CK(cudaEventCreateWithFlags(&s->chainSync.fork, cudaEventDisableTiming));
             for (int c = 1; c < CGRT_MAX_CHAINS; c++) {

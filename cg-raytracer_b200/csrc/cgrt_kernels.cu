@@ -450,9 +450,9 @@ struct Tuning {
     int vote = 1;    // 1: each step runs the node class picked by the warp vote; 0: every lane steps every iteration
     int wref = 4, wsub = 16, wleaf = 8;
     int blocks = 8;  // persistent CTAs (128 threads) per SM
-    int chains = 4;    // round pipeline: independent pixel subsets rendered on separate streams so that the tail of one
-                       // subset's launch is filled by the other subsets' work
-    int coop = 15000;  // round pipeline: rounds with fewer rays than this are searched by k_trace8 (8 lanes per ray: low
+    int chains = 0;    // round pipeline: independent pixel subsets rendered on separate streams so that the tail of one
+                       // subset's launch is filled by the other subsets' work; 0 = by frame size (4 for a 1080p frame on one GPU)
+    int coop = 0;      // round pipeline: rounds with fewer rays than this are searched by k_trace8 (8 lanes per ray: low
                        // latency), larger ones by k_trace (1 lane per ray: higher throughput)
 };
 static Tuning g_tune;
@@ -1931,10 +1931,20 @@ int launchPathPipeline(const DevScene& S, const FrameParams* dP, const FramePara
     return launches;
 }
 
-int roundPipelineChains()
+// chains by the size of this rank's share of the frame (measured on the 1080p C3 frame: 4 chains best on one GPU; a chain
+// needs enough rays per round to be worth its 18 launches)
+int roundPipelineChains(int nSlots)
 {
-    const int c = tuning().chains;
-    return c < 1 ? 1 : (c > CGRT_MAX_CHAINS ? CGRT_MAX_CHAINS : c);
+    int c = tuning().chains;
+    if (c <= 0) c = nSlots >= 1500000 ? 4 : (nSlots >= 700000 ? 2 : 1);
+    return c > CGRT_MAX_CHAINS ? CGRT_MAX_CHAINS : c;
+}
+// rays per chain-round below which the cooperative search is used (measured: 120 K for one chain, 15 K for four)
+static int coopThreshold(int nChains)
+{
+    const int c = tuning().coop; // > 0: explicit threshold, < 0: never (k_trace only), 0: by chain count
+    if (c != 0) return c < 0 ? 0 : c;
+    return nChains <= 1 ? 120000 : 60000 / nChains;
 }
 
 int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
@@ -1957,7 +1967,7 @@ int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FramePar
     const int flatChain = gridFor((size_t)hP.nSlots / nChains + 1, 128, numSMs * 16);
     const bool shadows = hP.nLights > 0;
     const int rounds = hP.traceLimit + (shadows ? 1 : 0);
-    const int coopMax = tuning().coop;
+    const int coopMax = coopThreshold(nChains);
     // fork: every chain's stream starts after the frame's parameter upload / counter reset on `st`
     if (nChains > 1) {
         cudaEventRecord(sync.fork, st);

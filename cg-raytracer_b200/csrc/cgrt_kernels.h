@@ -167,7 +167,7 @@ struct ChainSync {
     cudaStream_t streams[CGRT_MAX_CHAINS];
     cudaEvent_t fork, join[CGRT_MAX_CHAINS];
 };
-int roundPipelineChains(); // number of chains the round pipeline uses (CGRT_TUNE chains=N)
+int roundPipelineChains(int nSlots); // number of chains the round pipeline uses for a frame share of nSlots pixels (CGRT_TUNE chains=N overrides)
 int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
                         const RoundBuffers* chains, int nChains, const ChainSync& sync, const int2* dTileSeq, float* fb,
                         int numSMs, WaveTrace* tr, cudaStream_t st);
