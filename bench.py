@@ -269,7 +269,12 @@ def main():
     launches_per_step = int(st["kernel_launches"]) + R.extra_launches_per_frame()
     timeouts = R.timeouts()
 
-    # ---- end to end: host-buffer API, per-frame H2D of camera + lights, D2H of the float frame to pinned memory
+    # ---- end to end: host-buffer API, per-frame H2D of camera + lights, D2H of the float frame to pinned memory.
+    # One GPU: the streaming form (cgrt_render_submit / cgrt_render_wait, two frames in flight: the copy of frame k overlaps
+    # the kernels of frame k+1; all K frames are delivered before the clock stops). The synchronous call (cgrt_render, one
+    # frame at a time) is timed next to it and reported in config.e2e_synchronous. N > 1: synchronous frames on rank 0.
+    e2e_mode = "streaming (cgrt_render_submit x K + cgrt_render_wait, 2 frames in flight)" if world == 1 else \
+               "synchronous per frame (render, exchange, D2H, stream sync)"
     for _ in range(2):
         R.render_to_host(cam)
     barrier()
@@ -277,11 +282,20 @@ def main():
     for _ in range(args.steps):
         R.render_to_host(cam)
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_sync_s = time.perf_counter() - t0
+    e2e_s = e2e_sync_s
+    if world == 1:
+        R.stream_to_host(cam, 3)
+        barrier()
+        t0 = time.perf_counter()
+        last = R.stream_to_host(cam, args.steps)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        assert np.array_equal(last, R.render_to_host(cam)), "streamed frame differs from the synchronous frame"
+    t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s, e2e_sync_s = [float(x) for x in t.tolist()]
     e2e_value = rays_frame * args.steps / e2e_s / 1e6
     h2d = 128 + 32 * len(d.lights)  # FrameParams block + lights (cgrt_capi.cu: CGRT_PARAM_BLOCK_HEADER + 2 float4 per light)
     d2h = WIDTH * HEIGHT * 12
@@ -312,7 +326,8 @@ def main():
                        "parallelism": f"tiles{world}" if world > 1 else "single", "tile": "8x8 interleaved, row skew 3, centre-out order",
                        "exchange": {"single": "none", "p2p": "direct stores into rank 0's frame over NVLink peer memory + arrival/consumed flags",
                                     "nccl": "NCCL gather of tile-major buffers + assemble kernel"}[R.mode],
-                       "exchange_fallback_reason": R.fallback_reason, "handoff_timeouts": timeouts,
+                       "exchange_fallback_reason": R.fallback_reason, "handoff_timeouts": timeouts, "e2e_mode": e2e_mode,
+                       "e2e_synchronous": {"value": rays_frame * args.steps / e2e_sync_s / 1e6, "ms_per_step": e2e_sync_s / args.steps * 1e3},
                        "rays_per_frame": {"primary": n_primary, "shadow": n_shadow, "bounce": n_bounce},
                        "kernel_ms_per_frame_rank0": dict(zip(names, [round(v, 4) for v in st_prof["class_ms"]])),
                        "kernel_launches_per_frame": dict(zip(names, st_prof["class_launches"])),

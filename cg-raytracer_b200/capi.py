@@ -76,7 +76,7 @@ EXPORTS = [
     "cgrt_tile_buffer_floats", "cgrt_tile_list", "cgrt_assemble_tiles", "cgrt_quantize_rgba8", "cgrt_device_malloc", "cgrt_device_free",
     "cgrt_host_alloc_pinned", "cgrt_host_free_pinned", "cgrt_memcpy_h2d", "cgrt_memcpy_d2h", "cgrt_device_synchronize",
     "cgrt_memset_device", "cgrt_memcpy_d2h_async", "cgrt_peer_export", "cgrt_peer_open", "cgrt_peer_close",
-    "cgrt_flag_signal", "cgrt_flag_wait", "cgrt_bvh_fast_tree_stats",
+    "cgrt_flag_signal", "cgrt_flag_wait", "cgrt_bvh_fast_tree_stats", "cgrt_render_submit", "cgrt_render_wait",
 ]
 
 _lib = None
@@ -141,6 +141,8 @@ def load_library(path=None):
         "cgrt_flag_signal": (C.c_int, [C.c_int, C.POINTER(vp), i32, C.c_uint32, vp]),
         "cgrt_flag_wait": (C.c_int, [C.c_int, vp, i32, C.c_uint32, C.c_uint32, vp, vp]),
         "cgrt_bvh_fast_tree_stats": (C.c_int, [vp, C.POINTER(C.c_int64)]),
+        "cgrt_render_submit": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp]),
+        "cgrt_render_wait": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header/library drift
@@ -315,6 +317,13 @@ class Scene:
         st = RenderStats()
         check(self.lib.cgrt_render(self.h, C.byref(cam), C.byref(p), _vp(rgb), C.byref(st)))
         return rgb, st.as_dict()
+
+    def render_submit(self, cam, params, host_ptr):
+        """Streaming form: enqueue one frame into page-locked host memory (see cgrt_render_submit)."""
+        check(self.lib.cgrt_render_submit(self.h, C.byref(cam), C.byref(params), C.c_void_p(host_ptr)))
+
+    def render_wait(self):
+        check(self.lib.cgrt_render_wait(self.h))
 
     def render_device(self, cam, params, d_out_ptr, stream_ptr=0):
         check(self.lib.cgrt_render_device(self.h, C.byref(cam), C.byref(params), C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr)))

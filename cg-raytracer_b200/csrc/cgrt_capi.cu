@@ -254,6 +254,12 @@ struct cgrt_scene {
     DevBuf<float4> cRay[2], cRes[2], sRay[2], sRes[2];
     int lastPipeline = 0; // 0 counting wavefront, 1 path pipeline, 2 round pipeline
     int lastChains = 1;
+    // streaming form (cgrt_render_submit / cgrt_render_wait)
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t renderDone[2] = {nullptr, nullptr}, copyDone[2] = {nullptr, nullptr};
+    DevBuf<float> streamFrame[2];
+    bool slotUsed[2] = {false, false};
+    uint64_t submitSeq = 0;
     int64_t fastStats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     ChainSync chainSync{};
     bool lastPathPipeline = false;
@@ -308,6 +314,11 @@ static void destroyScene(cgrt_scene* s)
             if (s->chainSync.join[c]) cudaEventDestroy(s->chainSync.join[c]);
         }
     }
+    if (s->copyStream) {
+        cudaStreamDestroy(s->copyStream);
+        for (int k = 0; k < 2; k++) { cudaEventDestroy(s->renderDone[k]); cudaEventDestroy(s->copyDone[k]); }
+    }
+    s->streamFrame[0].release(); s->streamFrame[1].release();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -1258,6 +1269,48 @@ int cgrt_render(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params*
         }
     }
     if (stats) RC(cgrt_render_collect_stats(s, stats));
+    return CGRT_OK;
+}
+
+// ---- streaming form: up to two frames in flight, the D2H copy of frame k overlaps the kernels of frame k+1 -----------------
+int cgrt_render_submit(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, float* rgb_host)
+{
+    if (!s || !cam || !rgb_host) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(checkRenderParams(p));
+    if (p->world != 1) return fail(CGRT_ERR_INVALID, "cgrt_render_submit renders whole frames (world == 1)");
+    RC(useSceneDevice(s));
+    const size_t frameFloats = (size_t)p->width * p->height * 3;
+    int slot;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!s->copyStream) {
+            CK(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; k++) {
+                CK(cudaEventCreateWithFlags(&s->renderDone[k], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&s->copyDone[k], cudaEventDisableTiming));
+            }
+        }
+        slot = (int)(s->submitSeq++ & 1);
+        if (s->slotUsed[slot]) {
+            CK(cudaEventSynchronize(s->copyDone[slot])); // at most two frames in flight: frame k-2 has been delivered
+        }
+        RC(s->streamFrame[slot].ensure(frameFloats));
+        s->slotUsed[slot] = true;
+    }
+    RC(cgrt_render_device(s, cam, p, s->streamFrame[slot].p, s->stream));
+    CK(cudaEventRecord(s->renderDone[slot], s->stream));
+    CK(cudaStreamWaitEvent(s->copyStream, s->renderDone[slot], 0));
+    CK(cudaMemcpyAsync(rgb_host, s->streamFrame[slot].p, frameFloats * sizeof(float), cudaMemcpyDeviceToHost, s->copyStream));
+    CK(cudaEventRecord(s->copyDone[slot], s->copyStream));
+    return CGRT_OK;
+}
+
+int cgrt_render_wait(cgrt_scene* s)
+{
+    if (!s) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(useSceneDevice(s));
+    if (s->copyStream) CK(cudaStreamSynchronize(s->copyStream));
+    CK(cudaStreamSynchronize(s->stream));
     return CGRT_OK;
 }
 

@@ -238,6 +238,20 @@ class TiledRenderer:
             return 2
         return 1 if self.rank == 0 else 0
 
+    def stream_to_host(self, cam, n_frames):
+        """Single GPU, streaming: n_frames frames through cgrt_render_submit into two alternating page-locked buffers, then
+        cgrt_render_wait. Returns the last frame [H,W,3]. (Frame k's copy overlaps frame k+1's kernels.)"""
+        assert self.world == 1
+        torch = self.torch
+        if getattr(self, "_stream_bufs", None) is None:
+            self._stream_bufs = [torch.empty(self.H * self.W * 3, dtype=torch.float32).pin_memory() for _ in range(2)]
+        p = self.params
+        p.flags = 0
+        for k in range(n_frames):
+            self.scene.render_submit(cam, p, self._stream_bufs[k & 1].data_ptr())
+        self.scene.render_wait()
+        return self._stream_bufs[(n_frames - 1) & 1].numpy().reshape(self.H, self.W, 3)
+
     def render_to_host(self, cam):
         """End to end: per-frame inputs (camera + lights) go host->device inside the call, the finished frame comes back to
         pinned host memory on rank 0. Returns a numpy view [H,W,3] on rank 0."""

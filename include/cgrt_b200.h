@@ -222,6 +222,14 @@ int cgrt_render(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params*
  * stats (optional) are valid after the stream is synchronised and cgrt_render_collect_stats is called. */
 int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, float* d_out, void* stream);
 int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats);
+/* Streaming form of cgrt_render for hosts that render frame after frame (the reference re-renders every UI frame in
+ * ViewMode::RayTracing, src/main.cpp:907-914): cgrt_render_submit enqueues the frame (per-frame camera + lights upload, the
+ * kernels, the device->host copy into rgb_host) and returns; up to two frames are in flight, so the copy of frame k overlaps
+ * the kernels of frame k+1 (the call blocks only until frame k-2 has been delivered). cgrt_render_wait returns when every
+ * submitted frame has arrived. rgb_host should be page-locked (cgrt_host_alloc_pinned) and must stay valid until delivery;
+ * frames are delivered in submission order. world must be 1. Same pixels as cgrt_render. */
+int cgrt_render_submit(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, float* rgb_host);
+int cgrt_render_wait(cgrt_scene* s);
 size_t cgrt_tile_buffer_floats(const cgrt_render_params* p);
 /* global ids (ty * tilesX + tx, tilesX = ceil(width / tile_w)) of the tiles `rank` owns, increasing; returns the count
  * (-1 on bad arguments). Pure host arithmetic: callable without a GPU. */
