@@ -269,7 +269,8 @@ class Scene:
     def fast_tree_stats(self):
         out = (C.c_int64 * 8)()
         check(self.lib.cgrt_bvh_fast_tree_stats(self.h, out))
-        keys = ("wide_nodes", "triangles_reached", "coverage_errors", "containment_errors", "depth", "chain_errors", "present")
+        keys = ("wide_nodes", "triangles_reached", "coverage_errors", "containment_errors", "depth", "chain_errors", "present",
+                "always_tested")
         return dict(zip(keys, [int(v) for v in out]))
 
     def nodes(self):

@@ -217,9 +217,10 @@ void buildReferenceBVH(const std::vector<MeshView>& meshes, int maxDepth, BuiltB
 // reference's evaluation order, the plane distance t passes its range checks and the point p = fl(o + d t) passes the three
 // edge tests dot(n, cross(e_i, p - v_i)) >= 0 (src/ray_tracing.cpp:23-72). Each edge function is evaluated with an absolute
 // error below ~2e-6 |e_i| |p - v_i|, so an accepted p lies inside the triangle grown by 2e-6 |p - v_i| per edge; for a
-// triangle whose smallest angle is at least 0.01 rad this keeps p within 1e-3 * diameter of the triangle, and p itself is
-// within 2^-22 * max|coordinate| of the exact ray. A sub-tree box is the union of its triangles' boxes grown by
-//      eps = 1e-3 * diameter(triangle) + 1e-6 * max|coordinate|
+// triangle whose smallest angle is at least 0.01 rad this keeps p within 1e-3 * diameter of the triangle (thinner triangles get a
+// proportionally larger margin, conservativeBox), and p itself is within 2^-22 * max|coordinate| of the exact ray. A sub-tree
+// box is the union of its triangles' boxes grown by
+//      eps = (1e-3 + growth(smallest angle)) * diameter(triangle) + 1e-6 * max|coordinate|
 // (rounded outwards), hence every point the reference can accept lies inside the box of every ancestor of its triangle and
 // the (tolerant) slab test of the traversal can never cull a triangle the reference would accept. Triangles that violate the
 // angle condition or contain non-finite coordinates get an unbounded box.
@@ -227,6 +228,7 @@ namespace {
 
 struct TriBox {
     float lo[3], hi[3], c[3];
+    bool bounded;
 };
 
 inline float down(float x) { return std::nextafter(x, -std::numeric_limits<float>::infinity()); }
@@ -242,7 +244,7 @@ TriBox conservativeBox(const float* p0, const float* p1, const float* p2)
         finite = finite && std::isfinite(p0[k]) && std::isfinite(p1[k]) && std::isfinite(p2[k]);
     }
     bool bounded = finite;
-    double diam = 0.0, maxAbs = 0.0;
+    double diam = 0.0, maxAbs = 0.0, grow = 0.0;
     if (finite) {
         double e[3][3], len[3];
         for (int i = 0; i < 3; i++) {
@@ -265,8 +267,15 @@ TriBox conservativeBox(const float* p0, const float* p1, const float* p2)
             if (!(prod > 0.0)) { minSin = 0.0; break; }
             minSin = std::min(minSin, area2 / prod);
         }
-        if (!(minSin >= 0.01) || !(diam < 1e30)) bounded = false; // slivers / degenerate / huge: always tested
+        // growth of the accept region: offsetting the two edges at a vertex of angle theta by delta = 2e-6 |p - v| moves the
+        // corner by delta / sin(theta/2) ~ 4e-6 R / sin(theta), R = extent of the region: R <= diam / (1 - g), g = 4e-6 / minSin.
+        // The computed plane normal of a sliver is tilted by ~6e-8 / sin(theta) (cancellation in the cross product), which
+        // moves the hit point by less than that fraction of diam. Both stay far below the margin while minSin >= 2e-5;
+        // thinner, degenerate (cross product below the normal range) or huge triangles cannot be bounded: always tested.
+        if (!(minSin >= 2e-5) || !(diam < 1e30) || !(area2 >= 1e-30)) bounded = false;
+        else grow = 2.0 * (4e-6 / minSin) / (1.0 - 4e-6 / minSin);
     }
+    tb.bounded = bounded;
     for (int k = 0; k < 3; k++) {
         if (!bounded) {
             tb.lo[k] = -FLT_MAX;
@@ -274,7 +283,7 @@ TriBox conservativeBox(const float* p0, const float* p1, const float* p2)
             tb.c[k] = finite ? (float)((q[0][k] + q[1][k] + q[2][k]) / 3.0) : 0.0f;
             continue;
         }
-        const double eps = 1e-3 * diam + 1e-6 * maxAbs;
+        const double eps = (1e-3 + grow) * diam + 1e-6 * maxAbs;
         const double lo = std::min(q[0][k], std::min(q[1][k], q[2][k])) - eps;
         const double hi = std::max(q[0][k], std::max(q[1][k], q[2][k])) + eps;
         tb.lo[k] = down((float)lo);
@@ -412,6 +421,7 @@ void buildFastTree(const std::vector<MeshView>& meshes, BuiltBVH& bvh)
 {
     const size_t NN = bvh.nodes.size();
     bvh.fastRoot = 0u;
+    bvh.alwaysTest.clear();
     bvh.parent.assign(NN, -1);
     bvh.triLeafNode.assign(bvh.leafTris.size(), 0);
     if (NN == 0) return;
@@ -430,6 +440,10 @@ void buildFastTree(const std::vector<MeshView>& meshes, BuiltBVH& bvh)
                 const uint32_t* tri = mv.triangles + 3 * (size_t)lt.tri;
                 const TriBox tb = conservativeBox(mv.vertices + 6 * (size_t)tri[0], mv.vertices + 6 * (size_t)tri[1],
                                                   mv.vertices + 6 * (size_t)tri[2]);
+                if (!tb.bounded) { // would make every ancestor's box unbounded: kept out of the tree, tested for every ray
+                    bvh.alwaysTest.push_back(n.firstTri + t);
+                    continue;
+                }
                 for (int k = 0; k < 3; k++) { b.lo[k] = std::min(b.lo[k], tb.lo[k]); b.hi[k] = std::max(b.hi[k], tb.hi[k]); }
             }
         } else {
@@ -495,7 +509,8 @@ void buildFastTree(const std::vector<MeshView>& meshes, BuiltBVH& bvh)
         return ID_SUB | (uint32_t)self;
     };
     const uint32_t root = build(0);
-    bvh.fastRoot = (ok && root != 0xffffffffu) ? root : 0u;
+    // a scene with many unboundable triangles is not worth a speculative search (each costs every ray one exact test)
+    bvh.fastRoot = (ok && root != 0xffffffffu && bvh.alwaysTest.size() <= 256) ? root : 0u;
 }
 
 } // namespace cgrt

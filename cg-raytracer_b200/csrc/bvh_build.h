@@ -49,6 +49,8 @@ struct BuiltBVH {
     uint32_t fastRoot = 0;             // id of the root in the traversal's encoding, 0 = no fast tree
     std::vector<int32_t> parent;       // per reference node: parent index (-1 for the root)
     std::vector<int32_t> triLeafNode;  // per position: reference leaf that holds the triangle
+    std::vector<int32_t> alwaysTest;   // positions of triangles whose accept region cannot be bounded (extreme slivers, non-finite):
+                                       // not covered by the fast tree's boxes, tested for every ray that enters the tree
     int numLevels = 0;
 };
 

@@ -175,6 +175,9 @@ static void fastTreeSelfCheck(const std::vector<MeshView>& views, const BuiltBVH
     out[6] = 1;
     const uint32_t ID_MASK = 0x03ffffffu, ID_TRI = 0x20000000u;
     std::vector<int> seen(bvh.leafTris.size(), 0);
+    std::vector<char> always(bvh.leafTris.size(), 0);
+    for (int32_t a : bvh.alwaysTest) always[a] = 1;
+    out[7] = (int64_t)bvh.alwaysTest.size();
     struct Item { uint32_t id; int depth; float lo[3], hi[3]; };
     std::vector<Item> stack;
     Item root{bvh.fastRoot, 1, {-FLT_MAX, -FLT_MAX, -FLT_MAX}, {FLT_MAX, FLT_MAX, FLT_MAX}};
@@ -190,7 +193,7 @@ static void fastTreeSelfCheck(const std::vector<MeshView>& views, const BuiltBVH
                 out[1]++;
                 const LeafTri lt = bvh.leafTris[t];
                 const MeshView& mv = views[lt.mesh];
-                for (int k = 0; k < 3; k++) {
+                for (int k = 0; k < 3 && !always[t]; k++) { // (always-list triangles are not covered by the boxes by design)
                     const float* v = mv.vertices + 6 * (size_t)mv.triangles[3 * (size_t)lt.tri + k];
                     for (int a = 0; a < 3; a++)
                         if (std::isfinite(v[a]) && (v[a] < it.lo[a] || v[a] > it.hi[a])) out[3]++;
@@ -231,7 +234,7 @@ struct cgrt_scene {
     int nMeshes = 0;
 
     DevBuf<float4> wide8, tri4, nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, pairs, wide;
-    DevBuf<int> origToLeaf, refParent;
+    DevBuf<int> origToLeaf, refParent, alwaysTri;
     DevScene dev{};
 
     std::vector<cgrt_point_light> lights;
@@ -300,7 +303,7 @@ static void destroyScene(cgrt_scene* s)
     cudaSetDevice(s->device);
     s->wide8.release(); s->tri4.release(); s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
     s->triN0.release(); s->triN1.release(); s->triN2.release(); s->mats.release(); s->spheres.release();
-    s->origToLeaf.release(); s->refParent.release(); s->pairs.release(); s->wide.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
+    s->origToLeaf.release(); s->refParent.release(); s->alwaysTri.release(); s->pairs.release(); s->wide.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->tileSeq.release(); s->frame.release();
     s->tests.release(); s->hitRec.release(); s->hitList.release(); s->pathDepth.release(); s->replayShadow.release(); s->replayQ.release();
     for (int k = 0; k < 2; k++) { s->cRay[k].release(); s->cRes[k].release(); s->sRay[k].release(); s->sRes[k].release(); }
@@ -487,6 +490,8 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     std::vector<int> hParent(s->bvh.parent.begin(), s->bvh.parent.end());
     if (hParent.empty()) hParent.assign(std::max<size_t>(NN, 1), -1);
     UP(refParent, hParent);
+    std::vector<int> hAlways(s->bvh.alwaysTest.begin(), s->bvh.alwaysTest.end());
+    UP(alwaysTri, hAlways);
     // ---- the production traversal's node array: one 4 x float4 entry per inner node (reference or sub-tree) holding both
     // children with their visit ids (encoding documented in cgrt_device.cuh)
     const uint32_t ID_MASK = 0x03ffffffu, ID_REFLEAF = 0x10000000u, ID_TRI = 0x20000000u, ID_SUB = 0x40000000u,
@@ -577,6 +582,8 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     s->dev.wide = s->wide.p;
     s->dev.wide8 = s->wide8.p;
     s->dev.refParent = s->refParent.p;
+    s->dev.alwaysTri = s->alwaysTri.p;
+    s->dev.nAlways = s->bvh.fastRoot != 0u ? (int)s->bvh.alwaysTest.size() : 0;
     s->dev.fastRoot = s->bvh.fastRoot;
     s->dev.nNodes = (int)NN;
     s->dev.nTris = (int)T;

@@ -501,10 +501,15 @@ RT_DEV bool traverseFast(const DevScene& S, const V3& o, const V3& d, float tIn,
 struct FastTrav {
     V3 o, d, inv;
     float t;     // distance of the best acceptable triangle so far (initially the ray's bound)
-    int hitTri;  // its position, -1 none
+    float t2;    // smallest distance of any OTHER acceptable triangle met so far (runner-up), +inf none: see certifyClosest
+    float tIn;   // the ray's own bound
+    int hitTri;  // position of the best triangle, -1 none
     int sp;
     uint32_t node;
 };
+// acceptable triangles up to this factor beyond the best are still examined, so that the certificate knows every acceptable
+// triangle closer than t* (1 + 1e-6) (the pruning of the search uses the same factor)
+#define CGRT_NEAR 1.000001f
 #define CGRT_FASTSTACK 64
 #ifndef CGRT_PREFETCH
 #define CGRT_PREFETCH 0 // measured slower on B200 (k_trace 1.82 -> 2.08 ms/frame): the steps are issue-bound, not fetch-bound
@@ -523,6 +528,8 @@ RT_DEV int fastBegin(const DevScene& S, FastTrav& T, const V3& o, const V3& d, f
     T.o = o;
     T.d = d;
     T.t = tIn;
+    T.t2 = __int_as_float(0x7f800000);
+    T.tIn = tIn;
     T.hitTri = -1;
     T.sp = 0;
     T.node = 0u;
@@ -637,59 +644,126 @@ RT_DEV int fastStepWide(const DevScene& S, FastTrav& T, FastStack& K, float maxD
     return TRAV_CONTINUE;
 }
 
-// the triangles of one fast-tree leaf with the reference's accept arithmetic (same expression trees as leafCandidate)
+// One triangle against the search state, with the reference's accept arithmetic (same expression trees as leafCandidate).
+// Returns TRAV_CONTINUE (state possibly updated), TRAV_DEFER (the outcome depends on the reference's visiting order: exact
+// tie with the best, or the in-plane shortcut) or TRAV_FIRED (ANY: the shadow predicate holds for the new best).
+template <bool ANY>
+RT_DEV int fastTriangle(const DevScene& S, FastTrav& T, int i, float eps, float maxDist)
+{
+    if (i == T.hitTri) return TRAV_CONTINUE; // already the best candidate (always-list triangles are met twice): not a tie
+    // the whole 64-byte record at once: one memory round trip per triangle
+    const float4* tr = S.tri4 + 4 * (size_t)i;
+    const float4 pl = __ldg(tr), v0 = __ldg(tr + 1), v1 = __ldg(tr + 2), v2 = __ldg(tr + 3);
+    const V3 o = T.o, d = T.d;
+    const V3 n = mk3(pl);
+    const float on = dot3(o, n);
+    float tt = 0.0f;
+    const bool shortcut = (on == pl.w);
+    if (!shortcut) {
+        const float denominator = dot3(d, n);
+        if (denominator == 0) return TRAV_CONTINUE;
+        tt = (pl.w - on) / denominator;
+        if (tt < 0) return TRAV_CONTINUE;
+        if (!(tt < T.tIn)) return TRAV_CONTINUE;                                  // `t >= ray.t` for every ray.t the ray can have (or NaN)
+        if (T.hitTri >= 0 && !(tt <= T.t * CGRT_NEAR)) return TRAV_CONTINUE;       // clearly farther than the best
+    }
+    const V3 p = o + d * tt;
+    if (!pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), n, p)) return TRAV_CONTINUE;
+    if (shortcut) return TRAV_DEFER;
+    if (T.hitTri >= 0) {
+        if (tt == T.t) return TRAV_DEFER;                  // exact tie: the reference keeps whichever it reaches first
+        if (tt > T.t) {                                    // acceptable runner-up just behind the best
+            T.t2 = fminf(T.t2, tt);
+            return TRAV_CONTINUE;
+        }
+        T.t2 = fminf(T.t2, T.t);                           // the old best becomes the runner-up
+    }
+    T.t = tt;
+    T.hitTri = i;
+    if (ANY && !(tt + eps >= maxDist)) return TRAV_FIRED;
+    return TRAV_CONTINUE;
+}
+
+// the triangles of one fast-tree leaf
 template <bool ANY>
 RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps, float maxDist)
 {
     const uint32_t id = T.node;
     const int first = (int)(id & CGRT_IDX_MASK);
     const int count = (int)((id >> CGRT_TRICNT_SHIFT) & 7u) + 1;
-    const V3 o = T.o, d = T.d;
 #pragma unroll 1
     for (int i = first; i < first + count; i++) {
-        // the whole 64-byte record at once: one memory round trip per triangle
-        const float4* tr = S.tri4 + 4 * (size_t)i;
-        const float4 pl = __ldg(tr), v0 = __ldg(tr + 1), v1 = __ldg(tr + 2), v2 = __ldg(tr + 3);
-        const V3 n = mk3(pl);
-        const float on = dot3(o, n);
-        float tt = 0.0f;
-        const bool shortcut = (on == pl.w);
-        if (!shortcut) {
-            const float denominator = dot3(d, n);
-            if (denominator == 0) continue;
-            tt = (pl.w - on) / denominator;
-            if (tt < 0) continue;
-            if (!(tt <= T.t)) continue;                    // farther than the best (or NaN)
-            if (tt == T.t && T.hitTri < 0) continue;       // equals the ray's own bound: rejected by `t >= ray.t`
-        }
-        const V3 p = o + d * tt;
-        if (!pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), n, p)) continue;
-        if (shortcut || tt == T.t) return TRAV_DEFER;      // the outcome depends on the reference's visiting order
-        T.t = tt;
-        T.hitTri = i;
-        if (ANY && !(tt + eps >= maxDist)) return TRAV_FIRED;
+        const int r = fastTriangle<ANY>(S, T, i, eps, maxDist);
+        if (r != TRAV_CONTINUE) return r;
     }
     return fastPop(S, T, K, fastBound<ANY>(T, maxDist));
 }
 
-// does the reference reach the leaf of triangle `pos` while ray.t is still above tStar? (see the block comment above)
-RT_DEV bool certifyChain(const DevScene& S, const V3& o, const V3& d, int pos, float tStar)
+// Closest hit: does the reference find tri* (position `pos`, distance tStar)? Until tri* is accepted the reference's ray.t is
+// the ray's own bound tIn or the distance of another acceptable triangle. Every acceptable triangle closer than
+// tStar * (1 + 8e-7) has been examined by the search (its pruning factor CGRT_NEAR minus the rounding of the slab arithmetic),
+// the closest of them is t2; hence ray.t >= LB = min(tIn, t2, tStar * (1 + 5e-7)) > tStar at all those times. If every box on
+// the path root -> leaf(tri*) contains the origin strictly (visited unconditionally) or is reported hit by the reference's own
+// slabTest at a distance below LB, none of the reference's decisions on that path (`currentT >= ray.t` rejects, `ray.t <
+// tSecond` prunes a pending sibling) can go against descending, whatever the order of its visits; the leaf scan then accepts
+// tri* (tStar < ray.t) and nothing acceptable is closer. Boxes that are entered exactly where the triangle is hit (axis-aligned
+// geometry lying in a box face: distance within a few ulp of tStar) pass thanks to the 5e-7 margin.
+RT_DEV bool certifyClosest(const DevScene& S, const V3& o, const V3& d, int pos, float tStar, float t2, float tIn)
 {
+    const float lb = fminf(fminf(tIn, t2), tStar * 1.0000005f);
+    if (!(lb > tStar)) return false;
     int node = f2i(__ldg(S.triN0 + pos).w);
 #pragma unroll 1
     while (true) {
         const float4 q0 = __ldg(S.nodes + 2 * node), q1 = __ldg(S.nodes + 2 * node + 1);
         if (!startsInBox(o, mk3(q0), mk3(q1))) {
             float te = 0.0f;
-            if (!slabTest(mk3(q0), mk3(q1), o, d, tStar, te)) return false;
-            if (!(te < tStar)) return false; // NaN distances are not certificates
+            if (!slabTest(mk3(q0), mk3(q1), o, d, lb, te)) return false;
+            if (!(te < lb)) return false; // NaN distances are not certificates
         }
         if (node == 0) return true;
         node = __ldg(S.refParent + node);
     }
 }
 
+// Any hit: X (position `pos`, distance tX) is acceptable and satisfies the shadow predicate. On the path root -> leaf(X) the
+// reference either descends at every box - then it tests X and ends with ray.t <= tX - or it stops at a box because its ray.t
+// is already at or below that box's entry distance. Its final distance is therefore at most M = max(tX, entry distances of the
+// path's boxes), provided every box is geometrically hit; the predicate is monotone, so !(M + eps >= maxDist) proves "shadowed".
+RT_DEV bool certifyAny(const DevScene& S, const V3& o, const V3& d, int pos, float tX, float eps, float maxDist)
+{
+    float m = tX;
+    int node = f2i(__ldg(S.triN0 + pos).w);
+#pragma unroll 1
+    while (true) {
+        const float4 q0 = __ldg(S.nodes + 2 * node), q1 = __ldg(S.nodes + 2 * node + 1);
+        if (!startsInBox(o, mk3(q0), mk3(q1))) {
+            float te = 0.0f;
+            if (!slabTest(mk3(q0), mk3(q1), o, d, __int_as_float(0x7f800000), te)) return false;
+            if (!(te <= m)) m = te; // also taken for NaN, which then fails the predicate below
+        }
+        if (node == 0) break;
+        node = __ldg(S.refParent + node);
+    }
+    return !(m + eps >= maxDist);
+}
+
 RT_DEV bool travIsLeaf(uint32_t node) { return (node & CGRT_TRI) != 0u; }
+
+// fastBegin + the triangles the tree does not cover (DevScene::alwaysTri: extreme slivers / non-finite coordinates whose accept
+// region has no bounding box): every ray that enters the reference tree tests them with the same accept arithmetic.
+template <bool ANY>
+RT_DEV int fastStart(const DevScene& S, FastTrav& T, const V3& o, const V3& d, float tIn, float eps, float maxDist)
+{
+    int state = fastBegin(S, T, o, d, tIn);
+    if (state != TRAV_CONTINUE || S.nAlways <= 0) return state;
+#pragma unroll 1
+    for (int k = 0; k < S.nAlways; k++) {
+        const int r = fastTriangle<ANY>(S, T, __ldg(S.alwaysTri + k), eps, maxDist);
+        if (r != TRAV_CONTINUE) return r;
+    }
+    return TRAV_CONTINUE;
+}
 
 template <bool ANY>
 RT_DEV int fastStep(const DevScene& S, FastTrav& T, FastStack& K, float eps, float maxDist)
@@ -713,11 +787,11 @@ RT_DEV bool fastFinish(const DevScene& S, const FastTrav& T, int state, float ep
     }
     if (ANY) {
         if (state == TRAV_FIRED) {
-            if (!certifyChain(S, T.o, T.d, T.hitTri, T.t)) defer = true;
+            if (!certifyAny(S, T.o, T.d, T.hitTri, T.t, eps, maxDist)) defer = true;
             return !defer;
         }
     } else if (T.hitTri >= 0) {
-        if (!certifyChain(S, T.o, T.d, T.hitTri, T.t)) {
+        if (!certifyClosest(S, T.o, T.d, T.hitTri, T.t, T.t2, T.tIn)) {
             defer = true;
             return false;
         }
@@ -749,7 +823,7 @@ RT_DEV bool traverseSpec(const DevScene& S, const V3& o, const V3& d, float tIn,
     {
         FastTrav T;
         FastStack K;
-        int state = fastBegin(S, T, o, d, tIn);
+        int state = fastStart<ANY>(S, T, o, d, tIn, eps, maxDist);
         while (state == TRAV_CONTINUE) state = fastStep<ANY>(S, T, K, eps, maxDist);
         bool defer;
         const bool r = fastFinish<ANY>(S, T, state, eps, maxDist, R, defer);

@@ -893,7 +893,7 @@ RT_DEV void persistentFast(const DevScene& S, Policy& P, int n, int* workCounter
                     idx = mine;
                     V3 o, d;
                     traced = P.load(idx, o, d, tIn, eps, maxDist);
-                    state = traced ? fastBegin(S, T, o, d, tIn) : TRAV_DONE;
+                    state = traced ? fastStart<ANY>(S, T, o, d, tIn, eps, maxDist) : TRAV_DONE;
                 }
             }
             INSTR_ADD(8, 1); INSTR_ADD(9, nIdle);
@@ -911,7 +911,7 @@ RT_DEV void persistentFast(const DevScene& S, Policy& P, int n, int* workCounter
                 V3 no, nd;
                 const bool again = P.retire(fin && !defer, idx, traced, result, R, T.o, T.d, no, nd, tIn);
                 if (fin) {
-                    if (again) state = fastBegin(S, T, no, nd, tIn);
+                    if (again) state = fastStart<ANY>(S, T, no, nd, tIn, eps, maxDist);
                     else idx = -1;
                 }
                 continue;
@@ -1229,7 +1229,8 @@ __global__ void __launch_bounds__(128, CGRT_TRACE_MINBLOCKS) k_trace(DevScene S,
                     const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
                     maxDist = b.w;
                     eps = c.z;
-                    state = fastBegin(S, T, mk3(a), mk3(b), a.w);
+                    state = mine < nA ? fastStart<true>(S, T, mk3(a), mk3(b), a.w, eps, maxDist)
+                                      : fastStart<false>(S, T, mk3(a), mk3(b), a.w, eps, maxDist);
                 }
             }
             INSTR_ADD(8, 1); INSTR_ADD(9, nIdle);
@@ -1240,7 +1241,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE_MINBLOCKS) k_trace(DevScene S,
         for (int it = 0; it < CGRT_TRACE_STEPS; it++) {
             if (idx >= 0 && state != TRAV_CONTINUE) { // finished (possibly right at fastBegin): hand in the result
                 float4* out = idx < nA ? resA + idx : resB + (idx - nA);
-                *out = make_float4(i2f(state), T.t, i2f(T.hitTri), 0.0f);
+                *out = make_float4(i2f(state), T.t, i2f(T.hitTri), T.t2);
                 idx = -1;
                 TRACE_DONE_INSTR();
             }
@@ -1261,7 +1262,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE_MINBLOCKS) k_trace(DevScene S,
         }
         if (idx >= 0 && state != TRAV_CONTINUE) {
             float4* out = idx < nA ? resA + idx : resB + (idx - nA);
-            *out = make_float4(i2f(state), T.t, i2f(T.hitTri), 0.0f);
+            *out = make_float4(i2f(state), T.t, i2f(T.hitTri), T.t2);
             idx = -1;
             TRACE_DONE_INSTR();
         }
@@ -1305,7 +1306,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
     const float slack = 1.000001f;
     // group-uniform ray state (every lane of the group holds the same values)
     V3 o = mk3(0.0f, 0.0f, 0.0f), d = o, inv = o;
-    float t = 0.0f, eps = 0.0f, maxDist = 0.0f;
+    float t = 0.0f, t2 = 0.0f, tIn = 0.0f, eps = 0.0f, maxDist = 0.0f;
     int hitTri = -1, idx = -1, state = TRAV_DONE, sp = 0;
     uint32_t node = 0u;
     bool any = false;
@@ -1316,7 +1317,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
         if (idx >= 0 && state != TRAV_CONTINUE) {
             if (j == 0) {
                 float4* out = idx < nA ? resA + idx : resB + (idx - nA);
-                *out = make_float4(i2f(state), t, i2f(hitTri), 0.0f);
+                *out = make_float4(i2f(state), t, i2f(hitTri), t2);
             }
             idx = -1;
         }
@@ -1346,11 +1347,13 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
                     d = mk3(b);
                     maxDist = b.w;
                     eps = c.z;
-                    FastTrav T0;
-                    state = fastBegin(S, T0, o, d, a.w);
+                    FastTrav T0; // (every lane of the group evaluates the same start, incl. the always-list)
+                    state = any ? fastStart<true>(S, T0, o, d, a.w, eps, maxDist) : fastStart<false>(S, T0, o, d, a.w, eps, maxDist);
                     inv = T0.inv;
-                    t = a.w;
-                    hitTri = -1;
+                    t = T0.t;
+                    t2 = T0.t2;
+                    tIn = a.w;
+                    hitTri = T0.hitTri;
                     sp = 0;
                     node = T0.node;
                 }
@@ -1366,6 +1369,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
         const bool active = idx >= 0 && state == TRAV_CONTINUE;
         const bool isLeaf = (node & CGRT_TRI) != 0u;
         const float bound = (any ? fminf(t, maxDist) : t) * slack;
+        float near = __int_as_float(0x7f800000); // leaf: distance of an acceptable triangle that does not beat the best
         bool p = false, amb = false;     // p: this lane's child box is hit / this lane's triangle is an acceptable candidate
         unsigned key = 0xffffffffu;      // ordering key of the lane's result (entry distance | child, or candidate distance)
         uint32_t id = 0u;
@@ -1374,7 +1378,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
             if (isLeaf) {
                 // leaf: lane j tests triangle j with the reference's accept arithmetic (cgrt_device.cuh fastStepLeaf)
                 const int first = (int)(node & CGRT_IDX_MASK), count = (int)((node >> CGRT_TRICNT_SHIFT) & 7u) + 1;
-                if (j < count) {
+                if (j < count && first + j != hitTri) { // (own best candidate met again through the always-list: not a tie)
                     const float4* tr = S.tri4 + 4 * (size_t)(first + j);
                     const float4 pl = __ldg(tr), v0 = __ldg(tr + 1), v1 = __ldg(tr + 2), v2 = __ldg(tr + 3);
                     const V3 nrm = mk3(pl);
@@ -1388,14 +1392,15 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
                         else {
                             tt = (pl.w - on) / denominator;
                             if (tt < 0) cand = false;
-                            else if (!(tt <= t)) cand = false;               // farther than the best (or NaN)
-                            else if (tt == t && hitTri < 0) cand = false;    // equals the ray's own bound: `t >= ray.t`
+                            else if (!(tt < tIn)) cand = false;                                  // `t >= ray.t` always (or NaN)
+                            else if (hitTri >= 0 && !(tt <= t * CGRT_NEAR)) cand = false;        // clearly farther than the best
                         }
                     }
                     if (cand) {
                         const V3 pt = o + d * tt;
                         if (pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), nrm, pt)) {
-                            if (shortcut || tt == t) amb = true; // the outcome depends on the reference's visiting order
+                            if (shortcut || (hitTri >= 0 && tt == t)) amb = true; // depends on the reference's visiting order
+                            else if (hitTri >= 0 && tt > t) near = tt;            // acceptable runner-up just behind the best
                             else { p = true; key = __float_as_uint(tt + 0.0f); }
                         }
                     }
@@ -1423,13 +1428,20 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
         mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 4));
         const unsigned winm = (__ballot_sync(0xffffffffu, p && key == mn) >> (8 * g)) & 0xFFu;
         const uint32_t nextId = __shfl_sync(0xffffffffu, id, 8 * g + (int)(mn & 7u));
+        // leaf: smallest distance among the group's acceptable triangles that are not the new best (runner-up for the certificate)
+        float ru = (isLeaf && p && key != mn) ? __uint_as_float(key) : near;
+        ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 1));
+        ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 2));
+        ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 4));
         if (active) {
             bool pop = false;
             if (isLeaf) {
                 if (ambm != 0u || __popc(winm) > 1) {
                     state = TRAV_DEFER; // ties at the smallest distance / in-plane shortcut
                 } else {
+                    t2 = fminf(t2, ru);
                     if (pm != 0u) {
+                        if (hitTri >= 0) t2 = fminf(t2, t); // the old best becomes the runner-up
                         t = __uint_as_float(mn);
                         hitTri = (int)(node & CGRT_IDX_MASK) + (__ffs(winm) - 1);
                     }
@@ -1495,7 +1507,7 @@ __global__ void __launch_bounds__(128) k_finish(DevScene S, const FrameParams* _
             const float eps = c.z, maxDist = b.w;
             bool shadowed = false, settled = false;
             if (state == TRAV_FIRED) {
-                if (certifyChain(S, o, d, tri, res.y)) { shadowed = true; settled = true; }
+                if (certifyAny(S, o, d, tri, res.y, eps, maxDist)) { shadowed = true; settled = true; }
             } else if (state == TRAV_DONE) { // the tree does not shadow; spheres may (bvh.cpp:878-879)
                 settled = true;
                 float t = res.y;
@@ -1525,7 +1537,7 @@ __global__ void __launch_bounds__(128) k_finish(DevScene S, const FrameParams* _
             R.sphere = -1;
             R.tri = f2i(res.z);
             R.t = res.y;
-            bool settled = state == TRAV_DONE && (R.tri < 0 || certifyChain(S, o, d, R.tri, R.t));
+            bool settled = state == TRAV_DONE && (R.tri < 0 || certifyClosest(S, o, d, R.tri, R.t, res.w, a.w));
             if (settled) {
                 float t = R.t;
                 for (int sp = 0; sp < S.nSpheres; sp++) {

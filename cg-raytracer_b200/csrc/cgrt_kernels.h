@@ -42,6 +42,8 @@ struct DevScene {
     const float4* wide8;  // the same 8-wide nodes child-major: child j = [lo.xyz | id] [hi.xyz | -] at float4 2j, 2j+1 (256 B per
                           // node), for the cooperative search where lane j of a ray's group owns child j
     const int* origToLeaf; // global triangle id -> leaf-order index (brute-force path only)
+    const int* alwaysTri;  // positions of the triangles the fast tree does not cover (unboundable accept region): every ray tests them
+    int nAlways;
     const int* refParent;  // reference node -> parent (-1 for the root): certification of the speculative traversal
     uint32_t fastRoot;     // id of the root of the fast tree in `wide` (0 = none: exact traversal only)
     int nNodes;

@@ -17,14 +17,23 @@ def frames(name, flat, lights, W, H, L, reps=10):
     for _ in range(reps):
         _, st = s.render(cam, W, H, trace_limit=L)
         ms.append(st["device_ms"])
+    _, stp = s.render(cam, W, H, trace_limit=L, flags=capi.RENDER_PROFILE_ALL)
     _, stc = s.render(cam, W, H, trace_limit=L, flags=capi.RENDER_COUNT)
     rays = st["primary"] + st["shadow"] + st["bounce"]
     byt = 48 * rays + 32 * sum(stc["box_tests"]) + 48 * sum(stc["tri_tests"])
     best = min(ms)
     print(json.dumps(dict(config=name, W=W, H=H, trace_limit=L, rays=rays, primary_hit=st["primary_hit"], shadow=st["shadow"], bounce=st["bounce"],
                           device_ms=round(best, 4), Mrays_s=round(rays / best / 1e3, 1), bytes_per_ray=round(byt / rays, 1),
-                          alg_GBps=round(byt / best / 1e6, 1), frac_hbm=round(byt / best / 1e6 / 6537.6, 4), launches=st["kernel_launches"])))
+                          alg_GBps=round(byt / best / 1e6, 1), frac_hbm=round(byt / best / 1e6 / 6537.6, 4), launches=st["kernel_launches"],
+                          class_ms=dict(zip(capi.class_names(stp), [round(v, 3) for v in stp["class_ms"]])),
+                          replayed=[stp["replayed_closest"], stp["replayed_shadow"]])))
     s.close()
+    if os.environ.get("CGRT_CONFIGS_EXACT_TOO"):  # the exact path pipeline on the same frame, for comparison
+        s = capi.Scene(flat, lights=lights, exact_only=True)
+        s.render(cam, W, H, trace_limit=L)
+        ms = [s.render(cam, W, H, trace_limit=L)[1]["device_ms"] for _ in range(reps)]
+        print(json.dumps(dict(config=name + " (exact-only path pipeline)", device_ms=round(min(ms), 4))))
+        s.close()
 
 g = load_golden("cornell"); frames("C1 cornell", g.flat, g.lights, 512, 512, 2)
 g = load_golden("monkey"); frames("C2 monkey", g.flat, g.lights, 1920, 1080, 1)
