@@ -77,6 +77,7 @@ EXPORTS = [
     "cgrt_host_alloc_pinned", "cgrt_host_free_pinned", "cgrt_memcpy_h2d", "cgrt_memcpy_d2h", "cgrt_device_synchronize",
     "cgrt_memset_device", "cgrt_memcpy_d2h_async", "cgrt_peer_export", "cgrt_peer_open", "cgrt_peer_close",
     "cgrt_flag_signal", "cgrt_flag_wait", "cgrt_bvh_fast_tree_stats", "cgrt_render_submit", "cgrt_render_wait",
+    "cgrt_render_effects",
 ]
 
 _lib = None
@@ -143,6 +144,7 @@ def load_library(path=None):
         "cgrt_bvh_fast_tree_stats": (C.c_int, [vp, C.POINTER(C.c_int64)]),
         "cgrt_render_submit": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp]),
         "cgrt_render_wait": (C.c_int, [vp]),
+        "cgrt_render_effects": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(RenderParams), i32, vp, C.POINTER(RenderStats)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header/library drift
@@ -317,6 +319,15 @@ class Scene:
         rgb = np.zeros((H, W, 3), np.float32) if out is None else out
         st = RenderStats()
         check(self.lib.cgrt_render(self.h, C.byref(cam), C.byref(p), _vp(rgb), C.byref(st)))
+        return rgb, st.as_dict()
+
+    def render_effects(self, cam, W, H, trace_limit=2, antialias=False, motion_blur=False):
+        """renderRayTracing's anti-aliasing / motion-blur passes (cgrt_render_effects): (rgb[H,W,3], stats dict)."""
+        p = render_params(W, H, trace_limit)
+        rgb = np.zeros((H, W, 3), np.float32)
+        st = RenderStats()
+        check(self.lib.cgrt_render_effects(self.h, C.byref(cam), C.byref(p), (1 if antialias else 0) | (2 if motion_blur else 0),
+                                           _vp(rgb), C.byref(st)))
         return rgb, st.as_dict()
 
     def render_submit(self, cam, params, host_ptr):

@@ -261,6 +261,7 @@ struct cgrt_scene {
     cudaStream_t copyStream = nullptr;
     cudaEvent_t renderDone[2] = {nullptr, nullptr}, copyDone[2] = {nullptr, nullptr};
     DevBuf<float> streamFrame[2];
+    DevBuf<float> fxA, fxB; // cgrt_render_effects: supersampled / shifted frame, accumulator
     bool slotUsed[2] = {false, false};
     uint64_t submitSeq = 0;
     int64_t fastStats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -322,6 +323,7 @@ static void destroyScene(cgrt_scene* s)
         for (int k = 0; k < 2; k++) { cudaEventDestroy(s->renderDone[k]); cudaEventDestroy(s->copyDone[k]); }
     }
     s->streamFrame[0].release(); s->streamFrame[1].release();
+    s->fxA.release(); s->fxB.release();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -1276,6 +1278,72 @@ int cgrt_render(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params*
         }
     }
     if (stats) RC(cgrt_render_collect_stats(s, stats));
+    return CGRT_OK;
+}
+
+// ---- renderRayTracing's optional passes around the path -------------------------------------------------
+int cgrt_render_effects(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, int32_t effects, float* rgb,
+                        cgrt_render_stats* stats)
+{
+    if (!s || !cam || !rgb) return fail(CGRT_ERR_INVALID, "null argument");
+    RC(checkRenderParams(p));
+    if (p->world != 1) return fail(CGRT_ERR_INVALID, "cgrt_render_effects renders whole frames (world == 1)");
+    if (effects & ~(CGRT_EFFECT_ANTIALIAS | CGRT_EFFECT_MOTION_BLUR)) return fail(CGRT_ERR_INVALID, "unknown effect bits");
+    if (!effects) return cgrt_render(s, cam, p, rgb, stats);
+    RC(useSceneDevice(s));
+    const int W = p->width, H = p->height;
+    const size_t n = (size_t)W * H * 3;
+    cudaStream_t st = s->stream;
+    cgrt_render_stats total;
+    std::memset(&total, 0, sizeof total);
+    auto addStats = [&](const cgrt_render_stats& a) {
+        total.primary += a.primary; total.primary_hit += a.primary_hit; total.shadow += a.shadow; total.bounce += a.bounce;
+        total.kernel_launches += a.kernel_launches; total.device_ms += a.device_ms;
+        total.replayed_closest += a.replayed_closest; total.replayed_shadow += a.replayed_shadow;
+    };
+    if (effects & CGRT_EFFECT_MOTION_BLUR) {
+        // blurEffect runs after the pixel loop and overwrites every pixel (main.cpp:716-719, :581), whatever the loop drew
+        static const double shift[15] = {0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08, 0.09, 0.10, 0.11, 0.12, 0.13, 0.14, 0.15};
+        RC(s->fxA.ensure(n));
+        RC(s->fxB.ensure(n));
+        for (int k = 0; k < 15; k++) {
+            cgrt_camera c = *cam;
+            c.look_at[0] = (float)shift[k]; // cameraNew.setLookAt(glm::vec3(0.0k, 0, 0)), main.cpp:344-568
+            c.look_at[1] = 0.0f;
+            c.look_at[2] = 0.0f;
+            RC(cgrt_render_device(s, &c, p, s->fxA.p, st));
+            launchAccumulate(s->fxB.p, s->fxA.p, n, k == 0, st);
+            if (stats) {
+                cgrt_render_stats one;
+                RC(cgrt_render_collect_stats(s, &one));
+                addStats(one);
+            }
+        }
+        launchDivide(s->fxB.p, n, 16.0f, s->fxA.p, st);
+        total.kernel_launches += 16;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(rgb, s->fxA.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    } else { // anti-aliasing
+        if ((int64_t)W * 2 * H * 2 > (int64_t)1 << 28) return fail(CGRT_ERR_INVALID, "frame too large for 2x2 supersampling");
+        cgrt_render_params big = *p;
+        big.width = 2 * W;
+        big.height = 2 * H;
+        RC(s->fxA.ensure(n * 4));
+        RC(s->fxB.ensure(n));
+        RC(cgrt_render_device(s, cam, &big, s->fxA.p, st)); // aspect stays cam->aspect (W/H)
+        launchAADownsample(s->fxA.p, W, H, s->fxB.p, st);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(rgb, s->fxB.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (stats) {
+            cgrt_render_stats one;
+            RC(cgrt_render_collect_stats(s, &one));
+            addStats(one);
+            total.kernel_launches += 1;
+        }
+    }
+    if (stats) *stats = total;
     return CGRT_OK;
 }
 

@@ -502,7 +502,6 @@ struct FastTrav {
     V3 o, d, inv;
     float t;     // distance of the best acceptable triangle so far (initially the ray's bound)
     float t2;    // smallest distance of any OTHER acceptable triangle met so far (runner-up), +inf none: see certifyClosest
-    float tIn;   // the ray's own bound
     int hitTri;  // position of the best triangle, -1 none
     int sp;
     uint32_t node;
@@ -529,7 +528,6 @@ RT_DEV int fastBegin(const DevScene& S, FastTrav& T, const V3& o, const V3& d, f
     T.d = d;
     T.t = tIn;
     T.t2 = __int_as_float(0x7f800000);
-    T.tIn = tIn;
     T.hitTri = -1;
     T.sp = 0;
     T.node = 0u;
@@ -664,8 +662,11 @@ RT_DEV int fastTriangle(const DevScene& S, FastTrav& T, int i, float eps, float 
         if (denominator == 0) return TRAV_CONTINUE;
         tt = (pl.w - on) / denominator;
         if (tt < 0) return TRAV_CONTINUE;
-        if (!(tt < T.tIn)) return TRAV_CONTINUE;                                  // `t >= ray.t` for every ray.t the ray can have (or NaN)
-        if (T.hitTri >= 0 && !(tt <= T.t * CGRT_NEAR)) return TRAV_CONTINUE;       // clearly farther than the best
+        if (T.hitTri < 0) {
+            if (!(tt < T.t)) return TRAV_CONTINUE;             // T.t is the ray's own bound: `t >= ray.t` (or NaN)
+        } else if (!(tt <= T.t * CGRT_NEAR)) return TRAV_CONTINUE; // clearly farther than the best
+        // (a runner-up at or beyond the ray's own bound is not acceptable; recording it anyway only makes the certificate
+        // more cautious, and saves carrying the bound through the search)
     }
     const V3 p = o + d * tt;
     if (!pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), n, p)) return TRAV_CONTINUE;
@@ -775,7 +776,7 @@ RT_DEV int fastStep(const DevScene& S, FastTrav& T, FastStack& K, float eps, flo
 // After the search: certificate, then the sphere loop of BoundingVolumeHierarchy::intersect (bvh.cpp:878-879).
 // Returns false with `defer` set when the ray has to be replayed by the exact traversal.
 template <bool ANY>
-RT_DEV bool fastFinish(const DevScene& S, const FastTrav& T, int state, float eps, float maxDist, TraceResult& R, bool& defer)
+RT_DEV bool fastFinish(const DevScene& S, const FastTrav& T, int state, float tIn, float eps, float maxDist, TraceResult& R, bool& defer)
 {
     R.sphere = -1;
     R.t = T.t;
@@ -791,7 +792,7 @@ RT_DEV bool fastFinish(const DevScene& S, const FastTrav& T, int state, float ep
             return !defer;
         }
     } else if (T.hitTri >= 0) {
-        if (!certifyClosest(S, T.o, T.d, T.hitTri, T.t, T.t2, T.tIn)) {
+        if (!certifyClosest(S, T.o, T.d, T.hitTri, T.t, T.t2, tIn)) {
             defer = true;
             return false;
         }
@@ -826,7 +827,7 @@ RT_DEV bool traverseSpec(const DevScene& S, const V3& o, const V3& d, float tIn,
         int state = fastStart<ANY>(S, T, o, d, tIn, eps, maxDist);
         while (state == TRAV_CONTINUE) state = fastStep<ANY>(S, T, K, eps, maxDist);
         bool defer;
-        const bool r = fastFinish<ANY>(S, T, state, eps, maxDist, R, defer);
+        const bool r = fastFinish<ANY>(S, T, state, tIn, eps, maxDist, R, defer);
         if (!defer) return r;
     }
     return traverseFast<ANY>(S, o, d, tIn, eps, maxDist, R);

@@ -906,7 +906,7 @@ RT_DEV void persistentFast(const DevScene& S, Policy& P, int n, int* workCounter
                 TraceResult R;
                 R.sphere = -1; R.tri = -1; R.t = tIn;
                 bool result = false, defer = false;
-                if (fin && traced) result = fastFinish<ANY>(S, T, state, eps, maxDist, R, defer);
+                if (fin && traced) result = fastFinish<ANY>(S, T, state, tIn, eps, maxDist, R, defer);
                 if (fin && defer) P.defer(T.o, T.d, tIn);
                 V3 no, nd;
                 const bool again = P.retire(fin && !defer, idx, traced, result, R, T.o, T.d, no, nd, tIn);
@@ -1306,7 +1306,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
     const float slack = 1.000001f;
     // group-uniform ray state (every lane of the group holds the same values)
     V3 o = mk3(0.0f, 0.0f, 0.0f), d = o, inv = o;
-    float t = 0.0f, t2 = 0.0f, tIn = 0.0f, eps = 0.0f, maxDist = 0.0f;
+    float t = 0.0f, t2 = 0.0f, eps = 0.0f, maxDist = 0.0f;
     int hitTri = -1, idx = -1, state = TRAV_DONE, sp = 0;
     uint32_t node = 0u;
     bool any = false;
@@ -1352,7 +1352,6 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
                     inv = T0.inv;
                     t = T0.t;
                     t2 = T0.t2;
-                    tIn = a.w;
                     hitTri = T0.hitTri;
                     sp = 0;
                     node = T0.node;
@@ -1392,8 +1391,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
                         else {
                             tt = (pl.w - on) / denominator;
                             if (tt < 0) cand = false;
-                            else if (!(tt < tIn)) cand = false;                                  // `t >= ray.t` always (or NaN)
-                            else if (hitTri >= 0 && !(tt <= t * CGRT_NEAR)) cand = false;        // clearly farther than the best
+                            else if (hitTri < 0 ? !(tt < t) : !(tt <= t * CGRT_NEAR)) cand = false; // `t >= ray.t` / clearly farther
                         }
                     }
                     if (cand) {
@@ -1764,6 +1762,61 @@ __global__ void k_quantize(const float* __restrict__ frame, size_t nPixels, uint
     }
     o.x = (unsigned char)c[0]; o.y = (unsigned char)c[1]; o.z = (unsigned char)c[2]; o.w = 255;
     reinterpret_cast<uchar4*>(rgba)[i] = o;
+}
+
+// =================================================================================================================
+// Post passes of renderRayTracing (src/main.cpp:663-687 anti-aliasing, :318-584 motion blur): image kernels around the renderer
+// =================================================================================================================
+// Anti-aliasing (main.cpp:663-687): four rays per pixel at NDC (float(2x+i)/W * (2/level) - 1, float(2y+j)/H * (2/level) - 1),
+// level = 2, i.e. exactly the pixel-corner rays of a (2W x 2H) frame (float(k)/(2W)*2 == float(k)/W*1 bit for bit), summed in
+// the order (j outer, i inner) into `color` and divided by level * 2.5 = 5 (sic). `color` is never initialised in the reference;
+// this implementation starts it at zero (documented assumption).
+__global__ void k_aa_downsample(const float* __restrict__ big, int W, int H, float* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * H) return;
+    const int row = i / W, x = i - row * W; // Screen layout: row = H-1-y
+    const int y = H - 1 - row;
+    const int W2 = 2 * W, H2 = 2 * H;
+    float c[3] = {0.0f, 0.0f, 0.0f};
+    for (int j = 0; j < 2; j++)
+        for (int k = 0; k < 2; k++) {
+            const int xc = 2 * x + k, yc = 2 * y + j;
+            const float* src = big + 3 * ((size_t)(H2 - 1 - yc) * W2 + xc);
+            c[0] = c[0] + src[0]; c[1] = c[1] + src[1]; c[2] = c[2] + src[2];
+        }
+    const float level = 2.0f;
+    const float div = level * 2.5f;
+    out[3 * (size_t)i + 0] = c[0] / div;
+    out[3 * (size_t)i + 1] = c[1] / div;
+    out[3 * (size_t)i + 2] = c[2] / div;
+}
+
+// Motion blur (blurEffect, main.cpp:318-584): matrixPixels += frame for the 15 shifted look-at points, then / 16
+__global__ void k_accumulate(float* __restrict__ acc, const float* __restrict__ frame, size_t n, int first)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    acc[i] = first ? (0.0f + frame[i]) : (acc[i] + frame[i]);
+}
+__global__ void k_divide(const float* __restrict__ acc, size_t n, float div, float* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = acc[i] / div;
+}
+
+void launchAADownsample(const float* big, int W, int H, float* out, cudaStream_t st)
+{
+    k_aa_downsample<<<(W * H + 255) / 256, 256, 0, st>>>(big, W, H, out);
+}
+void launchAccumulate(float* acc, const float* frame, size_t n, bool first, cudaStream_t st)
+{
+    if (n) k_accumulate<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, frame, n, first ? 1 : 0);
+}
+void launchDivide(const float* acc, size_t n, float div, float* out, cudaStream_t st)
+{
+    if (n) k_divide<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, n, div, out);
 }
 
 // =================================================================================================================

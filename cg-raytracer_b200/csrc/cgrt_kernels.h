@@ -178,6 +178,9 @@ void launchAssemble(const float* gathered, size_t perRankFloats, const int* tile
                     cudaStream_t st);
 void launchFlagSignal(uint32_t* const* flags, int n, uint32_t seq, cudaStream_t st);
 void launchFlagWait(const uint32_t* flags, int n, uint32_t seq, unsigned long long timeoutNs, uint32_t* status, cudaStream_t st);
+void launchAADownsample(const float* big, int W, int H, float* out, cudaStream_t st);
+void launchAccumulate(float* acc, const float* frame, size_t n, bool first, cudaStream_t st);
+void launchDivide(const float* acc, size_t n, float div, float* out, cudaStream_t st);
 void launchQuantize(const float* frame, size_t nPixels, uint8_t* rgba, cudaStream_t st);
 
 } // namespace cgrt

@@ -222,6 +222,20 @@ int cgrt_render(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params*
  * stats (optional) are valid after the stream is synchronised and cgrt_render_collect_stats is called. */
 int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, float* d_out, void* stream);
 int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats);
+/* renderRayTracing's optional passes around the path (UI toggles, default off, src/main.cpp:33-35):
+ *   CGRT_EFFECT_ANTIALIAS   src/main.cpp:663-687: four rays per pixel = the pixel-corner rays of the (2W x 2H) frame, summed in
+ *                           the reference's order and divided by level * 2.5 = 5 (sic). The reference never initialises its
+ *                           accumulator `color` (undefined behaviour); this implementation starts it at zero.
+ *   CGRT_EFFECT_MOTION_BLUR blurEffect, src/main.cpp:318-584: the frames of 15 cameras whose look-at point is REPLACED by
+ *                           (0.01 k, 0, 0), k = 1..15, added in that order and divided by 16; as in the reference it overwrites
+ *                           whatever the pixel loop drew, so it wins over CGRT_EFFECT_ANTIALIAS.
+ * The bloom pass (src/main.cpp:586-628) is not offered: its 21 x 21 box average runs in place, every pixel reading neighbours
+ * that the same loop has already overwritten, i.e. it is a sequential recurrence over the image. world must be 1.
+ * stats (optional): sums over the rendered frames. */
+#define CGRT_EFFECT_ANTIALIAS 1
+#define CGRT_EFFECT_MOTION_BLUR 2
+int cgrt_render_effects(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, int32_t effects, float* rgb,
+                        cgrt_render_stats* stats);
 /* Streaming form of cgrt_render for hosts that render frame after frame (the reference re-renders every UI frame in
  * ViewMode::RayTracing, src/main.cpp:907-914): cgrt_render_submit enqueues the frame (per-frame camera + lights upload, the
  * kernels, the device->host copy into rgb_host) and returns; up to two frames are in flight, so the copy of frame k overlaps

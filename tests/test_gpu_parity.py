@@ -455,3 +455,40 @@ def test_streaming_render_equals_synchronous_render(capi, gpu):
         assert np.array_equal(bits(got), bits(want[k])), k
     for p in bufs:
         capi.check(lib.cgrt_host_free_pinned(p))
+
+
+# ---- renderRayTracing's optional passes: anti-aliasing and motion blur around the same renderer ---------------
+def test_antialiasing_and_motion_blur_against_oracle(capi, oracle, gpu, golden):
+    """cgrt_render_effects vs the oracle's frames combined exactly as src/main.cpp:663-687 (AA: the 4 pixel-corner rays of the
+    2W x 2H frame, (j outer, i inner) sum / 5, accumulator assumed zero-initialised) and :318-584 (motion blur: 15 look-at
+    points (0.01 k, 0, 0), running float sum / 16). Tolerance: 1/255 per channel (pow in the specular term), most pixels exact."""
+    flat, lights = golden.flat, golden.lights
+    s = capi.Scene(flat, lights=lights)
+    b = oracle.scene(flat, lights).bvh()
+    W, H, L = 160, 100, 2
+    # anti-aliasing
+    got, st = s.render_effects(capi.make_camera(W, H), W, H, trace_limit=L, antialias=True)
+    big, cnt = b.render(ob.default_camera(2 * W, 2 * H), 2 * W, 2 * H, trace_limit=L)
+    assert st["primary"] == 4 * W * H and st["shadow"] == cnt["shadow"] and st["bounce"] == cnt["bounce"]
+    yb = big[::-1]  # row index = y
+    acc = np.zeros((H, W, 3), np.float32)
+    for j in range(2):
+        for i in range(2):
+            acc = acc + yb[j::2, i::2]
+    want = (acc / np.float32(2.0 * 2.5))[::-1]
+    assert np.abs(got - want).max() <= PIXEL_TOL
+    assert (bits(got) == bits(want)).all(axis=2).mean() > 0.99
+    # motion blur (wins over anti-aliasing, as in the reference)
+    got, st = s.render_effects(capi.make_camera(W, H), W, H, trace_limit=L, motion_blur=True, antialias=True)
+    acc = np.zeros((H, W, 3), np.float32)
+    rays = 0
+    for k in range(1, 16):
+        cam = ob.default_camera(W, H)
+        cam.lookAt[:] = [np.float32(float("%.2f" % (0.01 * k))), 0.0, 0.0]
+        frame, cnt = b.render(cam, W, H, trace_limit=L)
+        acc = acc + frame
+        rays += cnt["primary"] + cnt["shadow"] + cnt["bounce"]
+    want = acc / np.float32(16.0)
+    assert st["primary"] + st["shadow"] + st["bounce"] == rays
+    assert np.abs(got - want).max() <= PIXEL_TOL
+    assert (bits(got) == bits(want)).all(axis=2).mean() > 0.99
