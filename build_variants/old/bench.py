@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s (primary + shadow + bounce) of the hot path on BASELINE.json's headline configuration.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU code (oracle/_ref) on the host cores
+
+Workload (config.workload): C3 = dragon 1920x1080 Whitted render, 1 point light, 1 shadow ray per hit and light, trace
+limit 5 (up to 4 mirror bounces), reference camera preset, reference-rule BVH (depth 12). data/dragon.obj is NOT part of the
+reference checkout, so the scene is the named procedural stand-in of the same size (87 040 triangles, mirror material
+assigned by the harness so that bounces exist) — said in `data`.
+
+A step = one frame. `value` = logical rays of the frame (all ranks) / device time of the frame with the scene resident in HBM,
+timed with CUDA events per step, L2 flushed between steps, max over ranks. `e2e` = the same through the host-buffer API:
+camera + lights go host->device and the float framebuffer comes back to pinned host memory inside the timed region.
+With N > 1 the frame is partitioned into interleaved tiles (strong scaling); the timed region includes the NCCL gather to
+rank 0 and the de-interleave kernel.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import __graft_entry__ as ge  # noqa: E402
+
+METRIC = "Mrays/s (primary+shadow+bounce)"
+WIDTH, HEIGHT, TRACE_LIMIT = 1920, 1080, 5
+SAMPLE_W, SAMPLE_H = 960, 540  # CPU legs: the even pixels of the frame (x/960 == 2x/1920: identical NDC positions)
+B_RAY, B_BOX, B_TRI = 48, 32, 48  # algorithmic bytes: ray in + hit out, per box test, per triangle test
+
+
+# re-exported for tests/test_multirank_gloo.py
+def _distributed():
+    from importlib import import_module
+    ge.load_package()
+    return import_module("cg_raytracer_b200.distributed")
+
+
+def pack_tiles(capi, params, frame):
+    return _distributed().pack_tiles(capi, params, frame)
+
+
+def assemble_on_host(capi, params, buffers):
+    return _distributed().assemble_on_host(capi, params, buffers)
+
+
+def gather_tiles(local, rank, world):
+    return _distributed().gather_tiles(local, rank, world)
+
+
+def workload_name(n_tris):
+    return (f"C3 dragon stand-in (procedural torus knot, {n_tris} triangles, mirror ks=0.5) {WIDTH}x{HEIGHT} Whitted: "
+            f"1 point light, 1 shadow ray/hit/light, trace limit {TRACE_LIMIT} (<=4 mirror bounces), reference camera preset, "
+            f"reference-rule BVH depth 12, strict arithmetic (-fmad=false)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_checker():
+    """oracle/_ref (the reference's own compiled TUs) when present, else the restatement. Test infrastructure: this is the
+    only place besides tests/ and smoke() where bench.py touches oracle/."""
+    from oracle import bindings as ob
+    try:
+        return ob.RefLib(), "reference", ob
+    except (FileNotFoundError, OSError):
+        return ob.OracleLib(), "port", ob
+
+
+def cpu_sample(flat, lights, reps=1):
+    """Time the reference CPU renderer on the bounded sample; returns (Mrays/s best of reps, threads, rays, seconds)."""
+    lib, kind, ob = cpu_checker()
+    fs = ob.FlatScene(flat.vcount, flat.tcount, flat.vertices, flat.triangles, flat.materials, flat.spheres)
+    b = lib.scene(fs, lights).bvh(mode=1)  # range-based fill of the reference's Node structs (the constructor needs ~25 GB here)
+    cam = ob.default_camera(SAMPLE_W, SAMPLE_H)
+    best = None
+    rays = 0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        _, cnt = b.render(cam, SAMPLE_W, SAMPLE_H, trace_limit=TRACE_LIMIT, duplicate_shading=True)
+        dt = time.perf_counter() - t0
+        rays = cnt["primary"] + cnt["shadow"] + cnt["bounce"]
+        best = dt if best is None else min(best, dt)
+    return rays / best / 1e6, lib.max_threads(), rays, best, kind
+
+
+def sample_text():
+    return (f"the {SAMPLE_W}x{SAMPLE_H} even-pixel sub-grid (1/4 of the pixels, identical NDC positions) of the same frame, "
+            f"reference code path incl. its duplicated shading() call (main.cpp:284), rays counted once, OpenMP static rows")
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    capi = ge.load_package().capi
+    d = capi.dragon_standin()
+    lib, kind, ob = cpu_checker()
+    fs = ob.FlatScene(d.vcount, d.tcount, d.vertices, d.triangles, d.materials, d.spheres)
+    b = lib.scene(fs, d.lights).bvh(mode=1)
+    cam = ob.default_camera(SAMPLE_W, SAMPLE_H)
+    rays = 0
+    for _ in range(args.warmup):
+        b.render(cam, SAMPLE_W, SAMPLE_H, trace_limit=TRACE_LIMIT, duplicate_shading=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, cnt = b.render(cam, SAMPLE_W, SAMPLE_H, trace_limit=TRACE_LIMIT, duplicate_shading=True)
+        rays += cnt["primary"] + cnt["shadow"] + cnt["bounce"]
+    dt = time.perf_counter() - t0
+    v = rays / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (procedural dragon stand-in; data/dragon.obj is not in the reference checkout)",
+        "config": {"workload": workload_name(d.n_triangles), "cpu_sample": sample_text()},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": lib.max_threads(), "kind": kind, "sample": sample_text()},
+        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ge.build()
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    pkg = ge.load_package()
+    capi = pkg.capi
+    distributed = _distributed()
+
+    if capi.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device visible — the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    # ---- scene (host build + upload: outside every timed region, like the reference's BVH construction at scene load)
+    d = capi.dragon_standin()
+    scene = capi.Scene(d, lights=d.lights, device=local_rank)
+    cam = capi.make_camera(WIDTH, HEIGHT)
+    R = distributed.TiledRenderer(scene, WIDTH, HEIGHT, TRACE_LIMIT, rank, world, local_rank,
+                                  mode=os.environ.get("CGRT_EXCHANGE"))  # p2p (default) | nccl
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # ---- untimed: warm-up, ray counts, reference test counts (algorithmic bytes), per-class kernel times
+    for _ in range(args.warmup):
+        R.render_device(cam)
+    barrier()
+    st_count = R.count_pass(cam)
+    R.render_device(cam, flags=capi.RENDER_PROFILE_ALL)
+    st_prof = scene.collect_stats()
+    rays_local = st_count["primary"] + st_count["shadow"] + st_count["bounce"]
+    dominant = int(np.argmax(st_prof["class_ms"]))
+    cls_rays = [st_count["primary"], st_count["bounce"], st_count["shadow"]]
+    alg_bytes_class = [B_RAY * cls_rays[c] + B_BOX * st_count["box_tests"][c] + B_TRI * st_count["tri_tests"][c] for c in range(3)]
+    alg_bytes_frame_local = sum(alg_bytes_class)
+    names = capi.class_names(st_prof)
+    if names is capi.ROUND_CLASS_NAMES:  # round pipeline: k_trace (class 2) searches every ray of the frame
+        alg_bytes_class = [0, 0, alg_bytes_frame_local]
+    elif st_prof["class_launches"][1] == 0:  # path pipeline: k_paths traces the primary AND the bounce rays
+        alg_bytes_class = [alg_bytes_class[0] + alg_bytes_class[1], 0, alg_bytes_class[2]]
+    tot = torch.tensor([rays_local, st_count["primary"], st_count["shadow"], st_count["bounce"], alg_bytes_frame_local],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    rays_frame, n_primary, n_shadow, n_bounce, alg_bytes_frame = [float(x) for x in tot.tolist()]
+
+    # ---- timed: K frames, CUDA events per frame on the launching stream, L2 flushed between frames (outside the events)
+    sampler = ClockSampler(local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    dom_ms, dom_launches = 0.0, 0
+    barrier()
+    if rank == 0:
+        sampler.start()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        R.render_device(cam, flags=(1 << dominant))
+        ev[k][1].record()
+        st = scene.collect_stats()  # synchronises the frame; reads the dominant kernel's event times
+        dom_ms += st["class_ms"][dominant]
+        dom_launches += st["class_launches"][dominant]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = rays_frame * args.steps / (total_ms * 1e-3) / 1e6
+    launches_per_step = int(st["kernel_launches"]) + R.extra_launches_per_frame()
+    timeouts = R.timeouts()
+
+    # ---- end to end: host-buffer API, per-frame H2D of camera + lights, D2H of the float frame to pinned memory.
+    # One GPU: the streaming form (cgrt_render_submit / cgrt_render_wait, two frames in flight: the copy of frame k overlaps
+    # the kernels of frame k+1; all K frames are delivered before the clock stops). The synchronous call (cgrt_render, one
+    # frame at a time) is timed next to it and reported in config.e2e_synchronous. N > 1: synchronous frames on rank 0.
+    e2e_mode = "streaming (cgrt_render_submit x K + cgrt_render_wait, 2 frames in flight)" if world == 1 else \
+               "synchronous per frame (render, exchange, D2H, stream sync)"
+    for _ in range(2):
+        R.render_to_host(cam)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        R.render_to_host(cam)
+    barrier()
+    e2e_sync_s = time.perf_counter() - t0
+    e2e_s = e2e_sync_s
+    if world == 1:
+        R.stream_to_host(cam, 3)
+        barrier()
+        t0 = time.perf_counter()
+        last = R.stream_to_host(cam, args.steps)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        assert np.array_equal(last, R.render_to_host(cam)), "streamed frame differs from the synchronous frame"
+    t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s, e2e_sync_s = [float(x) for x in t.tolist()]
+    e2e_value = rays_frame * args.steps / e2e_s / 1e6
+    h2d = 128 + 32 * len(d.lights)  # FrameParams block + lights (cgrt_capi.cu: CGRT_PARAM_BLOCK_HEADER + 2 float4 per light)
+    d2h = WIDTH * HEIGHT * 12
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        dom_name = names[dominant]
+        dom_avg_s = dom_ms * 1e-3 / max(dom_launches, 1)
+        # algorithmic bytes of the rays this rank's launches of the dominant kernel process, averaged per launch
+        dom_bytes_per_launch = alg_bytes_class[dominant] / max(st_prof["class_launches"][dominant], 1) if dominant < 3 else 0.0
+        achieved = dom_bytes_per_launch / dom_avg_s / 1e9 if dom_avg_s > 0 else 0.0
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = prof.get(dom_name, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (procedural dragon stand-in; data/dragon.obj is not in the reference checkout)",
+            "config": {"workload": workload_name(d.n_triangles), "l2": "flushed between timed frames (256 MiB memset outside the event pair)",
+                       "parallelism": f"tiles{world}" if world > 1 else "single", "tile": "8x8 interleaved, row skew 3, centre-out order",
+                       "exchange": {"single": "none", "p2p": "direct stores into rank 0's frame over NVLink peer memory + arrival/consumed flags",
+                                    "nccl": "NCCL gather of tile-major buffers + assemble kernel"}[R.mode],
+                       "exchange_fallback_reason": R.fallback_reason, "handoff_timeouts": timeouts, "e2e_mode": e2e_mode,
+                       "e2e_synchronous": {"value": rays_frame * args.steps / e2e_sync_s / 1e6, "ms_per_step": e2e_sync_s / args.steps * 1e3},
+                       "rays_per_frame": {"primary": n_primary, "shadow": n_shadow, "bounce": n_bounce},
+                       "kernel_ms_per_frame_rank0": dict(zip(names, [round(v, 4) for v in st_prof["class_ms"]])),
+                       "kernel_launches_per_frame": dict(zip(names, st_prof["class_launches"])),
+                       "frame_roofline": {"algorithmic_bytes_per_frame": alg_bytes_frame, "bytes_per_ray": alg_bytes_frame / rays_frame,
+                                          "achieved_GBps": alg_bytes_frame * args.steps / (total_ms * 1e-3) / 1e9,
+                                          "frac_of_hbm_peak": alg_bytes_frame * args.steps / (total_ms * 1e-3) / 1e9 / (peak * world)}},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": dom_bytes_per_launch, "avg_launch_ms": dom_avg_s * 1e3,
+                         "launches_timed": dom_launches,
+                         "note": "scene (~10 MB) is L2-resident: the HBM roofline is the contractual denominator, the practical "
+                                 "limiters are L1/L2 request rate, IEEE division throughput and divergence (see profiles/)"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, rays, secs, kind = cpu_sample(d, d.lights, reps=2)
+            line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample_text(),
+                                    "sample_rays": rays, "sample_seconds": secs}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -501,13 +501,10 @@ RT_DEV bool traverseFast(const DevScene& S, const V3& o, const V3& d, float tIn,
 struct FastTrav {
     V3 o, d, inv;
     float t;     // distance of the best acceptable triangle so far (initially the ray's bound)
-    int hitTri;  // position of the best triangle, -1 none
+    int hitTri;  // its position, -1 none
     int sp;
     uint32_t node;
 };
-// acceptable triangles up to this factor beyond the best are still examined, so that the certificate knows every acceptable
-// triangle closer than t* (1 + 1e-6) (the pruning of the search uses the same factor)
-#define CGRT_NEAR 1.000001f
 #define CGRT_FASTSTACK 64
 #ifndef CGRT_PREFETCH
 #define CGRT_PREFETCH 0 // measured slower on B200 (k_trace 1.82 -> 2.08 ms/frame): the steps are issue-bound, not fetch-bound
@@ -515,8 +512,6 @@ struct FastTrav {
 struct FastStack {
     uint32_t n[CGRT_FASTSTACK];
     float t[CGRT_FASTSTACK];
-    float t2; // smallest distance of any OTHER acceptable triangle met so far (runner-up), +inf none: see certifyClosest. Lives
-              // here (local memory) because it is touched only when a candidate is accepted; a register in the hot loop is not
 };
 
 RT_DEV void fastPrefetch(const DevScene& S, uint32_t id);
@@ -642,50 +637,7 @@ RT_DEV int fastStepWide(const DevScene& S, FastTrav& T, FastStack& K, float maxD
     return TRAV_CONTINUE;
 }
 
-// One triangle against the search state, with the reference's accept arithmetic (same expression trees as leafCandidate).
-// Returns TRAV_CONTINUE (state possibly updated), TRAV_DEFER (the outcome depends on the reference's visiting order: exact
-// tie with the best, or the in-plane shortcut) or TRAV_FIRED (ANY: the shadow predicate holds for the new best).
-template <bool ANY>
-RT_DEV int fastTriangle(const DevScene& S, FastTrav& T, float& t2, int i, float eps, float maxDist)
-{
-    if (i == T.hitTri) return TRAV_CONTINUE; // already the best candidate (always-list triangles are met twice): not a tie
-    // the whole 64-byte record at once: one memory round trip per triangle
-    const float4* tr = S.tri4 + 4 * (size_t)i;
-    const float4 pl = __ldg(tr), v0 = __ldg(tr + 1), v1 = __ldg(tr + 2), v2 = __ldg(tr + 3);
-    const V3 o = T.o, d = T.d;
-    const V3 n = mk3(pl);
-    const float on = dot3(o, n);
-    float tt = 0.0f;
-    const bool shortcut = (on == pl.w);
-    if (!shortcut) {
-        const float denominator = dot3(d, n);
-        if (denominator == 0) return TRAV_CONTINUE;
-        tt = (pl.w - on) / denominator;
-        if (tt < 0) return TRAV_CONTINUE;
-        if (T.hitTri < 0) {
-            if (!(tt < T.t)) return TRAV_CONTINUE;             // T.t is the ray's own bound: `t >= ray.t` (or NaN)
-        } else if (!(tt <= T.t * CGRT_NEAR)) return TRAV_CONTINUE; // clearly farther than the best
-        // (a runner-up at or beyond the ray's own bound is not acceptable; recording it anyway only makes the certificate
-        // more cautious, and saves carrying the bound through the search)
-    }
-    const V3 p = o + d * tt;
-    if (!pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), n, p)) return TRAV_CONTINUE;
-    if (shortcut) return TRAV_DEFER;
-    if (T.hitTri >= 0) {
-        if (tt == T.t) return TRAV_DEFER;                  // exact tie: the reference keeps whichever it reaches first
-        if (tt > T.t) {                                    // acceptable runner-up just behind the best
-            t2 = fminf(t2, tt);
-            return TRAV_CONTINUE;
-        }
-        t2 = fminf(t2, T.t);                               // the old best becomes the runner-up
-    }
-    T.t = tt;
-    T.hitTri = i;
-    if (ANY && !(tt + eps >= maxDist)) return TRAV_FIRED;
-    return TRAV_CONTINUE;
-}
-
-// the triangles of one fast-tree leaf
+// the triangles of one fast-tree leaf with the reference's accept arithmetic (same expression trees as leafCandidate)
 template <bool ANY>
 RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps, float maxDist)
 {
@@ -693,7 +645,6 @@ RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps,
     const int first = (int)(id & CGRT_IDX_MASK);
     const int count = (int)((id >> CGRT_TRICNT_SHIFT) & 7u) + 1;
     const V3 o = T.o, d = T.d;
-    // (fastTriangle written out: this is the hot loop of the search, and its shape matters to the compiler)
 #pragma unroll 1
     for (int i = first; i < first + count; i++) {
         // the whole 64-byte record at once: one memory round trip per triangle
@@ -708,17 +659,12 @@ RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps,
             if (denominator == 0) continue;
             tt = (pl.w - on) / denominator;
             if (tt < 0) continue;
-            if (!(tt <= T.t * CGRT_NEAR)) continue;        // clearly farther than the best (or NaN)
-            if (T.hitTri < 0 && !(tt < T.t)) continue;     // T.t is still the ray's own bound: `t >= ray.t`
+            if (!(tt <= T.t)) continue;                    // farther than the best (or NaN)
+            if (tt == T.t && T.hitTri < 0) continue;       // equals the ray's own bound: rejected by `t >= ray.t`
         }
         const V3 p = o + d * tt;
         if (!pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), n, p)) continue;
-        if (shortcut || (tt == T.t && i != T.hitTri)) return TRAV_DEFER; // depends on the reference's visiting order
-        if (tt >= T.t) {                                   // acceptable runner-up just behind the best (or the best itself again)
-            if (i != T.hitTri) K.t2 = fminf(K.t2, tt);
-            continue;
-        }
-        if (T.hitTri >= 0) K.t2 = fminf(K.t2, T.t);        // the old best becomes the runner-up
+        if (shortcut || tt == T.t) return TRAV_DEFER;      // the outcome depends on the reference's visiting order
         T.t = tt;
         T.hitTri = i;
         if (ANY && !(tt + eps >= maxDist)) return TRAV_FIRED;
@@ -726,81 +672,24 @@ RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps,
     return fastPop(S, T, K, fastBound<ANY>(T, maxDist));
 }
 
-// Closest hit: does the reference find tri* (position `pos`, distance tStar)? Until tri* is accepted the reference's ray.t is
-// the ray's own bound tIn or the distance of another acceptable triangle. Every acceptable triangle closer than
-// tStar * (1 + 8e-7) has been examined by the search (its pruning factor CGRT_NEAR minus the rounding of the slab arithmetic),
-// the closest of them is t2; hence ray.t >= LB = min(tIn, t2, tStar * (1 + 5e-7)) > tStar at all those times. If every box on
-// the path root -> leaf(tri*) contains the origin strictly (visited unconditionally) or is reported hit by the reference's own
-// slabTest at a distance below LB, none of the reference's decisions on that path (`currentT >= ray.t` rejects, `ray.t <
-// tSecond` prunes a pending sibling) can go against descending, whatever the order of its visits; the leaf scan then accepts
-// tri* (tStar < ray.t) and nothing acceptable is closer. Boxes that are entered exactly where the triangle is hit (axis-aligned
-// geometry lying in a box face: distance within a few ulp of tStar) pass thanks to the 5e-7 margin.
-RT_DEV bool certifyClosest(const DevScene& S, const V3& o, const V3& d, int pos, float tStar, float t2, float tIn)
+// does the reference reach the leaf of triangle `pos` while ray.t is still above tStar? (see the block comment above)
+RT_DEV bool certifyChain(const DevScene& S, const V3& o, const V3& d, int pos, float tStar)
 {
-    const float lb = fminf(fminf(tIn, t2), tStar * 1.0000005f);
-    if (!(lb > tStar)) return false;
     int node = f2i(__ldg(S.triN0 + pos).w);
 #pragma unroll 1
     while (true) {
         const float4 q0 = __ldg(S.nodes + 2 * node), q1 = __ldg(S.nodes + 2 * node + 1);
         if (!startsInBox(o, mk3(q0), mk3(q1))) {
             float te = 0.0f;
-            if (!slabTest(mk3(q0), mk3(q1), o, d, lb, te)) return false;
-            if (!(te < lb)) return false; // NaN distances are not certificates
+            if (!slabTest(mk3(q0), mk3(q1), o, d, tStar, te)) return false;
+            if (!(te < tStar)) return false; // NaN distances are not certificates
         }
         if (node == 0) return true;
         node = __ldg(S.refParent + node);
     }
 }
 
-// Any hit: X (position `pos`, distance tX) is acceptable and satisfies the shadow predicate. On the path root -> leaf(X) the
-// reference either descends at every box - then it tests X and ends with ray.t <= tX - or it stops at a box because its ray.t
-// is already at or below that box's entry distance. Its final distance is therefore at most M = max(tX, entry distances of the
-// path's boxes), provided every box is geometrically hit; the predicate is monotone, so !(M + eps >= maxDist) proves "shadowed".
-RT_DEV bool certifyAny(const DevScene& S, const V3& o, const V3& d, int pos, float tX, float eps, float maxDist)
-{
-    float m = tX;
-    int node = f2i(__ldg(S.triN0 + pos).w);
-#pragma unroll 1
-    while (true) {
-        const float4 q0 = __ldg(S.nodes + 2 * node), q1 = __ldg(S.nodes + 2 * node + 1);
-        if (!startsInBox(o, mk3(q0), mk3(q1))) {
-            float te = 0.0f;
-            if (!slabTest(mk3(q0), mk3(q1), o, d, __int_as_float(0x7f800000), te)) return false;
-            if (!(te <= m)) m = te; // also taken for NaN, which then fails the predicate below
-        }
-        if (node == 0) break;
-        node = __ldg(S.refParent + node);
-    }
-    return !(m + eps >= maxDist);
-}
-
 RT_DEV bool travIsLeaf(uint32_t node) { return (node & CGRT_TRI) != 0u; }
-
-// The triangles the tree does not cover (DevScene::alwaysTri: extreme slivers / non-finite coordinates whose accept region has
-// no bounding box): every ray that enters the reference tree tests them with the same accept arithmetic, before or after the
-// search - the order does not matter to the search state (best, runner-up, defer on ties).
-template <bool ANY>
-RT_DEV int fastAlways(const DevScene& S, FastTrav& T, float& t2, float eps, float maxDist)
-{
-#pragma unroll 1
-    for (int k = 0; k < S.nAlways; k++) {
-        const int r = fastTriangle<ANY>(S, T, t2, __ldg(S.alwaysTri + k), eps, maxDist);
-        if (r != TRAV_CONTINUE) return r;
-    }
-    return TRAV_CONTINUE;
-}
-
-// fastBegin + always-list, for the traversals that finish a ray in one place (batch kernels, path pipeline); the round
-// pipeline's search kernels start with fastBegin only and k_finish applies the always-list to their result
-template <bool ANY>
-RT_DEV int fastStart(const DevScene& S, FastTrav& T, FastStack& K, const V3& o, const V3& d, float tIn, float eps, float maxDist)
-{
-    K.t2 = __int_as_float(0x7f800000);
-    const int state = fastBegin(S, T, o, d, tIn);
-    if (state != TRAV_CONTINUE || S.nAlways <= 0) return state;
-    return fastAlways<ANY>(S, T, K.t2, eps, maxDist);
-}
 
 template <bool ANY>
 RT_DEV int fastStep(const DevScene& S, FastTrav& T, FastStack& K, float eps, float maxDist)
@@ -812,7 +701,7 @@ RT_DEV int fastStep(const DevScene& S, FastTrav& T, FastStack& K, float eps, flo
 // After the search: certificate, then the sphere loop of BoundingVolumeHierarchy::intersect (bvh.cpp:878-879).
 // Returns false with `defer` set when the ray has to be replayed by the exact traversal.
 template <bool ANY>
-RT_DEV bool fastFinish(const DevScene& S, const FastTrav& T, float t2, int state, float tIn, float eps, float maxDist, TraceResult& R, bool& defer)
+RT_DEV bool fastFinish(const DevScene& S, const FastTrav& T, int state, float eps, float maxDist, TraceResult& R, bool& defer)
 {
     R.sphere = -1;
     R.t = T.t;
@@ -824,11 +713,11 @@ RT_DEV bool fastFinish(const DevScene& S, const FastTrav& T, float t2, int state
     }
     if (ANY) {
         if (state == TRAV_FIRED) {
-            if (!certifyAny(S, T.o, T.d, T.hitTri, T.t, eps, maxDist)) defer = true;
+            if (!certifyChain(S, T.o, T.d, T.hitTri, T.t)) defer = true;
             return !defer;
         }
     } else if (T.hitTri >= 0) {
-        if (!certifyClosest(S, T.o, T.d, T.hitTri, T.t, t2, tIn)) {
+        if (!certifyChain(S, T.o, T.d, T.hitTri, T.t)) {
             defer = true;
             return false;
         }
@@ -860,10 +749,10 @@ RT_DEV bool traverseSpec(const DevScene& S, const V3& o, const V3& d, float tIn,
     {
         FastTrav T;
         FastStack K;
-        int state = fastStart<ANY>(S, T, K, o, d, tIn, eps, maxDist);
+        int state = fastBegin(S, T, o, d, tIn);
         while (state == TRAV_CONTINUE) state = fastStep<ANY>(S, T, K, eps, maxDist);
         bool defer;
-        const bool r = fastFinish<ANY>(S, T, K.t2, state, tIn, eps, maxDist, R, defer);
+        const bool r = fastFinish<ANY>(S, T, state, eps, maxDist, R, defer);
         if (!defer) return r;
     }
     return traverseFast<ANY>(S, o, d, tIn, eps, maxDist, R);

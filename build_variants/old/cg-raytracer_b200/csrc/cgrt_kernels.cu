@@ -893,7 +893,7 @@ RT_DEV void persistentFast(const DevScene& S, Policy& P, int n, int* workCounter
                     idx = mine;
                     V3 o, d;
                     traced = P.load(idx, o, d, tIn, eps, maxDist);
-                    state = traced ? fastStart<ANY>(S, T, K, o, d, tIn, eps, maxDist) : TRAV_DONE;
+                    state = traced ? fastBegin(S, T, o, d, tIn) : TRAV_DONE;
                 }
             }
             INSTR_ADD(8, 1); INSTR_ADD(9, nIdle);
@@ -906,12 +906,12 @@ RT_DEV void persistentFast(const DevScene& S, Policy& P, int n, int* workCounter
                 TraceResult R;
                 R.sphere = -1; R.tri = -1; R.t = tIn;
                 bool result = false, defer = false;
-                if (fin && traced) result = fastFinish<ANY>(S, T, K.t2, state, tIn, eps, maxDist, R, defer);
+                if (fin && traced) result = fastFinish<ANY>(S, T, state, eps, maxDist, R, defer);
                 if (fin && defer) P.defer(T.o, T.d, tIn);
                 V3 no, nd;
                 const bool again = P.retire(fin && !defer, idx, traced, result, R, T.o, T.d, no, nd, tIn);
                 if (fin) {
-                    if (again) state = fastStart<ANY>(S, T, K, no, nd, tIn, eps, maxDist);
+                    if (again) state = fastBegin(S, T, no, nd, tIn);
                     else idx = -1;
                 }
                 continue;
@@ -1229,8 +1229,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE_MINBLOCKS) k_trace(DevScene S,
                     const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
                     maxDist = b.w;
                     eps = c.z;
-                    K.t2 = __int_as_float(0x7f800000);
-                    state = fastBegin(S, T, mk3(a), mk3(b), a.w); // (the always-list is applied by k_finish)
+                    state = fastBegin(S, T, mk3(a), mk3(b), a.w);
                 }
             }
             INSTR_ADD(8, 1); INSTR_ADD(9, nIdle);
@@ -1241,7 +1240,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE_MINBLOCKS) k_trace(DevScene S,
         for (int it = 0; it < CGRT_TRACE_STEPS; it++) {
             if (idx >= 0 && state != TRAV_CONTINUE) { // finished (possibly right at fastBegin): hand in the result
                 float4* out = idx < nA ? resA + idx : resB + (idx - nA);
-                *out = make_float4(i2f(state), T.t, i2f(T.hitTri), K.t2);
+                *out = make_float4(i2f(state), T.t, i2f(T.hitTri), 0.0f);
                 idx = -1;
                 TRACE_DONE_INSTR();
             }
@@ -1262,7 +1261,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE_MINBLOCKS) k_trace(DevScene S,
         }
         if (idx >= 0 && state != TRAV_CONTINUE) {
             float4* out = idx < nA ? resA + idx : resB + (idx - nA);
-            *out = make_float4(i2f(state), T.t, i2f(T.hitTri), K.t2);
+            *out = make_float4(i2f(state), T.t, i2f(T.hitTri), 0.0f);
             idx = -1;
             TRACE_DONE_INSTR();
         }
@@ -1306,7 +1305,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
     const float slack = 1.000001f;
     // group-uniform ray state (every lane of the group holds the same values)
     V3 o = mk3(0.0f, 0.0f, 0.0f), d = o, inv = o;
-    float t = 0.0f, t2 = 0.0f, eps = 0.0f, maxDist = 0.0f;
+    float t = 0.0f, eps = 0.0f, maxDist = 0.0f;
     int hitTri = -1, idx = -1, state = TRAV_DONE, sp = 0;
     uint32_t node = 0u;
     bool any = false;
@@ -1317,7 +1316,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
         if (idx >= 0 && state != TRAV_CONTINUE) {
             if (j == 0) {
                 float4* out = idx < nA ? resA + idx : resB + (idx - nA);
-                *out = make_float4(i2f(state), t, i2f(hitTri), t2);
+                *out = make_float4(i2f(state), t, i2f(hitTri), 0.0f);
             }
             idx = -1;
         }
@@ -1347,12 +1346,11 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
                     d = mk3(b);
                     maxDist = b.w;
                     eps = c.z;
-                    FastTrav T0; // (every lane of the group evaluates the same start; the always-list is applied by k_finish)
+                    FastTrav T0;
                     state = fastBegin(S, T0, o, d, a.w);
                     inv = T0.inv;
-                    t = T0.t;
-                    t2 = __int_as_float(0x7f800000);
-                    hitTri = T0.hitTri;
+                    t = a.w;
+                    hitTri = -1;
                     sp = 0;
                     node = T0.node;
                 }
@@ -1368,7 +1366,6 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
         const bool active = idx >= 0 && state == TRAV_CONTINUE;
         const bool isLeaf = (node & CGRT_TRI) != 0u;
         const float bound = (any ? fminf(t, maxDist) : t) * slack;
-        float near = __int_as_float(0x7f800000); // leaf: distance of an acceptable triangle that does not beat the best
         bool p = false, amb = false;     // p: this lane's child box is hit / this lane's triangle is an acceptable candidate
         unsigned key = 0xffffffffu;      // ordering key of the lane's result (entry distance | child, or candidate distance)
         uint32_t id = 0u;
@@ -1377,7 +1374,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
             if (isLeaf) {
                 // leaf: lane j tests triangle j with the reference's accept arithmetic (cgrt_device.cuh fastStepLeaf)
                 const int first = (int)(node & CGRT_IDX_MASK), count = (int)((node >> CGRT_TRICNT_SHIFT) & 7u) + 1;
-                if (j < count && first + j != hitTri) { // (own best candidate met again through the always-list: not a tie)
+                if (j < count) {
                     const float4* tr = S.tri4 + 4 * (size_t)(first + j);
                     const float4 pl = __ldg(tr), v0 = __ldg(tr + 1), v1 = __ldg(tr + 2), v2 = __ldg(tr + 3);
                     const V3 nrm = mk3(pl);
@@ -1391,14 +1388,14 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
                         else {
                             tt = (pl.w - on) / denominator;
                             if (tt < 0) cand = false;
-                            else if (hitTri < 0 ? !(tt < t) : !(tt <= t * CGRT_NEAR)) cand = false; // `t >= ray.t` / clearly farther
+                            else if (!(tt <= t)) cand = false;               // farther than the best (or NaN)
+                            else if (tt == t && hitTri < 0) cand = false;    // equals the ray's own bound: `t >= ray.t`
                         }
                     }
                     if (cand) {
                         const V3 pt = o + d * tt;
                         if (pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), nrm, pt)) {
-                            if (shortcut || (hitTri >= 0 && tt == t)) amb = true; // depends on the reference's visiting order
-                            else if (hitTri >= 0 && tt > t) near = tt;            // acceptable runner-up just behind the best
+                            if (shortcut || tt == t) amb = true; // the outcome depends on the reference's visiting order
                             else { p = true; key = __float_as_uint(tt + 0.0f); }
                         }
                     }
@@ -1426,20 +1423,13 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
         mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 4));
         const unsigned winm = (__ballot_sync(0xffffffffu, p && key == mn) >> (8 * g)) & 0xFFu;
         const uint32_t nextId = __shfl_sync(0xffffffffu, id, 8 * g + (int)(mn & 7u));
-        // leaf: smallest distance among the group's acceptable triangles that are not the new best (runner-up for the certificate)
-        float ru = (isLeaf && p && key != mn) ? __uint_as_float(key) : near;
-        ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 1));
-        ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 2));
-        ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 4));
         if (active) {
             bool pop = false;
             if (isLeaf) {
                 if (ambm != 0u || __popc(winm) > 1) {
                     state = TRAV_DEFER; // ties at the smallest distance / in-plane shortcut
                 } else {
-                    t2 = fminf(t2, ru);
                     if (pm != 0u) {
-                        if (hitTri >= 0) t2 = fminf(t2, t); // the old best becomes the runner-up
                         t = __uint_as_float(mn);
                         hitTri = (int)(node & CGRT_IDX_MASK) + (__ffs(winm) - 1);
                     }
@@ -1501,28 +1491,14 @@ __global__ void __launch_bounds__(128) k_finish(DevScene S, const FrameParams* _
             const float4* r = raysA + 3 * (size_t)i;
             const float4 a = r[0], b = r[1], c = r[2], res = resA[i];
             const V3 o = mk3(a), d = mk3(b);
-            int state = f2i(res.x), tri = f2i(res.z);
+            const int state = f2i(res.x), tri = f2i(res.z);
             const float eps = c.z, maxDist = b.w;
-            float tBest = res.y;
             bool shadowed = false, settled = false;
-            if (state == TRAV_DONE && S.nAlways > 0) { // the triangles outside the tree, if the ray enters the reference tree
-                const float4 rq0 = __ldg(S.nodes + 0), rq1 = __ldg(S.nodes + 1);
-                float tmp;
-                if (startsInBox(o, mk3(rq0), mk3(rq1)) || slabTest(mk3(rq0), mk3(rq1), o, d, a.w, tmp)) {
-                    FastTrav T;
-                    float t2s = res.w;
-                    T.o = o; T.d = d; T.t = tBest; T.hitTri = tri; T.sp = 0; T.node = 0u;
-                    state = fastAlways<true>(S, T, t2s, eps, maxDist);
-                    if (state == TRAV_CONTINUE) state = TRAV_DONE;
-                    tBest = T.t;
-                    tri = T.hitTri;
-                }
-            }
             if (state == TRAV_FIRED) {
-                if (certifyAny(S, o, d, tri, tBest, eps, maxDist)) { shadowed = true; settled = true; }
+                if (certifyChain(S, o, d, tri, res.y)) { shadowed = true; settled = true; }
             } else if (state == TRAV_DONE) { // the tree does not shadow; spheres may (bvh.cpp:878-879)
                 settled = true;
-                float t = tBest;
+                float t = res.y;
                 for (int sp = 0; sp < S.nSpheres; sp++) {
                     const float4 sc = __ldg(S.spheres + 3 * sp);
                     float ts;
@@ -1544,25 +1520,12 @@ __global__ void __launch_bounds__(128) k_finish(DevScene S, const FrameParams* _
             const float4 a = r[0], b = r[1], c = r[2], res = resB[i - nA];
             const V3 o = mk3(a), d = mk3(b);
             slot = f2i(c.x);
-            int state = f2i(res.x);
+            const int state = f2i(res.x);
             TraceResult R;
             R.sphere = -1;
             R.tri = f2i(res.z);
             R.t = res.y;
-            float t2 = res.w;
-            if (state == TRAV_DONE && S.nAlways > 0) { // the triangles outside the tree, if the ray enters the reference tree
-                const float4 rq0 = __ldg(S.nodes + 0), rq1 = __ldg(S.nodes + 1);
-                float tmp;
-                if (startsInBox(o, mk3(rq0), mk3(rq1)) || slabTest(mk3(rq0), mk3(rq1), o, d, a.w, tmp)) {
-                    FastTrav T;
-                    T.o = o; T.d = d; T.t = R.t; T.hitTri = R.tri; T.sp = 0; T.node = 0u;
-                    state = fastAlways<false>(S, T, t2, 0.0f, 0.0f);
-                    if (state == TRAV_CONTINUE) state = TRAV_DONE;
-                    R.t = T.t;
-                    R.tri = T.hitTri;
-                }
-            }
-            bool settled = state == TRAV_DONE && (R.tri < 0 || certifyClosest(S, o, d, R.tri, R.t, t2, a.w));
+            bool settled = state == TRAV_DONE && (R.tri < 0 || certifyChain(S, o, d, R.tri, R.t));
             if (settled) {
                 float t = R.t;
                 for (int sp = 0; sp < S.nSpheres; sp++) {
@@ -1789,61 +1752,6 @@ __global__ void k_quantize(const float* __restrict__ frame, size_t nPixels, uint
     }
     o.x = (unsigned char)c[0]; o.y = (unsigned char)c[1]; o.z = (unsigned char)c[2]; o.w = 255;
     reinterpret_cast<uchar4*>(rgba)[i] = o;
-}
-
-// =================================================================================================================
-// Post passes of renderRayTracing (src/main.cpp:663-687 anti-aliasing, :318-584 motion blur): image kernels around the renderer
-// =================================================================================================================
-// Anti-aliasing (main.cpp:663-687): four rays per pixel at NDC (float(2x+i)/W * (2/level) - 1, float(2y+j)/H * (2/level) - 1),
-// level = 2, i.e. exactly the pixel-corner rays of a (2W x 2H) frame (float(k)/(2W)*2 == float(k)/W*1 bit for bit), summed in
-// the order (j outer, i inner) into `color` and divided by level * 2.5 = 5 (sic). `color` is never initialised in the reference;
-// this implementation starts it at zero (documented assumption).
-__global__ void k_aa_downsample(const float* __restrict__ big, int W, int H, float* __restrict__ out)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= W * H) return;
-    const int row = i / W, x = i - row * W; // Screen layout: row = H-1-y
-    const int y = H - 1 - row;
-    const int W2 = 2 * W, H2 = 2 * H;
-    float c[3] = {0.0f, 0.0f, 0.0f};
-    for (int j = 0; j < 2; j++)
-        for (int k = 0; k < 2; k++) {
-            const int xc = 2 * x + k, yc = 2 * y + j;
-            const float* src = big + 3 * ((size_t)(H2 - 1 - yc) * W2 + xc);
-            c[0] = c[0] + src[0]; c[1] = c[1] + src[1]; c[2] = c[2] + src[2];
-        }
-    const float level = 2.0f;
-    const float div = level * 2.5f;
-    out[3 * (size_t)i + 0] = c[0] / div;
-    out[3 * (size_t)i + 1] = c[1] / div;
-    out[3 * (size_t)i + 2] = c[2] / div;
-}
-
-// Motion blur (blurEffect, main.cpp:318-584): matrixPixels += frame for the 15 shifted look-at points, then / 16
-__global__ void k_accumulate(float* __restrict__ acc, const float* __restrict__ frame, size_t n, int first)
-{
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    acc[i] = first ? (0.0f + frame[i]) : (acc[i] + frame[i]);
-}
-__global__ void k_divide(const float* __restrict__ acc, size_t n, float div, float* __restrict__ out)
-{
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    out[i] = acc[i] / div;
-}
-
-void launchAADownsample(const float* big, int W, int H, float* out, cudaStream_t st)
-{
-    k_aa_downsample<<<(W * H + 255) / 256, 256, 0, st>>>(big, W, H, out);
-}
-void launchAccumulate(float* acc, const float* frame, size_t n, bool first, cudaStream_t st)
-{
-    if (n) k_accumulate<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, frame, n, first ? 1 : 0);
-}
-void launchDivide(const float* acc, size_t n, float div, float* out, cudaStream_t st)
-{
-    if (n) k_divide<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, n, div, out);
 }
 
 // =================================================================================================================

@@ -14,7 +14,7 @@ echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k k_trace --launch-skip 72 --launch-count 8 \
     -o /tmp/prof_${tag}_trace -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$tag.log 2>&1
 echo "full k_trace rc=$?"
-ncu --set full --clock-control none -k regex:'k_trace8|k_finish|k_gen|k_shade_slots' --launch-skip 150 --launch-count 30 \
+ncu --set full --clock-control none -k regex:'k_trace8|k_finish|k_gen|k_shade_slots' --launch-skip 150 --launch-count 50 \
     -o /tmp/prof_${tag}_rest -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline >> gpurun_out/ncu_full_$tag.log 2>&1
 echo "full rest rc=$?"
 for k in trace rest; do
