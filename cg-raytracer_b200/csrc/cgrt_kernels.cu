@@ -2092,7 +2092,7 @@ int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FramePar
             if (coopMax > 0)
                 k_trace8<<<numSMs * CGRT_TRACE8_MINBLOCKS, 128, 0, sc>>>(S, raysA, resA, nA, hP.nLights, raysB, resB, nB,
                                                                          counts + CGRT_CNT_WORK + r, coopMax);
-            launches++;
+            launches += (coopMax < (1 << 30) ? 1 : 0) + (coopMax > 0 ? 1 : 0); // both are launches, one returns at once
             traceEnd(tr, 2, sc);
             traceBegin(tr, 1, sc);
             k_finish<<<flatChain, 128, 0, sc>>>(S, dP, dLights, B, r, raysA, resA, nA, raysB, resB, nB, B.cRay[(r + 1) & 1],
