@@ -275,8 +275,10 @@ def main():
     # One GPU: the streaming form (cgrt_render_submit / cgrt_render_wait, two frames in flight: the copy of frame k overlaps
     # the kernels of frame k+1; all K frames are delivered before the clock stops). The synchronous call (cgrt_render, one
     # frame at a time) is timed next to it and reported in config.e2e_synchronous. N > 1: synchronous frames on rank 0.
+    streaming = world == 1 or R.mode == "p2p"
     e2e_mode = "streaming (cgrt_render_submit x K + cgrt_render_wait, 2 frames in flight)" if world == 1 else \
-               "synchronous per frame (render, exchange, D2H, stream sync)"
+               ("streaming (two frames on rank 0, copy-out of frame k on a second stream while frame k+1 renders)" if streaming
+                else "synchronous per frame (render, exchange, D2H, stream sync)")
     for _ in range(2):
         R.render_to_host(cam)
     barrier()
@@ -286,14 +288,17 @@ def main():
     barrier()
     e2e_sync_s = time.perf_counter() - t0
     e2e_s = e2e_sync_s
-    if world == 1:
+    if streaming:
         R.stream_to_host(cam, 3)
         barrier()
         t0 = time.perf_counter()
         last = R.stream_to_host(cam, args.steps)
         barrier()
         e2e_s = time.perf_counter() - t0
-        assert np.array_equal(last, R.render_to_host(cam)), "streamed frame differs from the synchronous frame"
+        last = last.copy() if rank == 0 else None
+        ref_frame = R.render_to_host(cam)
+        if rank == 0:
+            assert np.array_equal(last, ref_frame), "streamed frame differs from the synchronous frame"
     t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

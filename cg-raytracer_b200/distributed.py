@@ -146,11 +146,12 @@ class TiledRenderer:
         HB = _capi.IPC_HANDLE_BYTES
         self.consumed = self._malloc(256)  # [0] consumed sequence number of this rank, [64] wait-timeout counter
         self.status = C.c_void_p(self.consumed.value + 64)  # same allocation, 64 bytes in
-        mine = [self._export(self.consumed), bytes(HB), bytes(HB)]
+        mine = [self._export(self.consumed), bytes(HB), bytes(HB), bytes(HB)]
         if self.rank == 0:
-            self.frame_ptr = self._malloc(nfl * 4)
+            # two frames: frame k lives in buffer k & 1, so that the copy-out of frame k can overlap the rendering of k + 1
+            self.frame_ptrs = [self._malloc(nfl * 4), self._malloc(nfl * 4)]
             self.arrive = self._malloc(4 * max(self.world, 64))
-            mine[1], mine[2] = self._export(self.frame_ptr), self._export(self.arrive)
+            mine[1], mine[2], mine[3] = self._export(self.frame_ptrs[0]), self._export(self.arrive), self._export(self.frame_ptrs[1])
         _capi.check(self.lib.cgrt_device_synchronize(self.device))
         t = torch.tensor(list(b"".join(mine)), dtype=torch.uint8, device=self.dev)
         allh = [torch.empty_like(t) for _ in range(self.world)]
@@ -158,12 +159,13 @@ class TiledRenderer:
         allh = [bytes(x.cpu().tolist()) for x in allh]
         if self.rank == 0:
             self.peer_consumed = [None] + [self._open(allh[r][0:HB]) for r in range(1, self.world)]
-            self.frame = torch.as_tensor(_DevicePtr(self.frame_ptr.value, nfl), device=self.dev)
-            self.out_ptr = self.frame_ptr
+            self.frames = [torch.as_tensor(_DevicePtr(q.value, nfl), device=self.dev) for q in self.frame_ptrs]
+            self.out_ptrs = self.frame_ptrs
         else:
-            self.frame = None
-            self.out_ptr = self._open(allh[0][HB:2 * HB])
+            self.frames = [None, None]
+            self.out_ptrs = [self._open(allh[0][HB:2 * HB]), self._open(allh[0][3 * HB:4 * HB])]
             self.peer_arrive = self._open(allh[0][2 * HB:3 * HB])
+        self._copy_done = [None, None]  # rank 0, streaming: event after the copy-out of the frame that last used the buffer
         dist.barrier(device_ids=[self.device])
 
     def _stream(self):
@@ -176,15 +178,22 @@ class TiledRenderer:
         lib, dv = self.lib, self.device
         self.seq += 1
         seq = self.seq
+        b = seq & 1
+        free = max(seq - 2, 0)  # the frame that used buffer b before
         if self.rank == 0:
-            # everything enqueued on this stream so far (the consumer of frame seq-1) precedes this signal
+            # the consumer of frame seq-2 precedes this signal: either it was enqueued on this stream (stream order), or it is
+            # the streaming copy-out, whose event the stream waits for first
+            if self._copy_done[b] is not None:
+                self.torch.cuda.current_stream(self.dev).wait_event(self._copy_done[b])
+                self._copy_done[b] = None
             ptrs = (C.c_void_p * (self.world - 1))(*[q.value for q in self.peer_consumed[1:]])
-            _capi.check(lib.cgrt_flag_signal(dv, ptrs, self.world - 1, seq - 1, st))
-            self.scene.render_device(cam, p, self.out_ptr.value, st.value)
+            _capi.check(lib.cgrt_flag_signal(dv, ptrs, self.world - 1, free, st))
+            self.scene.render_device(cam, p, self.out_ptrs[b].value, st.value)
             _capi.check(lib.cgrt_flag_wait(dv, C.c_void_p(self.arrive.value + 4), self.world - 1, seq, self.TIMEOUT_MS, self.status, st))
+            self.frame = self.frames[b]
             return self.frame
-        _capi.check(lib.cgrt_flag_wait(dv, self.consumed, 1, seq - 1, self.TIMEOUT_MS, self.status, st))
-        self.scene.render_device(cam, p, self.out_ptr.value, st.value)
+        _capi.check(lib.cgrt_flag_wait(dv, self.consumed, 1, free, self.TIMEOUT_MS, self.status, st))
+        self.scene.render_device(cam, p, self.out_ptrs[b].value, st.value)
         ptrs = (C.c_void_p * 1)(self.peer_arrive.value + 4 * self.rank)
         _capi.check(lib.cgrt_flag_signal(dv, ptrs, 1, seq, st))
         return None
@@ -239,18 +248,49 @@ class TiledRenderer:
         return 1 if self.rank == 0 else 0
 
     def stream_to_host(self, cam, n_frames):
-        """Single GPU, streaming: n_frames frames through cgrt_render_submit into two alternating page-locked buffers, then
-        cgrt_render_wait. Returns the last frame [H,W,3]. (Frame k's copy overlaps frame k+1's kernels.)"""
-        assert self.world == 1
+        """Streaming: n_frames frames end to end with two frames in flight, so that the device->host copy of frame k overlaps
+        the kernels of frame k+1; returns the last frame [H,W,3] on rank 0 once every frame has been delivered.
+        One GPU: cgrt_render_submit / cgrt_render_wait. Several GPUs (p2p mode): rank 0 owns two frames (buffer k & 1), copies
+        them out on a second stream, and only frees a buffer for the peers ("consumed" flag) when its copy has finished."""
         torch = self.torch
-        if getattr(self, "_stream_bufs", None) is None:
+        if getattr(self, "_stream_bufs", None) is None and self.rank == 0:
             self._stream_bufs = [torch.empty(self.H * self.W * 3, dtype=torch.float32).pin_memory() for _ in range(2)]
-        p = self.params
-        p.flags = 0
+        if self.world == 1:
+            p = self.params
+            p.flags = 0
+            for k in range(n_frames):
+                self.scene.render_submit(cam, p, self._stream_bufs[k & 1].data_ptr())
+            self.scene.render_wait()
+            return self._stream_bufs[(n_frames - 1) & 1].numpy().reshape(self.H, self.W, 3)
+        if self.mode != "p2p":  # the gather mode has no second frame: synchronous frames
+            out = None
+            for _ in range(n_frames):
+                out = self.render_to_host(cam)
+            return out
+        main = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        last = None
         for k in range(n_frames):
-            self.scene.render_submit(cam, p, self._stream_bufs[k & 1].data_ptr())
-        self.scene.render_wait()
-        return self._stream_bufs[(n_frames - 1) & 1].numpy().reshape(self.H, self.W, 3)
+            frame = self.render_device(cam)
+            if self.rank == 0:
+                b = self.seq & 1
+                done = torch.cuda.Event()
+                done.record(main)
+                self._copy_stream.wait_event(done)
+                with torch.cuda.stream(self._copy_stream):
+                    self._stream_bufs[b].copy_(frame, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                self._copy_done[b] = ev
+                last = self._stream_bufs[b]
+            if (k & 15) == 15:
+                main.synchronize()  # bound the host's run-ahead (per-frame parameter ring of the library)
+        main.synchronize()
+        if self.rank == 0:
+            self._copy_stream.synchronize()
+            return last.numpy().reshape(self.H, self.W, 3)
+        return None
 
     def render_to_host(self, cam):
         """End to end: per-frame inputs (camera + lights) go host->device inside the call, the finished frame comes back to

@@ -43,9 +43,12 @@ def main():
                         print(f"[multi_check] {W}x{H} limit {L} mode {R.mode} (asked {mode}, fallback {R.fallback_reason}) frame {k}: "
                               f"{'bit-identical' if same else 'MISMATCH max|d|=%g' % float((f - ref).abs().max())}", flush=True)
                     f.zero_()  # the next frame must rewrite every pixel
+            hs = R.stream_to_host(cam, 5)  # two frames in flight (p2p) / synchronous frames (nccl)
+            if rank == 0:
+                ok &= bool(np.array_equal(hs.reshape(-1), ref.cpu().numpy()))
             h = R.render_to_host(cam)
             if rank == 0:
-                same = np.array_equal(h.reshape(-1), ref.cpu().numpy())
+                same = np.array_equal(h.reshape(-1), ref.cpu().numpy()) and ok
                 ok &= bool(same)
                 print(f"[multi_check] {W}x{H} mode {R.mode} host frame: {'bit-identical' if same else 'MISMATCH'}; timeouts {R.timeouts()}", flush=True)
                 ok &= R.timeouts() == 0
