@@ -207,7 +207,7 @@ def render_params(W, H, trace_limit=2, rank=0, world=1, tile_w=0, tile_h=0, flag
 
 
 class Scene:
-    """Device-resident scene + BVH (cgrt_scene). `flat` needs the attributes of oracle.bindings.FlatScene /
+    """Device-resident scene + BVH (cgrt_scene). `flat` needs the attributes of the flat-scene layout /
     host loader output: vcount, tcount, vertices[.,6], triangles[.,3], materials[.,8], spheres[.,12]."""
 
     def __init__(self, flat, lights=None, device=0, bvh_max_depth=12, host_only=False, no_subtrees=False, exact_only=None):

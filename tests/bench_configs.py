@@ -1,7 +1,7 @@
 """Device-time table for every BASELINE.json configuration (C1..C5) on one GPU. Not the contract bench (bench.py); used to
 fill the per-config numbers in profiles/ and README."""
 import os, sys, time, json, ctypes as C
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # (lives under tests/: it uses the oracle's scene generators and the golden fixtures)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import __graft_entry__ as ge
