@@ -15,6 +15,7 @@
 #include <functional>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstddef>
 #include <limits>
 
@@ -417,10 +418,164 @@ void buildLeafSubTrees(const std::vector<MeshView>& meshes, BuiltBVH& bvh, int m
 // =================================================================================================================
 // Fast tree: the reference tree collapsed into 8-wide conservative nodes on top of the leaf sub-trees
 // =================================================================================================================
-void buildFastTree(const std::vector<MeshView>& meshes, BuiltBVH& bvh)
+namespace {
+
+// ---- binned SAH over conservative triangle boxes -> binary tree -> 8-wide nodes ---------------------------------------------
+struct SahNode {
+    float lo[3], hi[3];
+    int left, right;  // -1 for leaves
+    int first, count; // leaves: range of the order array
+};
+
+struct SahBuilder {
+    const std::vector<TriBox>& boxes; // per position
+    std::vector<int32_t>& order;      // positions, permuted in place; leaves are contiguous ranges
+    std::vector<SahNode> nodes;
+    int leafMax;
+
+    static double area(const float lo[3], const float hi[3])
+    {
+        const double dx = std::max(0.0, (double)hi[0] - lo[0]), dy = std::max(0.0, (double)hi[1] - lo[1]),
+                     dz = std::max(0.0, (double)hi[2] - lo[2]);
+        return dx * dy + dy * dz + dz * dx;
+    }
+
+    int build(int begin, int end)
+    {
+        const int self = (int)nodes.size();
+        nodes.push_back(SahNode());
+        SahNode n;
+        float clo[3], chi[3];
+        for (int k = 0; k < 3; k++) { n.lo[k] = clo[k] = FLT_MAX; n.hi[k] = chi[k] = -FLT_MAX; }
+        for (int i = begin; i < end; i++) {
+            const TriBox& b = boxes[order[i]];
+            for (int k = 0; k < 3; k++) {
+                n.lo[k] = std::min(n.lo[k], b.lo[k]); n.hi[k] = std::max(n.hi[k], b.hi[k]);
+                clo[k] = std::min(clo[k], b.c[k]); chi[k] = std::max(chi[k], b.c[k]);
+            }
+        }
+        n.left = n.right = -1;
+        n.first = begin;
+        n.count = end - begin;
+        const int N = end - begin;
+        int mid = -1;
+        if (N > leafMax) {
+            // 16 bins per axis over the centroid bounds; cost of a split = A_L N_L + A_R N_R
+            const int NB = 16;
+            double bestCost = 1e300;
+            int bestAxis = -1, bestBin = -1;
+            for (int axis = 0; axis < 3; axis++) {
+                const float ext = chi[axis] - clo[axis];
+                if (!(ext > 0.0f) || !std::isfinite(ext)) continue;
+                int cnt[NB] = {0};
+                float blo[NB][3], bhi[NB][3];
+                for (int b = 0; b < NB; b++)
+                    for (int k = 0; k < 3; k++) { blo[b][k] = FLT_MAX; bhi[b][k] = -FLT_MAX; }
+                const float scale = NB / ext;
+                for (int i = begin; i < end; i++) {
+                    const TriBox& t = boxes[order[i]];
+                    int b = (int)((t.c[axis] - clo[axis]) * scale);
+                    b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+                    cnt[b]++;
+                    for (int k = 0; k < 3; k++) { blo[b][k] = std::min(blo[b][k], t.lo[k]); bhi[b][k] = std::max(bhi[b][k], t.hi[k]); }
+                }
+                double rightA[NB];
+                int rightN[NB];
+                float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+                int acc = 0;
+                for (int b = NB - 1; b >= 1; b--) {
+                    for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], blo[b][k]); hi[k] = std::max(hi[k], bhi[b][k]); }
+                    acc += cnt[b];
+                    rightA[b] = area(lo, hi);
+                    rightN[b] = acc;
+                }
+                for (int k = 0; k < 3; k++) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
+                acc = 0;
+                for (int b = 0; b < NB - 1; b++) { // split between bin b and b + 1
+                    for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], blo[b][k]); hi[k] = std::max(hi[k], bhi[b][k]); }
+                    acc += cnt[b];
+                    if (acc == 0 || rightN[b + 1] == 0) continue;
+                    const double cost = area(lo, hi) * acc + rightA[b + 1] * rightN[b + 1];
+                    if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
+                }
+            }
+            const bool worthIt = bestAxis >= 0 && (N > 8 || bestCost < area(n.lo, n.hi) * N);
+            if (worthIt) {
+                const float ext = chi[bestAxis] - clo[bestAxis];
+                const float scale = NB / ext;
+                auto it = std::partition(order.begin() + begin, order.begin() + end, [&](int32_t p) {
+                    int b = (int)((boxes[p].c[bestAxis] - clo[bestAxis]) * scale);
+                    b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+                    return b <= bestBin;
+                });
+                mid = (int)(it - order.begin());
+                if (mid == begin || mid == end) mid = -1;
+            }
+            if (mid < 0 && N > 8) { // no usable plane (coincident centroids ...): split the range in two halves
+                mid = begin + N / 2;
+            }
+        }
+        if (mid >= 0) {
+            n.left = build(begin, mid);
+            n.right = build(mid, end);
+        }
+        nodes[self] = n;
+        return self;
+    }
+};
+
+} // namespace
+
+static uint32_t buildFastTreeSah(const std::vector<TriBox>& boxes, std::vector<int32_t>& order, BuiltBVH& bvh)
+{
+    const uint32_t ID_TRI = 0x20000000u, ID_SUB = 0x40000000u;
+    if (order.empty()) return 0u;
+    int leafMax = 6; // triangles per leaf (speed only; CGRT_SAH_LEAF overrides for tuning)
+    if (const char* e = getenv("CGRT_SAH_LEAF")) leafMax = std::max(1, std::min(8, atoi(e)));
+    SahBuilder sb{boxes, order, {}, leafMax};
+    sb.nodes.reserve(order.size());
+    const int root = sb.build(0, (int)order.size());
+    std::function<uint32_t(int)> wide = [&](int bi) -> uint32_t {
+        const SahNode& b = sb.nodes[bi];
+        if (b.left < 0) return ID_SUB | ID_TRI | ((uint32_t)(b.count - 1) << 26) | (uint32_t)b.first;
+        std::vector<int> slots{b.left, b.right};
+        while (slots.size() < 8) {
+            int best = -1;
+            double bestA = -1.0;
+            for (size_t c = 0; c < slots.size(); c++) {
+                const SahNode& sn = sb.nodes[slots[c]];
+                if (sn.left < 0) continue;
+                const double a = SahBuilder::area(sn.lo, sn.hi);
+                if (a > bestA) { bestA = a; best = (int)c; }
+            }
+            if (best < 0) break;
+            const SahNode o = sb.nodes[slots[best]];
+            slots[best] = o.left;
+            slots.push_back(o.right);
+        }
+        const int self = (int)bvh.wide.size();
+        bvh.wide.push_back(WideNode());
+        WideNode w;
+        for (int c = 0; c < 8; c++) {
+            for (int k = 0; k < 3; k++) { w.lo[c][k] = FLT_MAX; w.hi[c][k] = -FLT_MAX; }
+            w.id[c] = 0u;
+        }
+        for (size_t c = 0; c < slots.size(); c++) {
+            const SahNode& sn = sb.nodes[slots[c]];
+            for (int k = 0; k < 3; k++) { w.lo[c][k] = sn.lo[k]; w.hi[c][k] = sn.hi[k]; }
+            w.id[c] = wide(slots[c]);
+        }
+        bvh.wide[self] = w;
+        return ID_SUB | (uint32_t)self;
+    };
+    return wide(root);
+}
+
+void buildFastTree(const std::vector<MeshView>& meshes, BuiltBVH& bvh, bool sah)
 {
     const size_t NN = bvh.nodes.size();
     bvh.fastRoot = 0u;
+    bvh.fastOrder.clear();
     bvh.alwaysTest.clear();
     bvh.parent.assign(NN, -1);
     bvh.triLeafNode.assign(bvh.leafTris.size(), 0);
@@ -428,6 +583,7 @@ void buildFastTree(const std::vector<MeshView>& meshes, BuiltBVH& bvh)
     if (bvh.wideRoot.size() != NN) bvh.wideRoot.assign(NN, -1);
     // conservative box of every reference node, bottom-up (children always have larger indices: BFS numbering)
     std::vector<TriBox> cons(NN);
+    std::vector<TriBox> triBoxes(sah ? bvh.leafTris.size() : 0);
     for (size_t i = NN; i-- > 0;) {
         const HostNode& n = bvh.nodes[i];
         TriBox& b = cons[i];
@@ -440,6 +596,7 @@ void buildFastTree(const std::vector<MeshView>& meshes, BuiltBVH& bvh)
                 const uint32_t* tri = mv.triangles + 3 * (size_t)lt.tri;
                 const TriBox tb = conservativeBox(mv.vertices + 6 * (size_t)tri[0], mv.vertices + 6 * (size_t)tri[1],
                                                   mv.vertices + 6 * (size_t)tri[2]);
+                if (sah) triBoxes[n.firstTri + t] = tb;
                 if (!tb.bounded) { // would make every ancestor's box unbounded: kept out of the tree, tested for every ray
                     bvh.alwaysTest.push_back(n.firstTri + t);
                     continue;
@@ -454,6 +611,19 @@ void buildFastTree(const std::vector<MeshView>& meshes, BuiltBVH& bvh)
                 for (int k = 0; k < 3; k++) { b.lo[k] = std::min(b.lo[k], cb.lo[k]); b.hi[k] = std::max(b.hi[k], cb.hi[k]); }
             }
         }
+    }
+    if (sah) { // independent tree with its own triangle order; unbounded triangles go last (reached only through alwaysTest)
+        std::vector<char> unb(bvh.leafTris.size(), 0);
+        for (int32_t a : bvh.alwaysTest) unb[a] = 1;
+        std::vector<int32_t> order;
+        order.reserve(bvh.leafTris.size());
+        for (size_t p = 0; p < bvh.leafTris.size(); p++)
+            if (!unb[p]) order.push_back((int32_t)p);
+        const uint32_t root = bvh.alwaysTest.size() <= 256 ? buildFastTreeSah(triBoxes, order, bvh) : 0u;
+        bvh.fastOrder = order;
+        for (int32_t a : bvh.alwaysTest) bvh.fastOrder.push_back(a);
+        bvh.fastRoot = root;
+        return;
     }
     const uint32_t ID_TRI = 0x20000000u, ID_SUB = 0x40000000u;
     // id of a reference leaf in the fast tree: its sub-tree root, or its triangles directly (leaves without a sub-tree hold at

@@ -49,6 +49,8 @@ struct BuiltBVH {
     uint32_t fastRoot = 0;             // id of the root in the traversal's encoding, 0 = no fast tree
     std::vector<int32_t> parent;       // per reference node: parent index (-1 for the root)
     std::vector<int32_t> triLeafNode;  // per position: reference leaf that holds the triangle
+    std::vector<int32_t> fastOrder;    // fast-tree triangle order: fast position -> position (the fast tree's leaves are ranges of
+                                       // THIS order; identity when the fast tree reuses the reference leaves' sub-trees)
     std::vector<int32_t> alwaysTest;   // positions of triangles whose accept region cannot be bounded (extreme slivers, non-finite):
                                        // not covered by the fast tree's boxes, tested for every ray that enters the tree
     int numLevels = 0;
@@ -68,6 +70,9 @@ void buildLeafSubTrees(const std::vector<MeshView>& meshes, BuiltBVH& bvh, int m
 // The speculative traversal's tree (after buildLeafSubTrees): appends the collapsed top levels to bvh.wide and fills
 // fastRoot / parent / triLeafNode. Boxes are unions of the triangles' conservative boxes, so the tolerant slab test can never
 // cull a triangle the reference could accept, wherever it sits in the reference tree.
-void buildFastTree(const std::vector<MeshView>& meshes, BuiltBVH& bvh);
+// sah = false: the reference tree collapsed three levels at a time on top of the leaf sub-trees (shares their triangle order).
+// sah = true : an independent binned-SAH tree over all triangles with its own triangle order (fastOrder); the certificate
+//              still walks the REFERENCE tree (parent / triLeafNode), so results do not depend on this choice.
+void buildFastTree(const std::vector<MeshView>& meshes, BuiltBVH& bvh, bool sah = false);
 
 } // namespace cgrt

@@ -187,7 +187,9 @@ static void fastTreeSelfCheck(const std::vector<MeshView>& views, const BuiltBVH
         stack.pop_back();
         if (it.id & ID_TRI) {
             const int first = (int)(it.id & ID_MASK), count = (int)((it.id >> 26) & 7u) + 1;
-            for (int t = first; t < first + count; t++) {
+            for (int ft = first; ft < first + count; ft++) {
+                // leaves hold positions of the fast tree's own order (identity unless the SAH tree is used)
+                const int t = bvh.fastOrder.empty() ? ft : (ft >= 0 && (size_t)ft < bvh.fastOrder.size() ? bvh.fastOrder[ft] : -1);
                 if (t < 0 || (size_t)t >= seen.size()) { out[2]++; continue; }
                 seen[t]++;
                 out[1]++;
@@ -216,6 +218,8 @@ static void fastTreeSelfCheck(const std::vector<MeshView>& views, const BuiltBVH
             stack.push_back(ch);
         }
     }
+    if (!bvh.fastOrder.empty()) // SAH tree: the always-list triangles are outside the tree by construction
+        for (int32_t a : bvh.alwaysTest) { seen[a]++; out[1]++; }
     for (int v : seen)
         if (v != 1) out[2]++;
 }
@@ -233,8 +237,8 @@ struct cgrt_scene {
     int64_t nTris = 0;
     int nMeshes = 0;
 
-    DevBuf<float4> wide8, tri4, nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, pairs, wide;
-    DevBuf<int> origToLeaf, refParent, alwaysTri;
+    DevBuf<float4> wide8, tri4, tri4f, nodes, triPl, triV0, triV1, triV2, triN0, triN1, triN2, mats, spheres, pairs, wide;
+    DevBuf<int> origToLeaf, refParent, alwaysTri, fastOrder;
     DevScene dev{};
 
     std::vector<cgrt_point_light> lights;
@@ -302,7 +306,7 @@ static void destroyScene(cgrt_scene* s)
         return;
     }
     cudaSetDevice(s->device);
-    s->wide8.release(); s->tri4.release(); s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
+    s->wide8.release(); s->tri4.release(); s->tri4f.release(); s->fastOrder.release(); s->nodes.release(); s->triPl.release(); s->triV0.release(); s->triV1.release(); s->triV2.release();
     s->triN0.release(); s->triN1.release(); s->triN2.release(); s->mats.release(); s->spheres.release();
     s->origToLeaf.release(); s->refParent.release(); s->alwaysTri.release(); s->pairs.release(); s->wide.release(); s->dParamBlock.release(); s->hitQ.release(); s->bounceQ.release(); s->pathState.release();
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->tileSeq.release(); s->frame.release();
@@ -427,7 +431,9 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
                 for (int i = 0; i < n.triCount; i++) s->bvh.leafRank[n.firstTri + i] = i;
     }
     if (fastTree) {
-        buildFastTree(views, s->bvh);
+        // fast-tree flavour (speed only; results do not depend on it): independent binned-SAH tree unless CGRT_FAST_TREE=ref
+        const char* ft = getenv("CGRT_FAST_TREE");
+        buildFastTree(views, s->bvh, !(ft && std::string(ft) == "ref"));
         fastTreeSelfCheck(views, s->bvh, s->fastStats);
     }
     if (hostOnly) { // BVH introspection only (builder tests on machines without a GPU); every query entry refuses it
@@ -562,6 +568,15 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     if (rc) { destroyScene(s); return rc; }
     rc = s->tri4.ensure(4 * T);
     if (rc) { destroyScene(s); return rc; }
+    rc = s->tri4f.ensure(4 * T);
+    if (rc) { destroyScene(s); return rc; }
+    if (s->bvh.fastOrder.size() == T && T > 0) {
+        std::vector<int> hOrder(s->bvh.fastOrder.begin(), s->bvh.fastOrder.end());
+        rc = s->fastOrder.ensure(T);
+        if (rc) { destroyScene(s); return rc; }
+        cudaError_t e_ = cudaMemcpy(s->fastOrder.p, hOrder.data(), T * sizeof(int), cudaMemcpyHostToDevice);
+        if (e_ != cudaSuccess) { destroyScene(s); return fail(CGRT_ERR_CUDA, cudaGetErrorString(e_)); }
+    }
 
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
@@ -569,6 +584,7 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     if (e != cudaSuccess) { destroyScene(s); return fail(CGRT_ERR_CUDA, cudaGetErrorString(e)); }
 
     launchSetupPlanes(s->triV0.p, s->triV1.p, s->triV2.p, s->triPl.p, s->tri4.p, (int)T, s->stream);
+    launchPermuteTri4(s->tri4.p, s->bvh.fastOrder.size() == T ? s->fastOrder.p : nullptr, s->tri4f.p, (int)T, s->stream);
     e = cudaStreamSynchronize(s->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { destroyScene(s); return fail(CGRT_ERR_CUDA, std::string("plane set-up kernel: ") + cudaGetErrorString(e)); }
@@ -576,6 +592,7 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     s->dev.nodes = s->nodes.p;
     s->dev.triPl = s->triPl.p;
     s->dev.tri4 = s->tri4.p;
+    s->dev.tri4f = s->tri4f.p;
     s->dev.triV0 = s->triV0.p; s->dev.triV1 = s->triV1.p; s->dev.triV2 = s->triV2.p;
     s->dev.triN0 = s->triN0.p; s->dev.triN1 = s->triN1.p; s->dev.triN2 = s->triN2.p;
     s->dev.mats = s->mats.p;

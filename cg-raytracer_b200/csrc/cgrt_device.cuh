@@ -558,7 +558,7 @@ RT_DEV void fastPrefetch(const DevScene& S, uint32_t id)
 {
 #if CGRT_PREFETCH
     if (id & CGRT_TRI) {
-        const float4* tr = S.tri4 + 4 * (size_t)(id & CGRT_IDX_MASK);
+        const float4* tr = S.tri4f + 4 * (size_t)(id & CGRT_IDX_MASK);
         const int count = (int)((id >> CGRT_TRICNT_SHIFT) & 7u) + 1;
         for (int k = 0; k < count; k++) prefetchL1(tr + 4 * k);
     } else {
@@ -696,8 +696,8 @@ RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps,
     // (fastTriangle written out: this is the hot loop of the search, and its shape matters to the compiler)
 #pragma unroll 1
     for (int i = first; i < first + count; i++) {
-        // the whole 64-byte record at once: one memory round trip per triangle
-        const float4* tr = S.tri4 + 4 * (size_t)i;
+        // the whole 64-byte record at once: one memory round trip per triangle (fast-tree order; v2.w = position in tri4)
+        const float4* tr = S.tri4f + 4 * (size_t)i;
         const float4 pl = __ldg(tr), v0 = __ldg(tr + 1), v1 = __ldg(tr + 2), v2 = __ldg(tr + 3);
         const V3 n = mk3(pl);
         const float on = dot3(o, n);
@@ -713,14 +713,15 @@ RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps,
         }
         const V3 p = o + d * tt;
         if (!pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), n, p)) continue;
-        if (shortcut || (tt == T.t && i != T.hitTri)) return TRAV_DEFER; // depends on the reference's visiting order
+        const int pos = f2i(v2.w);
+        if (shortcut || (tt == T.t && pos != T.hitTri)) return TRAV_DEFER; // depends on the reference's visiting order
         if (tt >= T.t) {                                   // acceptable runner-up just behind the best (or the best itself again)
-            if (i != T.hitTri) K.t2 = fminf(K.t2, tt);
+            if (pos != T.hitTri) K.t2 = fminf(K.t2, tt);
             continue;
         }
         if (T.hitTri >= 0) K.t2 = fminf(K.t2, T.t);        // the old best becomes the runner-up
         T.t = tt;
-        T.hitTri = i;
+        T.hitTri = pos;
         if (ANY && !(tt + eps >= maxDist)) return TRAV_FIRED;
     }
     return fastPop(S, T, K, fastBound<ANY>(T, maxDist));

@@ -26,6 +26,20 @@ __global__ void k_setup_planes(const float4* __restrict__ v0, const float4* __re
     tri4[4 * (size_t)i + 3] = c;
 }
 
+// tri4f[k] = tri4[fastOrder[k]] with the position in tri4 in v2.w (fastOrder == nullptr: identity)
+__global__ void k_permute_tri4(const float4* __restrict__ tri4, const int* __restrict__ fastOrder, float4* __restrict__ tri4f, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int p = fastOrder ? fastOrder[k] : k;
+    float4 c = tri4[4 * (size_t)p + 3];
+    c.w = __int_as_float(p);
+    tri4f[4 * (size_t)k + 0] = tri4[4 * (size_t)p + 0];
+    tri4f[4 * (size_t)k + 1] = tri4[4 * (size_t)p + 1];
+    tri4f[4 * (size_t)k + 2] = tri4[4 * (size_t)p + 2];
+    tri4f[4 * (size_t)k + 3] = c;
+}
+
 // =================================================================================================================
 // Batch closest hit: one thread per ray.  BoundingVolumeHierarchy::intersect, src/bounding_volume_hierarchy.cpp:850-881
 // =================================================================================================================
@@ -1368,6 +1382,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
         const bool active = idx >= 0 && state == TRAV_CONTINUE;
         const bool isLeaf = (node & CGRT_TRI) != 0u;
         const float bound = (any ? fminf(t, maxDist) : t) * slack;
+        int pos = -1;                            // leaf: position of this lane's triangle
         float near = __int_as_float(0x7f800000); // leaf: distance of an acceptable triangle that does not beat the best
         bool p = false, amb = false;     // p: this lane's child box is hit / this lane's triangle is an acceptable candidate
         unsigned key = 0xffffffffu;      // ordering key of the lane's result (entry distance | child, or candidate distance)
@@ -1377,9 +1392,10 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
             if (isLeaf) {
                 // leaf: lane j tests triangle j with the reference's accept arithmetic (cgrt_device.cuh fastStepLeaf)
                 const int first = (int)(node & CGRT_IDX_MASK), count = (int)((node >> CGRT_TRICNT_SHIFT) & 7u) + 1;
-                if (j < count && first + j != hitTri) { // (own best candidate met again through the always-list: not a tie)
-                    const float4* tr = S.tri4 + 4 * (size_t)(first + j);
+                if (j < count) {
+                    const float4* tr = S.tri4f + 4 * (size_t)(first + j);
                     const float4 pl = __ldg(tr), v0 = __ldg(tr + 1), v1 = __ldg(tr + 2), v2 = __ldg(tr + 3);
+                    pos = f2i(v2.w); // position of the triangle in the reference-ordered arrays
                     const V3 nrm = mk3(pl);
                     const float on = dot3(o, nrm);
                     const bool shortcut = (on == pl.w);
@@ -1426,6 +1442,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
         mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 4));
         const unsigned winm = (__ballot_sync(0xffffffffu, p && key == mn) >> (8 * g)) & 0xFFu;
         const uint32_t nextId = __shfl_sync(0xffffffffu, id, 8 * g + (int)(mn & 7u));
+        const int winPos = __shfl_sync(0xffffffffu, pos, 8 * g + (winm ? __ffs(winm) - 1 : 0)); // leaf: position of the new best
         // leaf: smallest distance among the group's acceptable triangles that are not the new best (runner-up for the certificate)
         float ru = (isLeaf && p && key != mn) ? __uint_as_float(key) : near;
         ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 1));
@@ -1441,7 +1458,7 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
                     if (pm != 0u) {
                         if (hitTri >= 0) t2 = fminf(t2, t); // the old best becomes the runner-up
                         t = __uint_as_float(mn);
-                        hitTri = (int)(node & CGRT_IDX_MASK) + (__ffs(winm) - 1);
+                        hitTri = winPos;
                     }
                     if (any && pm != 0u && !(t + eps >= maxDist)) state = TRAV_FIRED;
                     else pop = true;
@@ -1855,6 +1872,11 @@ static inline int gridFor(size_t n, int block, int maxBlocks)
     if (g < 1) g = 1;
     if (g > (size_t)maxBlocks) g = maxBlocks;
     return (int)g;
+}
+
+void launchPermuteTri4(const float4* tri4, const int* fastOrder, float4* tri4f, int n, cudaStream_t st)
+{
+    if (n > 0) k_permute_tri4<<<(n + 255) / 256, 256, 0, st>>>(tri4, fastOrder, tri4f, n);
 }
 
 void launchSetupPlanes(const float4* v0, const float4* v1, const float4* v2, float4* pl, float4* tri4, int n, cudaStream_t st)

@@ -32,6 +32,8 @@ struct DevScene {
     const float4* triV2;
     const float4* tri4;   // 4 x float4 per triangle (64 B, one cache line half): [plane] [v0|gid] [v1|mesh] [v2|rank] - the
                           // traversal's copy of triPl/triV0/1/2, so that one triangle test touches one line instead of four
+    const float4* tri4f;  // the same records in the FAST TREE's triangle order, with [v2 | position in tri4] - read by the
+                          // speculative search only (identity order unless the fast tree is the independent SAH tree)
     const float4* triN0;
     const float4* triN1;
     const float4* triN2;
@@ -146,6 +148,7 @@ struct WaveTrace {
 };
 
 void launchSetupPlanes(const float4* v0, const float4* v1, const float4* v2, float4* pl, float4* tri4, int n, cudaStream_t st);
+void launchPermuteTri4(const float4* tri4, const int* fastOrder, float4* tri4f, int n, cudaStream_t st);
 void launchClosestBatch(const DevScene& S, const float4* rays, size_t n, float4* hits, uint32_t* counts, int numSMs,
                         cudaStream_t st);
 void launchAnyBatch(const DevScene& S, const float4* rays, const float* maxDist, float eps, size_t n, uint8_t* occluded,
