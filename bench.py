@@ -349,8 +349,11 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes_per_launch, "avg_launch_ms": dom_avg_s * 1e3,
                          "launches_timed": dom_launches,
-                         "note": "scene (~10 MB) is L2-resident: the HBM roofline is the contractual denominator, the practical "
-                                 "limiters are L1/L2 request rate, IEEE division throughput and divergence (see profiles/)"},
+                         "note": "algorithmic bytes = the box / triangle tests the REFERENCE traversal performs for these rays (counting "
+                                 "pass, SURVEY 8d); the speculative search performs far fewer and the scene (~20 MB) is L2-resident, so "
+                                 "frac can exceed 1 and DRAM traffic is ~50x lower: the HBM roofline is the contractual denominator, "
+                                 "the practical limiters are issued instructions per ray and the latency of dependent steps in "
+                                 "launch tails (profiles/)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             v, cores, rays, secs, kind = cpu_sample(d, d.lights, reps=2)

@@ -111,5 +111,8 @@ for part in ("trace", "rest"):
         lines.append("")
 open(os.path.join(P, f"{tag}_summary.md"), "w").write("\n".join(lines) + "\n")
 if traffic:
-    json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+    tp = os.path.join(P, "traffic.json")
+    old = json.load(open(tp)) if os.path.exists(tp) else {}
+    old.update(traffic)  # kernels not captured in this pass keep their previous entry (its `source` says which pass)
+    json.dump(old, open(tp, "w"), indent=1)
 print("\n".join(lines[:60]))
