@@ -646,116 +646,6 @@ RT_DEV void persistentTraverse(const DevScene& S, Policy& P, int n, int* workCou
     }
 }
 
-struct PrimaryPolicy {
-    const DevScene& S;
-    const FrameParams& P;
-    const WaveBuffers& B;
-    const int* tileList;
-    float* fb;
-    int outIdx; // per lane: output index of the item being traced
-    RT_DEV bool load(int slot, V3& o, V3& d, float& tIn, float& eps, float& maxDist)
-    {
-        int x, y;
-        outIdx = -1;
-        if (!slotToPixel(P, tileList, slot, x, y, outIdx)) {
-            outIdx = -1;
-            return false;
-        }
-        o = mk3(P.camX, P.camY, P.camZ);
-        d = primaryDirection(P, x, y);
-        tIn = FLT_MAX;
-        eps = 0.0f;
-        maxDist = 0.0f;
-        return true;
-    }
-    RT_DEV bool retire(bool fin, int slot, bool traced, bool hit, const TraceResult& R, const V3& ro, const V3& rd, V3&, V3&, float&)
-    {
-        if (fin) {
-            if (!traced) {
-                if (P.world > 1) storeRGB(fb, slot, mk3(0.0f, 0.0f, 0.0f)); // padding pixels of edge tiles
-            } else if (!hit) {
-                storeRGB(fb, outIdx, mk3(0.0f, 0.0f, 0.0f)); // trace(): miss -> black, src/main.cpp:288-294
-            }
-        }
-        pushHitRecord(S, B, 0, fin && traced && hit, R, ro, rd, outIdx, -1);
-        return false;
-    }
-};
-
-struct BouncePolicy {
-    const DevScene& S;
-    const WaveBuffers& B;
-    float* fb;
-    int level;
-    int pathId, outIdx;
-    RT_DEV bool load(int i, V3& o, V3& d, float& tIn, float& eps, float& maxDist)
-    {
-        const float4 r0 = B.bounceQ[2 * (size_t)i], r1 = B.bounceQ[2 * (size_t)i + 1];
-        o = mk3(r0);
-        d = mk3(r1);
-        tIn = r0.w;
-        pathId = f2i(r1.w);
-        outIdx = B.pathPix[pathId];
-        eps = 0.0f;
-        maxDist = 0.0f;
-        return true;
-    }
-    RT_DEV bool retire(bool fin, int, bool, bool hit, const TraceResult& R, const V3& ro, const V3& rd, V3&, V3&, float&)
-    {
-        if (fin && !hit) // reflected colour is black; unwind the levels above (src/main.cpp:288-294 then :263)
-            storeRGB(fb, outIdx, foldPath(B.pathState, B.cap, level, pathId, mk3(0.0f, 0.0f, 0.0f)));
-        pushHitRecord(S, B, level, fin && hit, R, ro, rd, outIdx, pathId);
-        return false;
-    }
-};
-
-struct ShadowPolicy {
-    const WaveBuffers& B;
-    const float4* lights;
-    int nL;
-    RT_DEV bool load(int i, V3& o, V3& d, float& tIn, float& eps, float& maxDist)
-    { // pointInShadow, src/main.cpp:104-135
-        const int h = i / nL, l = i - h * nL;
-        const float4 a = B.hitQ[3 * (size_t)h];
-        const V3 pointOn = mk3(a);
-        const V3 lightPos = mk3(__ldg(lights + 2 * l));
-        const V3 fromPosToLight = lightPos - pointOn;
-        d = normalize3(fromPosToLight);
-        eps = 0.001f;
-        o = pointOn + eps * d;
-        tIn = FLT_MAX;
-        maxDist = length3(fromPosToLight);
-        return true;
-    }
-    RT_DEV bool retire(bool fin, int i, bool, bool shadowed, const TraceResult&, const V3&, const V3&, V3&, V3&, float&)
-    {
-        if (fin) B.lit[i] = shadowed ? 0 : 1;
-        return false;
-    }
-};
-
-__global__ void __launch_bounds__(128) k_primary_p(DevScene S, const FrameParams* __restrict__ Pp, WaveBuffers B,
-                                                   const int* __restrict__ tileList, float* __restrict__ fb, int* work, Tuning U)
-{
-    const FrameParams P = *Pp;
-    PrimaryPolicy pol{S, P, B, tileList, fb, -1};
-    persistentTraverse<false>(S, pol, P.nSlots, work, U);
-}
-
-__global__ void __launch_bounds__(128) k_bounce_closest_p(DevScene S, WaveBuffers B, int level, float* __restrict__ fb, int* work, Tuning U)
-{
-    BouncePolicy pol{S, B, fb, level, -1, 0};
-    persistentTraverse<false>(S, pol, B.counts[CGRT_CNT_BOUNCE + level], work, U);
-}
-
-__global__ void __launch_bounds__(128) k_shadow_p(DevScene S, const FrameParams* __restrict__ Pp,
-                                                  const float4* __restrict__ lights, WaveBuffers B, int level, int* work, Tuning U)
-{
-    const int nL = Pp->nLights;
-    ShadowPolicy pol{B, lights, nL};
-    persistentTraverse<true>(S, pol, B.counts[CGRT_CNT_HIT + level] * nL, work, U);
-}
-
 // =================================================================================================================
 // Path pipeline (production): k_paths -> k_shadow_all -> k_shade_paths
 // =================================================================================================================
@@ -1936,7 +1826,9 @@ void launchGenerateRays(const FrameParams* dP, int nPixels, float4* rays, cudaSt
     if (nPixels) k_generate_rays<<<(nPixels + 127) / 128, 128, 0, st>>>(dP, rays);
 }
 
-// One frame of the wavefront. Every queue length lives in device memory (B.counts), so the sequence needs no host round trip:
+// One frame of the level-by-level COUNTING wavefront (CGRT_RENDER_COUNT: sequential leaf scans that count the reference's box /
+// triangle tests; the production frames go through launchRoundPipeline / launchPathPipeline below).
+// Every queue length lives in device memory (B.counts), so the sequence needs no host round trip:
 // the grids are sized for the worst case the host knows (nSlots) and the kernels loop over the device-side count.
 // `tr` (optional) records CUDA events around the kernels whose class is selected, for per-kernel device times.
 static inline void traceBegin(WaveTrace* tr, int cls, cudaStream_t st)
@@ -1967,9 +1859,7 @@ int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams&
     const int persistent = numSMs * 8; // persistent warps: 8 CTAs x 4 warps per SM (register-limited residency is 5-8 CTAs)
     const int gPrimary = gridFor((size_t)hP.nSlots, 128, 1 << 30);
     traceBegin(tr, 0, st);
-    int workSlot = CGRT_CNT_WORK;
-    if (countTests) k_primary<true><<<gPrimary, 128, 0, st>>>(S, dP, B, dTileList, fb);
-    else k_primary_p<<<min(gPrimary, persistent), 128, 0, st>>>(S, dP, B, dTileList, fb, B.counts + workSlot++, tuning());
+    k_primary<true><<<gPrimary, 128, 0, st>>>(S, dP, B, dTileList, fb);
     traceEnd(tr, 0, st);
     launches++;
     const int gHit = gridFor((size_t)hP.nSlots, 128, persistent);
@@ -1977,15 +1867,13 @@ int launchWavefront(const DevScene& S, const FrameParams* dP, const FrameParams&
     for (int level = 0; level < hP.traceLimit; level++) {
         if (level > 0) {
             traceBegin(tr, 1, st);
-            if (countTests) k_bounce_closest<true><<<gHit, 128, 0, st>>>(S, B, level, fb);
-            else k_bounce_closest_p<<<gHit, 128, 0, st>>>(S, B, level, fb, B.counts + workSlot++, tuning());
+            k_bounce_closest<true><<<gHit, 128, 0, st>>>(S, B, level, fb);
             traceEnd(tr, 1, st);
             launches++;
         }
         if (hP.nLights > 0) {
             traceBegin(tr, 2, st);
-            if (countTests) k_shadow<true><<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level);
-            else k_shadow_p<<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level, B.counts + workSlot++, tuning());
+            k_shadow<true><<<gShadow, 128, 0, st>>>(S, dP, dLights, B, level);
             traceEnd(tr, 2, st);
             launches++;
         }
