@@ -190,7 +190,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    ge.build()
+    if args.impl == "reference" and rank != 0:
+        return  # the CPU arm runs on rank 0 alone; the other ranks exit without work
+    # one builder per node: concurrent ranks must not run make / nvcc on the same outputs (the built files ship with the
+    # snapshot, so this is normally a no-op time-stamp check)
+    if local_rank == 0:
+        ge.build()
+    else:
+        t_wait = time.time()
+        while not os.path.exists(ge.LIB) and time.time() - t_wait < 600:
+            time.sleep(0.5)
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -220,3 +220,26 @@ def test_fast_tree_on_bundled_scenes(capi, golden):
     st = capi.Scene(golden.flat, host_only=True).fast_tree_stats()
     assert st["present"] == 1 and st["triangles_reached"] == golden.flat.n_triangles
     assert st["coverage_errors"] == 0 and st["containment_errors"] == 0 and st["chain_errors"] == 0
+
+
+@pytest.mark.parametrize("flavour", ["sah", "ref"])
+def test_fast_tree_flavours_are_structurally_sound(capi, golden, monkeypatch, flavour):
+    """both fast-tree flavours (independent binned-SAH tree / reference tree collapsed on the leaf sub-trees) cover every
+    triangle exactly once with boxes that contain their geometry; slivers and degenerate triangles included"""
+    monkeypatch.setenv("CGRT_FAST_TREE", flavour)
+    rng = np.random.default_rng(11)
+    flat = ob.random_soup(5000, seed=99, scale=0.05, n_meshes=3)
+    v = flat.vertices.copy()
+    t = flat.triangles
+    # make some triangles extreme slivers / degenerate (mesh-local indices: only touch mesh 0's first triangles)
+    for k in range(6):
+        a, b, c = t[k]
+        v[c, :3] = v[a, :3] + (v[b, :3] - v[a, :3]) * np.float32(0.5) + rng.normal(0, 1e-9, 3).astype(np.float32)
+    a, b, c = t[6]
+    v[b, :3] = v[a, :3]
+    flat2 = ob.FlatScene(flat.vcount, flat.tcount, v, t, flat.materials, flat.spheres)
+    for f in (flat, flat2, golden.flat):
+        st = capi.Scene(f, host_only=True).fast_tree_stats()
+        assert st["present"] == 1 and st["triangles_reached"] == f.n_triangles
+        assert st["coverage_errors"] == 0 and st["containment_errors"] == 0 and st["chain_errors"] == 0
+    assert capi.Scene(flat2, host_only=True).fast_tree_stats()["always_tested"] >= 1
