@@ -11,9 +11,11 @@ assigned by the harness so that bounces exist) — said in `data`.
 
 A step = one frame. `value` = logical rays of the frame (all ranks) / device time of the frame with the scene resident in HBM,
 timed with CUDA events per step, L2 flushed between steps, max over ranks. `e2e` = the same through the host-buffer API:
-camera + lights go host->device and the float framebuffer comes back to pinned host memory inside the timed region.
-With N > 1 the frame is partitioned into interleaved tiles (strong scaling); the timed region includes the NCCL gather to
-rank 0 and the de-interleave kernel.
+camera + lights go host->device and the float framebuffer comes back to pinned host memory inside the timed region
+(streaming form: two frames in flight; the synchronous number is reported in config.e2e_synchronous).
+With N > 1 the frame is partitioned into interleaved tiles (strong scaling); the timed region includes the exchange: every
+rank stores its pixels straight into rank 0's frame over NVLink peer memory and signals arrival with a flag
+(CGRT_EXCHANGE=nccl selects the NCCL gather + de-interleave kernel instead).
 """
 import argparse
 import json
