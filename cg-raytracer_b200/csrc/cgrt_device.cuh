@@ -110,7 +110,14 @@ RT_DEV bool leafCandidate(const DevScene& S, int i, const V3& o, const V3& d, Le
 #define CGRT_WIDE_STRIDE 16 // float4 per 8-wide node: 14 used, padded to 256 B = exactly two 128-byte lines
 
 // L1 prefetch hint: starts the fetch of a line the next step will read, without tying up a register
-RT_DEV void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+RT_DEV void prefetchL1(const void* p)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p; // (this header is also compiled for the host by tests/spec_harness.cpp)
+#endif
+}
 
 #define CGRT_RHO 1e-6f
 #define CGRT_TAU 1e-30f
