@@ -427,6 +427,9 @@ struct SahNode {
     int first, count; // leaves: range of the order array
 };
 
+#ifndef SAH_BINS
+#define SAH_BINS 16
+#endif
 struct SahBuilder {
     const std::vector<TriBox>& boxes; // per position
     std::vector<int32_t>& order;      // positions, permuted in place; leaves are contiguous ranges
@@ -461,7 +464,7 @@ struct SahBuilder {
         int mid = -1;
         if (N > leafMax) {
             // 16 bins per axis over the centroid bounds; cost of a split = A_L N_L + A_R N_R
-            const int NB = 16;
+            const int NB = SAH_BINS;
             double bestCost = 1e300;
             int bestAxis = -1, bestBin = -1;
             for (int axis = 0; axis < 3; axis++) {
@@ -530,21 +533,30 @@ static uint32_t buildFastTreeSah(const std::vector<TriBox>& boxes, std::vector<i
 {
     const uint32_t ID_TRI = 0x20000000u, ID_SUB = 0x40000000u;
     if (order.empty()) return 0u;
-    int leafMax = 6; // triangles per leaf (speed only; CGRT_SAH_LEAF overrides for tuning)
-    if (const char* e = getenv("CGRT_SAH_LEAF")) leafMax = std::max(1, std::min(8, atoi(e)));
-    SahBuilder sb{boxes, order, {}, leafMax};
+    // The binary SAH tree is built down to 2-triangle leaves; the 8-wide collapse decides the real leaf size: a slot whose
+    // subtree holds at most `leafCap` triangles becomes a triangle leaf, and while a node has free slots the largest slots keep
+    // being opened (also below leafCap): all 8 box tests of a step are paid anyway, fuller nodes mean fewer triangle tests.
+    int leafCap = 6; // triangles per leaf (speed only; CGRT_SAH_LEAF overrides for tuning)
+    if (const char* e = getenv("CGRT_SAH_LEAF")) leafCap = std::max(1, std::min(8, atoi(e)));
+    int binLeaf = leafCap; // default: binary leaves = wide leaves (the configuration measured on the GPU, profiles/r01_tuning.md);
+                           // CGRT_SAH_BINLEAF=2 gives 27 % fewer triangle tests for 17 % more leaf steps on the CPU proxy
+                           // (tests/tree_work.py) - to be measured on the GPU
+    if (const char* e = getenv("CGRT_SAH_BINLEAF")) binLeaf = std::max(1, std::min(8, atoi(e)));
+    int minOpen = 2; // slots with fewer triangles than this are not opened further
+    if (const char* e = getenv("CGRT_SAH_MINOPEN")) minOpen = std::max(2, atoi(e));
+    SahBuilder sb{boxes, order, {}, std::min(binLeaf, leafCap)};
     sb.nodes.reserve(order.size());
     const int root = sb.build(0, (int)order.size());
     std::function<uint32_t(int)> wide = [&](int bi) -> uint32_t {
         const SahNode& b = sb.nodes[bi];
-        if (b.left < 0) return ID_SUB | ID_TRI | ((uint32_t)(b.count - 1) << 26) | (uint32_t)b.first;
+        if (b.left < 0 || b.count <= leafCap) return ID_SUB | ID_TRI | ((uint32_t)(b.count - 1) << 26) | (uint32_t)b.first;
         std::vector<int> slots{b.left, b.right};
         while (slots.size() < 8) {
             int best = -1;
             double bestA = -1.0;
             for (size_t c = 0; c < slots.size(); c++) {
                 const SahNode& sn = sb.nodes[slots[c]];
-                if (sn.left < 0) continue;
+                if (sn.left < 0 || sn.count < minOpen) continue;
                 const double a = SahBuilder::area(sn.lo, sn.hi);
                 if (a > bestA) { bestA = a; best = (int)c; }
             }

@@ -119,6 +119,33 @@ void flatten(const cgrt_scene_desc* d, int maxDepth, bool sah, HostScene& H)
 
 extern "C" {
 
+// search work of the speculative traversal for a ray set (closest hit): totals of 8-wide node steps, leaf steps and triangle
+// tests - a CPU proxy for tuning the fast tree (builder flavour, leaf size) without a GPU. out[4] = wide, leaf, triangles, max steps
+int spec_work(const cgrt_scene_desc* d, int max_depth, int sah, const float* rays, int64_t n, int64_t* out)
+{
+    HostScene H;
+    flatten(d, max_depth > 0 ? max_depth : 12, sah != 0, H);
+    const DevScene& S = H.S;
+    int64_t nw = 0, nl = 0, ntri = 0, mx = 0;
+#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : nw, nl, ntri) reduction(max : mx)
+    for (int64_t i = 0; i < n; i++) {
+        const float* r = rays + 8 * i;
+        FastTrav T;
+        FastStack K;
+        int state = fastStart<false>(S, T, K, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], 0.0f, 0.0f);
+        int64_t steps = 0;
+        while (state == TRAV_CONTINUE) {
+            if (travIsLeaf(T.node)) { nl++; ntri += (int64_t)((T.node >> CGRT_TRICNT_SHIFT) & 7u) + 1; }
+            else nw++;
+            steps++;
+            state = fastStep<false>(S, T, K, 0.0f, 0.0f);
+        }
+        if (steps > mx) mx = steps;
+    }
+    out[0] = nw; out[1] = nl; out[2] = ntri; out[3] = mx;
+    return 0;
+}
+
 // rays: [n][8] = origin, t, direction, pad. mode 0: closest hit, mode 1: any hit (max_dist[n], eps).
 // out_exact / out_fast: [n][2] int32 = (global triangle id or -1 | shadowed flag, t bits | 0); certified[n] = 1 when the speculative
 // result carries a certificate (or is a certain miss). stats[8] = rays, certified, deferred, mismatches, first mismatch,
