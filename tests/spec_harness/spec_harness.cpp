@@ -26,8 +26,9 @@ using namespace cgrt;
 namespace {
 struct HostScene {
     BuiltBVH bvh;
-    std::vector<float4> nodes, triPl, v[3], n[3], tri4, tri4f, wide;
+    std::vector<float4> nodes, triPl, v[3], n[3], tri4, tri4f, wide, pairs;
     std::vector<int> parent, always;
+    int rootId = 0;
     DevScene S;
 };
 
@@ -95,6 +96,31 @@ void flatten(const cgrt_scene_desc* d, int maxDepth, bool sah, HostScene& H)
             out[12 + h] = make_float4(f[0], f[1], f[2], f[3]);
         }
     }
+    // the exact traversal's child-pair array (cgrt_capi.cu): both children of every inner reference node with their visit ids
+    {
+        const uint32_t ID_REFLEAF = 0x10000000u, ID_REFSCAN = 0x80000000u;
+        auto refId = [&](int cidx) -> uint32_t {
+            const HostNode& n = H.bvh.nodes[cidx];
+            if (!n.isLeaf) return (uint32_t)((n.child0 - 1) / 2);
+            const int wr = H.bvh.wideRoot[cidx];
+            if (wr >= 0) return ID_REFLEAF | (uint32_t)wr;
+            return ID_REFSCAN | (uint32_t)cidx;
+        };
+        const int nPairs = NN > 0 ? (int)(NN - 1) / 2 : 0;
+        H.pairs.assign((size_t)nPairs * 4, make_float4(0, 0, 0, 0));
+        for (size_t i = 0; i < NN; i++) {
+            const HostNode& n = H.bvh.nodes[i];
+            if (n.isLeaf) continue;
+            float4* out = H.pairs.data() + 4 * (size_t)((n.child0 - 1) / 2);
+            const HostNode &l = H.bvh.nodes[n.child0], &r = H.bvh.nodes[n.child1];
+            out[0] = make_float4(l.lo[0], l.lo[1], l.lo[2], __int_as_float((int)refId(n.child0)));
+            out[1] = make_float4(l.hi[0], l.hi[1], l.hi[2], __int_as_float(n.child0));
+            out[2] = make_float4(r.lo[0], r.lo[1], r.lo[2], __int_as_float((int)refId(n.child1)));
+            out[3] = make_float4(r.hi[0], r.hi[1], r.hi[2], __int_as_float(n.child1));
+        }
+        H.S.rootId = 0;
+        H.rootId = NN > 0 ? (int)refId(0) : 0;
+    }
     H.parent.assign(H.bvh.parent.begin(), H.bvh.parent.end());
     if (H.parent.empty()) H.parent.assign(NN ? NN : 1, -1);
     H.always.assign(H.bvh.alwaysTest.begin(), H.bvh.alwaysTest.end());
@@ -106,6 +132,8 @@ void flatten(const cgrt_scene_desc* d, int maxDepth, bool sah, HostScene& H)
     H.S.triV0 = H.v[0].data(); H.S.triV1 = H.v[1].data(); H.S.triV2 = H.v[2].data();
     H.S.triN0 = H.n[0].data(); H.S.triN1 = H.n[1].data(); H.S.triN2 = H.n[2].data();
     H.S.wide = H.wide.data();
+    H.S.pairs = H.pairs.data();
+    H.S.rootId = H.rootId;
     H.S.refParent = H.parent.data();
     H.S.alwaysTri = H.always.data();
     H.S.nAlways = H.bvh.fastRoot != 0u ? (int)H.always.size() : 0;
@@ -146,7 +174,8 @@ int spec_work(const cgrt_scene_desc* d, int max_depth, int sah, const float* ray
     return 0;
 }
 
-// rays: [n][8] = origin, t, direction, pad. mode 0: closest hit, mode 1: any hit (max_dist[n], eps).
+// rays: [n][8] = origin, t, direction, pad. mode 0: closest hit, mode 1: any hit (max_dist[n], eps); modes 2 / 3: the same
+// two queries through the EXACT replay traversal (traverseFast), which must equal the literal traversal for every ray.
 // out_exact / out_fast: [n][2] int32 = (global triangle id or -1 | shadowed flag, t bits | 0); certified[n] = 1 when the speculative
 // result carries a certificate (or is a certain miss). stats[8] = rays, certified, deferred, mismatches, first mismatch,
 // fast tree present, always-list size, wide nodes.
@@ -170,6 +199,30 @@ int spec_run(const cgrt_scene_desc* d, int max_depth, int sah, const float* rays
         bool defer = false, resF;
         FastTrav T;
         FastStack K;
+        if (mode == 2 || mode == 3) { // the exact replay traversal (filtered reference decisions + leaf sub-trees) vs the literal one
+            const float md = mode == 3 ? max_dist[i] : 0.0f;
+            TraceResult X;
+            const bool r = mode == 3 ? traverseFast<true>(S, o, dd, tIn, eps, md, X) : traverseFast<false>(S, o, dd, tIn, 0.0f, 0.0f, X);
+            if (mode == 2) {
+                auto gidOf = [&](int pos) { return pos >= 0 ? __float_as_int(H.v[0][pos].w) : -1; };
+                out_exact[2 * i] = hitE ? gidOf(E.tri) : -1;
+                out_exact[2 * i + 1] = __float_as_int(hitE ? E.t : tIn);
+                out_fast[2 * i] = r ? gidOf(X.tri) : -1;
+                out_fast[2 * i + 1] = __float_as_int(r ? X.t : tIn);
+            } else {
+                out_exact[2 * i] = (hitE && !(E.t + eps >= md)) ? 1 : 0;
+                out_fast[2 * i] = r ? 1 : 0;
+                out_exact[2 * i + 1] = out_fast[2 * i + 1] = 0;
+            }
+            if (out_exact[2 * i] != out_fast[2 * i] || out_exact[2 * i + 1] != out_fast[2 * i + 1]) {
+                nBad++;
+#pragma omp critical
+                if (firstBad < 0 || i < firstBad) firstBad = i;
+            }
+            certified[i] = 1;
+            nCert++;
+            continue;
+        }
         if (mode == 0) {
             int state = fastStart<false>(S, T, K, o, dd, tIn, 0.0f, 0.0f);
             while (state == TRAV_CONTINUE) state = fastStep<false>(S, T, K, 0.0f, 0.0f);

@@ -204,6 +204,21 @@ def test_certified_results_are_the_references(harness, kind, sah):
         assert sa["mismatch"] == 0, sa
 
 
+@pytest.mark.parametrize("kind", SCENES)
+def test_exact_replay_traversal_is_the_literal_one(harness, kind):
+    """the traversal that handles deferred rays (filtered reference box decisions, culling sub-trees in the reference leaves)
+    gives the literal reference-order traversal's result for EVERY ray, closest and any hit"""
+    flat, grid = scene(kind)
+    rays = ray_mix(flat, seed=40 + len(kind), n=90000, grid=grid)
+    ex, fa, _, st = run(harness, flat, rays, mode=2)
+    assert st["mismatch"] == 0, (st, rays[st["first"]], ex[st["first"]], fa[st["first"]])
+    far = rays.copy()
+    far["t"] = FLT_MAX
+    md = np.random.default_rng(9).uniform(0, 2, len(rays)).astype(np.float32)
+    _, _, _, sa = run(harness, flat, far, mode=3, max_dist=md)
+    assert sa["mismatch"] == 0, sa
+
+
 def test_harness_reference_order_traversal_is_the_oracles(harness):
     """ties the harness's ground truth (the product's traverseStrict compiled for the host) to the CPU oracle"""
     for kind in ("soup_meshes", "boxes", "cornell"):
