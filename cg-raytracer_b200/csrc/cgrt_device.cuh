@@ -551,7 +551,9 @@ RT_DEV int fastBegin(const DevScene& S, FastTrav& T, const V3& o, const V3& d, f
     const bool oky = (ay == 0.0f) || (ay >= 1e-20f && ay <= 1e20f);
     const bool okz = (az == 0.0f) || (az >= 1e-20f && az <= 1e20f);
     const bool fin = fabsf(o.x) <= 1e30f && fabsf(o.y) <= 1e30f && fabsf(o.z) <= 1e30f; // false for NaN
-    if (!(okx && oky && okz && fin) || S.fastRoot == 0u) return TRAV_DEFER;
+    // a negative or NaN ray bound is garbage the reference still has defined behaviour for (its in-plane shortcut accepts t = 0
+    // whatever ray.t is, and `t >= NaN` never rejects); the search prunes with the bound, so such rays take the exact traversal
+    if (!(okx && oky && okz && fin) || !(tIn >= 0.0f) || S.fastRoot == 0u) return TRAV_DEFER;
     T.inv.x = ax == 0.0f ? 1e30f : 1.0f / d.x;
     T.inv.y = ay == 0.0f ? 1e30f : 1.0f / d.y;
     T.inv.z = az == 0.0f ? 1e30f : 1.0f / d.z;

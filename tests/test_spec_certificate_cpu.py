@@ -231,3 +231,27 @@ def test_harness_reference_order_traversal_is_the_oracles(harness):
         assert np.array_equal(ids, g["tri"])
         hit = g["tri"] >= 0
         assert np.array_equal(ex[hit, 1], g["t"][hit].view(np.int32))
+
+
+@pytest.mark.parametrize("kind", ["boxes", "grid", "soup_meshes", "cornell"])
+def test_special_float_values(harness, kind):
+    """garbage in, reference behaviour out: NaN / inf / denormal / zero components in origins and directions, negative, NaN
+    and zero ray bounds. The reference has defined (if odd) behaviour for all of it - e.g. its in-plane shortcut accepts t = 0
+    whatever ray.t is - and both the certified speculative results and the exact replay traversal must reproduce it."""
+    rng = np.random.default_rng(7)
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-38, -1e-38, 1e38, -1e38, 1e-45, 3.4e38, 1.0, -1.0, 0.5], np.float32)
+    flat, _ = scene(kind)
+    n = 80000
+    rays = ob.random_rays(n, seed=5)
+    for field in ("o", "d"):
+        m = rng.random((n, 3)) < 0.25
+        rays[field] = np.where(m, special[rng.integers(0, len(special), (n, 3))], rays[field])
+    rays["t"] = np.where(rng.random(n) < 0.4, special[rng.integers(0, len(special), n)], rays["t"]).astype(np.float32)
+    md = special[rng.integers(0, len(special), n)].astype(np.float32)
+    for sah in (True, False):
+        for mode in (0, 2):
+            ex, fa, _, st = run(harness, flat, rays, mode=mode, sah=sah)
+            assert st["mismatch"] == 0, (mode, st, rays[st["first"]], ex[st["first"]], fa[st["first"]])
+        for mode in (1, 3):
+            _, _, _, st = run(harness, flat, rays, mode=mode, max_dist=md, sah=sah)
+            assert st["mismatch"] == 0, (mode, st)
