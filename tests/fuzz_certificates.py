@@ -50,3 +50,23 @@ for rnd in range(rounds):
             if sa["mismatch"]:
                 print("   ANY-HIT mismatch", sa, flush=True)
 print("TOTAL rays", tot, "mismatches", bad)
+
+# ---- BVH depths 1..33 on tiny / multi-mesh scenes, every traversal mode (0/1 speculative + certificate, 2/3 exact replay)
+tot2 = bad2 = 0
+cases = [("soup1", ob.random_soup(1, seed=1, scale=0.5)), ("soup2", ob.random_soup(2, seed=2, scale=0.5)),
+         ("soup9x3", ob.random_soup(9, seed=3, scale=0.4, n_meshes=3)), ("soup300x300", ob.random_soup(300, seed=4, scale=0.3, n_meshes=300)),
+         ("soup3000", ob.random_soup(3000, seed=5, scale=0.1)), ("boxes", T.box_walls()), ("grid", T.grid_planes(8)[0])]
+for name, flat in cases:
+    rays = T.ray_mix(flat, seed=11, n=60000)
+    far = rays.copy(); far["t"] = T.FLT_MAX
+    md = np.random.default_rng(3).uniform(0, 2, len(rays)).astype(np.float32)
+    for depth in (1, 2, 3, 12, 20, 33):
+        for sah in (True, False):
+            for mode in (0, 2):
+                st = T.run(lib, flat, rays, mode=mode, sah=sah, depth=depth)[3]
+                tot2 += st["rays"]; bad2 += st["mismatch"]
+            for mode in (1, 3):
+                st = T.run(lib, flat, far, mode=mode, max_dist=md, sah=sah, depth=depth)[3]
+                tot2 += st["rays"]; bad2 += st["mismatch"]
+    print("depth sweep", name, "mismatches so far", bad2, flush=True)
+print("DEPTH SWEEP rays", tot2, "mismatches", bad2)
