@@ -11,8 +11,11 @@ assigned by the harness so that bounces exist) — said in `data`.
 
 A step = one frame. `value` = logical rays of the frame (all ranks) / device time of the frame with the scene resident in HBM,
 timed with CUDA events per step, L2 flushed between steps, max over ranks. `e2e` = the same through the host-buffer API:
-camera + lights go host->device and the float framebuffer comes back to pinned host memory inside the timed region
-(streaming form: two frames in flight; the synchronous number is reported in config.e2e_synchronous).
+camera + lights go host->device and the float framebuffer comes back to pinned host memory inside the timed region, one
+synchronous call per frame (the kept renderRayTracing signature); `e2e_streaming` = the pipelined form, two frames in flight.
+The line also carries `parity` (the GPU frame against the CPU reference's frame of the same configuration, rendered in this
+run) and, for N > 1, `frame_equals_single_gpu`. The CPU legs read the scene from tests/golden/dragon_standin.npz and never
+load the product library; their thread count is set explicitly (torchrun exports OMP_NUM_THREADS=1).
 With N > 1 the frame is partitioned into interleaved tiles (strong scaling); the timed region includes the exchange: every
 rank stores its pixels straight into rank 0's frame over NVLink peer memory and signals arrival with a flag
 (CGRT_EXCHANGE=nccl selects the NCCL gather + de-interleave kernel instead).
@@ -35,7 +38,7 @@ import __graft_entry__ as ge  # noqa: E402
 
 METRIC = "Mrays/s (primary+shadow+bounce)"
 WIDTH, HEIGHT, TRACE_LIMIT = 1920, 1080, 5
-SAMPLE_W, SAMPLE_H = 960, 540  # CPU legs: the even pixels of the frame (x/960 == 2x/1920: identical NDC positions)
+CPU_BUDGET_S = 12.0  # cpu_baseline leg of our arm: the full frame is repeated until about this much CPU time has been spent
 B_RAY, B_BOX, B_TRI = 48, 32, 48  # algorithmic bytes: ray in + hit out, per box test, per triangle test
 
 
@@ -56,6 +59,9 @@ def assemble_on_host(capi, params, buffers):
 
 def gather_tiles(local, rank, world):
     return _distributed().gather_tiles(local, rank, world)
+
+
+DATA = "synthetic (procedural dragon stand-in; data/dragon.obj is not in the reference checkout)"
 
 
 def workload_name(n_tris):
@@ -115,9 +121,19 @@ class ClockSampler:
         return out
 
 
+def cpu_threads():
+    """Host threads the CPU legs use: every core this process may run on. Passed explicitly to the renderer, so that
+    torchrun's OMP_NUM_THREADS=1 (set for N > 1) does not turn the reference arm into a single-thread run."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_checker():
     """oracle/_ref (the reference's own compiled TUs) when present, else the restatement. Test infrastructure: this is the
-    only place besides tests/ and smoke() where bench.py touches oracle/."""
+    only place besides tests/ and smoke() where bench.py touches oracle/. Never loads the product library."""
+    ge.build_checkers()
     from oracle import bindings as ob
     try:
         return ob.RefLib(), "reference", ob
@@ -125,54 +141,60 @@ def cpu_checker():
         return ob.OracleLib(), "port", ob
 
 
-def cpu_sample(flat, lights, reps=1, budget_s=12.0):
-    """Time the reference CPU renderer on the bounded sample, repeated until ~budget_s seconds of CPU work (at least `reps`
-    times); returns (Mrays/s over all repetitions, threads, rays of all repetitions, seconds)."""
+def cpu_scene():
+    """The C3 stand-in on the CPU side: flat arrays from tests/golden/dragon_standin.npz (the product generator's output,
+    committed as a fixture), BVH by range-based fill of the reference's own Node structs (its constructor needs ~25 GB)."""
     lib, kind, ob = cpu_checker()
-    fs = ob.FlatScene(flat.vcount, flat.tcount, flat.vertices, flat.triangles, flat.materials, flat.spheres)
-    b = lib.scene(fs, lights).bvh(mode=1)  # range-based fill of the reference's Node structs (the constructor needs ~25 GB here)
-    cam = ob.default_camera(SAMPLE_W, SAMPLE_H)
-    b.render(cam, SAMPLE_W, SAMPLE_H, trace_limit=TRACE_LIMIT, duplicate_shading=True)  # warm-up (page faults, thread pool)
-    rays, total, n = 0, 0.0, 0
-    while n < reps or total < budget_s:
+    flat, lights = ob.dragon_standin_fixture()
+    b = lib.scene(flat, lights).bvh(mode=1)
+    return lib, kind, ob, flat, lights, b
+
+
+def cpu_frames(b, ob, steps, warmup, budget_s=None):
+    """Render the full WIDTH x HEIGHT frame on the host cores: `warmup` untimed frames, then `steps` timed ones (or, with
+    budget_s, as many as fit in that much wall time, at least one). Returns (Mrays/s, threads, rays, seconds, frames, last
+    frame, its counters)."""
+    nt = cpu_threads()
+    cam = ob.default_camera(WIDTH, HEIGHT)
+    for _ in range(warmup):
+        b.render(cam, WIDTH, HEIGHT, trace_limit=TRACE_LIMIT, duplicate_shading=True, nthreads=nt)
+    rays, total, n, rgb, cnt = 0, 0.0, 0, None, None
+    while (n < steps) if budget_s is None else (n < 1 or total < budget_s):
         t0 = time.perf_counter()
-        _, cnt = b.render(cam, SAMPLE_W, SAMPLE_H, trace_limit=TRACE_LIMIT, duplicate_shading=True)
+        rgb, cnt = b.render(cam, WIDTH, HEIGHT, trace_limit=TRACE_LIMIT, duplicate_shading=True, nthreads=nt)
         total += time.perf_counter() - t0
         rays += cnt["primary"] + cnt["shadow"] + cnt["bounce"]
         n += 1
-    return rays / total / 1e6, lib.max_threads(), rays, total, kind
+    return rays / total / 1e6, nt, rays, total, n, rgb, cnt
 
 
-def sample_text():
-    return (f"the {SAMPLE_W}x{SAMPLE_H} even-pixel sub-grid (1/4 of the pixels, identical NDC positions) of the same frame, "
-            f"reference code path incl. its duplicated shading() call (main.cpp:284), rays counted once, OpenMP static rows; "
-            f"cpu_baseline repeats the sample for ~12 s of wall time")
+def sample_text(frames):
+    return (f"{frames} full {WIDTH}x{HEIGHT} frame(s) of the same scene, camera, lights and trace limit through the reference's own "
+            f"code path incl. its duplicated shading() call (main.cpp:284), rays counted once, OpenMP static rows, "
+            f"{cpu_threads()} threads set explicitly")
 
 
-def run_reference(args, rank):
-    if rank != 0:
-        return
-    capi = ge.load_package().capi
-    d = capi.dragon_standin()
-    lib, kind, ob = cpu_checker()
-    fs = ob.FlatScene(d.vcount, d.tcount, d.vertices, d.triangles, d.materials, d.spheres)
-    b = lib.scene(fs, d.lights).bvh(mode=1)
-    cam = ob.default_camera(SAMPLE_W, SAMPLE_H)
-    rays = 0
-    for _ in range(args.warmup):
-        b.render(cam, SAMPLE_W, SAMPLE_H, trace_limit=TRACE_LIMIT, duplicate_shading=True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        _, cnt = b.render(cam, SAMPLE_W, SAMPLE_H, trace_limit=TRACE_LIMIT, duplicate_shading=True)
-        rays += cnt["primary"] + cnt["shadow"] + cnt["bounce"]
-    dt = time.perf_counter() - t0
-    v = rays / dt / 1e6
+def frame_parity(rgb, counters, ref_rgb, ref_cnt):
+    """GPU frame vs the CPU reference's frame of the same configuration (bench line `parity`)."""
+    a = np.ascontiguousarray(rgb, np.float32).reshape(HEIGHT, WIDTH, 3)
+    b = np.ascontiguousarray(ref_rgb, np.float32).reshape(HEIGHT, WIDTH, 3)
+    keys = ("primary", "shadow", "bounce")
+    return {"against": "CPU reference frame rendered in this run (cpu_baseline leg), full frame",
+            "counters_equal": bool(all(int(counters[k]) == int(ref_cnt[k]) for k in keys)),
+            "max_abs": float(np.abs(a - b).max()),
+            "bit_equal_frac": float((a.view(np.uint32) == b.view(np.uint32)).all(axis=2).mean()),
+            "tolerance": "max_abs <= 1/255, bit_equal_frac >= 0.999 (pow() in the specular term is the only inexact op)"}
+
+
+def run_reference(args):
+    lib, kind, ob, flat, lights, b = cpu_scene()
+    v, nt, rays, dt, n, _, _ = cpu_frames(b, ob, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (procedural dragon stand-in; data/dragon.obj is not in the reference checkout)",
-        "config": {"workload": workload_name(d.n_triangles), "cpu_sample": sample_text()},
-        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": lib.max_threads(), "kind": kind, "sample": sample_text()},
+        "warmup": args.warmup, "ms_per_step": dt / max(n, 1) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": DATA,
+        "config": {"workload": workload_name(flat.n_triangles)},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": nt, "kind": kind, "sample": sample_text(n)},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -192,19 +214,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference" and rank != 0:
-        return  # the CPU arm runs on rank 0 alone; the other ranks exit without work
-    # one builder per node: concurrent ranks must not run make / nvcc on the same outputs (the built files ship with the
-    # snapshot, so this is normally a no-op time-stamp check)
-    if local_rank == 0:
-        ge.build()
-    else:
-        t_wait = time.time()
-        while not os.path.exists(ge.LIB) and time.time() - t_wait < 600:
-            time.sleep(0.5)
     if args.impl == "reference":
-        run_reference(args, rank)
+        if rank == 0:  # the CPU arm runs on rank 0 alone; the other ranks exit without work. The product library is not loaded.
+            run_reference(args)
         return
+    ge.build()  # every rank: serialised by a file lock, a no-op time-stamp check when the built files shipped with the snapshot
 
     import torch
     import torch.distributed as dist
@@ -285,7 +299,7 @@ def main():
     # ---- end to end: host-buffer API, per-frame H2D of camera + lights, D2H of the float frame to pinned memory.
     # One GPU: the streaming form (cgrt_render_submit / cgrt_render_wait, two frames in flight: the copy of frame k overlaps
     # the kernels of frame k+1; all K frames are delivered before the clock stops). The synchronous call (cgrt_render, one
-    # frame at a time) is timed next to it and reported in config.e2e_synchronous. N > 1: synchronous frames on rank 0.
+    # frame at a time) is the line's `e2e`; the streaming number is `e2e_streaming`. N > 1: synchronous frames on rank 0.
     streaming = world == 1 or R.mode == "p2p"
     e2e_mode = "streaming (cgrt_render_submit x K + cgrt_render_wait, 2 frames in flight)" if world == 1 else \
                ("streaming (two frames on rank 0, copy-out of frame k on a second stream while frame k+1 renders)" if streaming
@@ -316,6 +330,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s, e2e_sync_s = [float(x) for x in t.tolist()]
     e2e_value = rays_frame * args.steps / e2e_s / 1e6
+    e2e_sync_value = rays_frame * args.steps / e2e_sync_s / 1e6
+    timeouts = max(timeouts, R.timeouts())
+
+    # ---- untimed checks carried in the line: (i) N > 1: the frame the timed mode delivers on rank 0 == the frame rank 0 renders
+    # alone on one GPU, bit for bit; (ii) the frame against the CPU reference's frame of the same configuration
+    gpu_frame = R.render_to_host(cam)
+    gpu_frame = gpu_frame.copy() if rank == 0 else None
+    frame_equals_single = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            single, _ = scene.render(cam, WIDTH, HEIGHT, trace_limit=TRACE_LIMIT)
+            frame_equals_single = bool(np.array_equal(single.view(np.uint32), gpu_frame.view(np.uint32)))
+        barrier()
     h2d = 128 + 32 * len(d.lights)  # FrameParams block + lights (cgrt_capi.cu: CGRT_PARAM_BLOCK_HEADER + 2 float4 per light)
     d2h = WIDTH * HEIGHT * 12
 
@@ -346,15 +374,19 @@ def main():
                        "exchange": {"single": "none", "p2p": "direct stores into rank 0's frame over NVLink peer memory + arrival/consumed flags",
                                     "nccl": "NCCL gather of tile-major buffers + assemble kernel"}[R.mode],
                        "exchange_fallback_reason": R.fallback_reason, "handoff_timeouts": timeouts, "e2e_mode": e2e_mode, "e2e_streamed_frame_equals_synchronous_frame": e2e_frames_equal,
-                       "e2e_synchronous": {"value": rays_frame * args.steps / e2e_sync_s / 1e6, "ms_per_step": e2e_sync_s / args.steps * 1e3},
+                       "frame_equals_single_gpu": frame_equals_single,
                        "rays_per_frame": {"primary": n_primary, "shadow": n_shadow, "bounce": n_bounce},
                        "kernel_ms_per_frame_rank0": dict(zip(names, [round(v, 4) for v in st_prof["class_ms"]])),
                        "kernel_launches_per_frame": dict(zip(names, st_prof["class_launches"])),
                        "frame_roofline": {"algorithmic_bytes_per_frame": alg_bytes_frame, "bytes_per_ray": alg_bytes_frame / rays_frame,
                                           "achieved_GBps": alg_bytes_frame * args.steps / (total_ms * 1e-3) / 1e9,
                                           "frac_of_hbm_peak": alg_bytes_frame * args.steps / (total_ms * 1e-3) / 1e9 / (peak * world)}},
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s / args.steps * 1e3},
+            # e2e = the kept synchronous call (one cgrt_render per frame: what the renderRayTracing shim of INTEGRATION.md makes);
+            # e2e_streaming = the pipelined form (two frames in flight) next to it
+            "e2e": {"value": e2e_sync_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_sync_s / args.steps * 1e3, "mode": "synchronous: render, exchange, D2H to pinned host memory, stream sync per frame"},
+            "e2e_streaming": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_s / args.steps * 1e3, "mode": e2e_mode},
+            "frame_equals_single_gpu": frame_equals_single,
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -367,13 +399,21 @@ def main():
                                  "the practical limiters are issued instructions per ray and the latency of dependent steps in "
                                  "launch tails (profiles/)"},
         }
+        if timeouts:
+            line["invalid"] = f"{timeouts} exchange hand-off wait(s) timed out: frames may be incomplete"
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, rays, secs, kind = cpu_sample(d, d.lights, reps=2)
-            line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample_text(),
+            lib, kind, ob, cflat, clights, b = cpu_scene()
+            fixture_ok = bool(np.array_equal(cflat.vertices.view(np.uint32), np.ascontiguousarray(d.vertices, np.float32).reshape(-1, 6).view(np.uint32))
+                              and np.array_equal(cflat.triangles, np.ascontiguousarray(d.triangles, np.uint32).reshape(-1, 3)))
+            v, cores, rays, secs, n, ref_rgb, ref_cnt = cpu_frames(b, ob, 0, 1, budget_s=CPU_BUDGET_S)
+            line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample_text(n),
                                     "sample_rays": rays, "sample_seconds": secs}
+            line["parity"] = frame_parity(gpu_frame, {"primary": n_primary, "shadow": n_shadow, "bounce": n_bounce}, ref_rgb, ref_cnt)
+            line["parity"]["cpu_scene_equals_gpu_scene"] = fixture_ok
         print(json.dumps(line))
     if world > 1:
         dist.barrier(device_ids=[local_rank])
+        R.close()
         dist.destroy_process_group()
 
 

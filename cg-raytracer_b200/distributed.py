@@ -103,17 +103,12 @@ class TiledRenderer:
         self.seq = 0
         self.mode = "single" if world == 1 else (mode or "p2p")
         self.fallback_reason = None
+        self._owned, self._mapped, self._pinned = [], [], []
         if self.mode == "p2p":
-            try:
-                self._init_p2p()
-            except Exception as e:  # no peer mapping between these processes: the NCCL gather is the other GPU path
-                self.fallback_reason = f"{type(e).__name__}: {e}"
-                self.mode = "nccl"
-            # all ranks must agree on the mode
-            import torch.distributed as dist
-            ok = torch.tensor([1 if self.mode == "p2p" else 0], dtype=torch.int32, device=self.dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
+            # _init_p2p runs the same collective sequence on every rank whatever fails locally and agrees on the outcome
+            self.fallback_reason = self._init_p2p()
+            if self.fallback_reason is not None:  # no peer mapping between these processes: the NCCL gather is the other GPU path
+                self._release()
                 self.mode = "nccl"
         if self.mode != "p2p":
             n = _capi.tile_buffer_floats(self.params)
@@ -125,6 +120,7 @@ class TiledRenderer:
     def _malloc(self, nbytes):
         p = C.c_void_p()
         _capi.check(self.lib.cgrt_device_malloc(self.device, nbytes, C.byref(p)))
+        self._owned.append(p)
         _capi.check(self.lib.cgrt_memset_device(self.device, p, 0, nbytes, None))
         return p
 
@@ -137,36 +133,95 @@ class TiledRenderer:
         h = (C.c_uint8 * _capi.IPC_HANDLE_BYTES).from_buffer_copy(handle)
         p = C.c_void_p()
         _capi.check(self.lib.cgrt_peer_open(self.device, h, C.byref(p)))
+        self._mapped.append(p)
         return p
 
+    def _agree(self, err):
+        """One all_reduce after each phase of the set-up: every rank learns whether ANY rank failed, so all of them take the
+        same branch and issue the same collectives (a rank that failed locally still takes part)."""
+        import torch.distributed as dist
+        ok = self.torch.tensor([0 if err else 1], dtype=self.torch.int32, device=self.dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return int(ok.item()) == 1
+
     def _init_p2p(self):
+        """Returns None when every rank has its peer mappings, else the reason for the fallback (the same decision on every rank)."""
         torch = self.torch
         import torch.distributed as dist
         nfl = self.H * self.W * 3
         HB = _capi.IPC_HANDLE_BYTES
-        self.consumed = self._malloc(256)  # [0] consumed sequence number of this rank, [64] wait-timeout counter
-        self.status = C.c_void_p(self.consumed.value + 64)  # same allocation, 64 bytes in
-        mine = [self._export(self.consumed), bytes(HB), bytes(HB), bytes(HB)]
-        if self.rank == 0:
-            # two frames: frame k lives in buffer k & 1, so that the copy-out of frame k can overlap the rendering of k + 1
-            self.frame_ptrs = [self._malloc(nfl * 4), self._malloc(nfl * 4)]
-            self.arrive = self._malloc(4 * max(self.world, 64))
-            mine[1], mine[2], mine[3] = self._export(self.frame_ptrs[0]), self._export(self.arrive), self._export(self.frame_ptrs[1])
-        _capi.check(self.lib.cgrt_device_synchronize(self.device))
+        err = None
+        mine = [bytes(HB)] * 4
+        # phase 1 (local): allocate + export
+        try:
+            self.consumed = self._malloc(256)  # [0] consumed sequence number of this rank
+            # wait-timeout counter: pinned host memory the wait kernel writes through its device alias, so that checking it after
+            # a stream synchronisation is a plain host read (no copy in the timed region)
+            st = C.c_void_p()
+            _capi.check(self.lib.cgrt_host_alloc_pinned(64, C.byref(st)))
+            self._pinned.append(st)
+            C.memset(st, 0, 64)
+            self.status = st
+            mine[0] = self._export(self.consumed)
+            if self.rank == 0:
+                # two frames: frame k lives in buffer k & 1, so that the copy-out of frame k can overlap the rendering of k + 1
+                self.frame_ptrs = [self._malloc(nfl * 4), self._malloc(nfl * 4)]
+                self.arrive = self._malloc(4 * max(self.world, 64))
+                mine[1], mine[2], mine[3] = self._export(self.frame_ptrs[0]), self._export(self.arrive), self._export(self.frame_ptrs[1])
+            _capi.check(self.lib.cgrt_device_synchronize(self.device))
+        except Exception as e:
+            err = f"{type(e).__name__}: {e}"
+        if not self._agree(err):
+            return err or "a peer rank could not allocate / export its buffers"
+        # phase 2 (collective): exchange the handles
         t = torch.tensor(list(b"".join(mine)), dtype=torch.uint8, device=self.dev)
         allh = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(allh, t)
         allh = [bytes(x.cpu().tolist()) for x in allh]
-        if self.rank == 0:
-            self.peer_consumed = [None] + [self._open(allh[r][0:HB]) for r in range(1, self.world)]
-            self.frames = [torch.as_tensor(_DevicePtr(q.value, nfl), device=self.dev) for q in self.frame_ptrs]
-            self.out_ptrs = self.frame_ptrs
-        else:
-            self.frames = [None, None]
-            self.out_ptrs = [self._open(allh[0][HB:2 * HB]), self._open(allh[0][3 * HB:4 * HB])]
-            self.peer_arrive = self._open(allh[0][2 * HB:3 * HB])
+        # phase 3 (local): map the peers' buffers
+        try:
+            if self.rank == 0:
+                self.peer_consumed = [None] + [self._open(allh[r][0:HB]) for r in range(1, self.world)]
+                self.frames = [torch.as_tensor(_DevicePtr(q.value, nfl), device=self.dev) for q in self.frame_ptrs]
+                self.out_ptrs = self.frame_ptrs
+            else:
+                self.frames = [None, None]
+                self.out_ptrs = [self._open(allh[0][HB:2 * HB]), self._open(allh[0][3 * HB:4 * HB])]
+                self.peer_arrive = self._open(allh[0][2 * HB:3 * HB])
+        except Exception as e:
+            err = f"{type(e).__name__}: {e}"
+        if not self._agree(err):
+            return err or "a peer rank could not map the exported buffers"
         self._copy_done = [None, None]  # rank 0, streaming: event after the copy-out of the frame that last used the buffer
         dist.barrier(device_ids=[self.device])
+        return None
+
+    def _release(self):
+        """Unmap peer buffers, free this rank's device allocations and pinned blocks (idempotent)."""
+        try:
+            self.lib.cgrt_device_synchronize(self.device)
+        except Exception:
+            pass
+        for q in self._mapped:
+            self.lib.cgrt_peer_close(self.device, q)
+        for q in self._owned:
+            self.lib.cgrt_device_free(self.device, q)
+        for q in self._pinned:
+            self.lib.cgrt_host_free_pinned(q)
+        self._mapped, self._owned, self._pinned = [], [], []
+
+    def close(self):
+        """Collective-free teardown; call it on every rank after the last frame (peers must have stopped writing: barrier first)."""
+        self.frames = [None, None]
+        self.frame = None
+        self._release()
+
+    def _check_handoff(self):
+        """After a stream synchronisation: a hand-off wait that gave up means a frame with missing peer tiles (or a buffer
+        overwritten while it was being copied out) - an error, not a statistic."""
+        n = self.timeouts()
+        if n:
+            raise RuntimeError(f"rank {self.rank}: {n} exchange hand-off wait(s) timed out after {self.TIMEOUT_MS} ms; the frame is not trustworthy")
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.dev).cuda_stream
@@ -199,12 +254,11 @@ class TiledRenderer:
         return None
 
     def timeouts(self):
-        """Number of hand-off waits that gave up (0 in a healthy run); synchronises the device."""
+        """Number of hand-off waits that gave up so far (0 in a healthy run). A host read of the pinned counter: meaningful
+        after the stream has been synchronised."""
         if self.mode != "p2p":
             return 0
-        v = C.c_uint32(0)
-        _capi.check(self.lib.cgrt_memcpy_d2h(self.device, C.byref(v), self.status, 4))
-        return int(v.value)
+        return int(C.cast(self.status, C.POINTER(C.c_uint32))[0])
 
     def render_device(self, cam, flags=0):
         """Enqueue one frame on the current torch stream; returns the device frame tensor on rank 0 (None elsewhere).
@@ -289,6 +343,8 @@ class TiledRenderer:
         main.synchronize()
         if self.rank == 0:
             self._copy_stream.synchronize()
+        self._check_handoff()
+        if self.rank == 0:
             return last.numpy().reshape(self.H, self.W, 3)
         return None
 
@@ -309,4 +365,6 @@ class TiledRenderer:
                 self.host_frame = torch.empty(self.H * self.W * 3, dtype=torch.float32).pin_memory()
             self.host_frame.copy_(frame, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
+        if self.mode == "p2p":
+            self._check_handoff()
         return self.host_frame.numpy().reshape(self.H, self.W, 3) if self.rank == 0 else None

@@ -336,3 +336,10 @@ def random_rays(n, seed=5678, tmax=None):
     d = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
     d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
     return make_rays(o, d.astype(np.float32), tmax)
+
+
+def dragon_standin_fixture():
+    """(FlatScene, lights) of the C3 stand-in scene from tests/golden/dragon_standin.npz (written by
+    tests/golden/make_dragon_fixture.py from the product's host generator): lets the CPU arms run without the product library."""
+    z = np.load(os.path.join(os.path.dirname(HERE), "tests", "golden", "dragon_standin.npz"))
+    return FlatScene(z["vcount"], z["tcount"], z["vertices"], z["triangles"], z["materials"], z["spheres"]), z["lights"]

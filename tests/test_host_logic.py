@@ -184,6 +184,11 @@ def test_dragon_standin(capi):
     assert same_bits(again.vertices, d.vertices)  # deterministic
     s = capi.Scene(d, host_only=True)
     assert s.num_levels() == 12 and s.num_nodes() == 4095  # as the report quotes for the dragon (12 levels)
+    # the committed copy the CPU legs of bench.py and the full-size parity tests read (tests/golden/make_dragon_fixture.py)
+    flat, lights = ob.dragon_standin_fixture()
+    assert same_bits(flat.vertices, d.vertices) and np.array_equal(flat.triangles, d.triangles)
+    assert same_bits(flat.materials, d.materials) and same_bits(lights, d.lights)
+    assert np.array_equal(flat.vcount, d.vcount) and np.array_equal(flat.tcount, d.tcount)
 
 
 def test_bmp_writer(capi, tmp_path):

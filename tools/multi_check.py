@@ -55,6 +55,7 @@ def main():
             else:
                 R.timeouts()
             dist.barrier(device_ids=[local])
+            R.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier(device_ids=[local])
