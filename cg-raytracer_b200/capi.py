@@ -56,14 +56,15 @@ class RenderStats(C.Structure):
     _fields_ = [("primary", C.c_uint64), ("primary_hit", C.c_uint64), ("shadow", C.c_uint64), ("bounce", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("box_tests", C.c_uint64 * 3), ("tri_tests", C.c_uint64 * 3),
                 ("device_ms", C.c_float), ("class_ms", C.c_float * 4), ("class_launches", C.c_uint32 * 4),
-                ("replayed_closest", C.c_uint32), ("replayed_shadow", C.c_uint32), ("reserved", C.c_float * 1)]
+                ("replayed_closest", C.c_uint32), ("replayed_shadow", C.c_uint32), ("pipeline", C.c_uint32)]
 
     def as_dict(self):
         return dict(primary=int(self.primary), primary_hit=int(self.primary_hit), shadow=int(self.shadow),
                     bounce=int(self.bounce), kernel_launches=int(self.kernel_launches), device_ms=float(self.device_ms),
                     box_tests=[int(v) for v in self.box_tests], tri_tests=[int(v) for v in self.tri_tests],
                     class_ms=[float(v) for v in self.class_ms], class_launches=[int(v) for v in self.class_launches],
-                    replayed_closest=int(self.replayed_closest), replayed_shadow=int(self.replayed_shadow))
+                    replayed_closest=int(self.replayed_closest), replayed_shadow=int(self.replayed_shadow),
+                    pipeline=int(self.pipeline))
 
 
 EXPORTS = [
@@ -189,12 +190,14 @@ def make_camera(W, H, fovy_deg=50.0, dist=3.0, look_at=(0.0, 0.0, 0.0), euler_de
 K_PRIMARY, K_BOUNCE, K_SHADOW, K_SHADE = 0, 1, 2, 3
 # production (path pipeline) kernels per class; class 1 is only launched by the level-by-level counting pipeline
 KERNEL_CLASS_NAMES = ["k_paths", "k_bounce_closest", "k_shadow_all", "k_shade_paths"]  # path pipeline (exact-only scenes)
-ROUND_CLASS_NAMES = ["k_gen", "k_finish", "k_trace", "k_shade_slots"]                   # round pipeline (production)
+ROUND_CLASS_NAMES = ["k_gen", "k_finish", "k_trace", "k_shade_slots"]                   # round pipeline (CGRT_PIPELINE=rounds)
+WAVE_CLASS_NAMES = ["-", "-", "k_wave", "-"]                                             # persistent wavefront (production)
+COUNT_CLASS_NAMES = ["k_primary", "k_bounce_closest", "k_shadow", "k_shade"]             # counting wavefront (CGRT_RENDER_COUNT)
 
 
 def class_names(stats):
     """Kernel names behind cgrt_render_stats.class_ms / class_launches for the pipeline that produced `stats`."""
-    return ROUND_CLASS_NAMES if stats["class_launches"][1] > 0 and stats["box_tests"] == [0, 0, 0] else KERNEL_CLASS_NAMES
+    return [COUNT_CLASS_NAMES, KERNEL_CLASS_NAMES, ROUND_CLASS_NAMES, WAVE_CLASS_NAMES][stats["pipeline"]]
 RENDER_PROFILE_ALL, RENDER_COUNT, RENDER_SCREEN_LAYOUT = 0xF, 0x100, 0x200
 IPC_HANDLE_BYTES = 64
 

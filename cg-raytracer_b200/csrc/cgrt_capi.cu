@@ -259,6 +259,9 @@ struct cgrt_scene {
     DevBuf<int> hitList, pathDepth, replayShadow;
     DevBuf<float4> replayQ;
     DevBuf<float4> cRay[2], cRes[2], sRay[2], sRes[2];
+    DevBuf<float4> waveRays, waveFin; // persistent wavefront: ticket-indexed ray records / finished-search records
+    DevBuf<int> waveCtl;
+    uint32_t waveSeq = 0;
     int lastPipeline = 0; // 0 counting wavefront, 1 path pipeline, 2 round pipeline
     int lastChains = 1;
     // streaming form (cgrt_render_submit / cgrt_render_wait)
@@ -312,6 +315,7 @@ static void destroyScene(cgrt_scene* s)
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->tileSeq.release(); s->frame.release();
     s->tests.release(); s->hitRec.release(); s->hitList.release(); s->pathDepth.release(); s->replayShadow.release(); s->replayQ.release();
     for (int k = 0; k < 2; k++) { s->cRay[k].release(); s->cRes[k].release(); s->sRay[k].release(); s->sRes[k].release(); }
+    s->waveRays.release(); s->waveFin.release(); s->waveCtl.release();
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->hParamRing) cudaFreeHost(s->hParamRing);
     if (s->hFramePinned) cudaFreeHost(s->hFramePinned);
@@ -955,6 +959,60 @@ static bool useRounds(const cgrt_scene* s, const FrameParams& P)
     return flags < ((uint64_t)1 << 30);
 }
 
+// the persistent wavefront (one kernel per frame) is the production pipeline wherever the round pipeline applies;
+// CGRT_PIPELINE=rounds selects the round pipeline (one kernel per level and chain) for A/B runs
+static bool useWave(const cgrt_scene* s, const FrameParams& P)
+{
+    static int pref = -1;
+    if (pref < 0) {
+        const char* e = getenv("CGRT_PIPELINE");
+        pref = (e && std::strcmp(e, "rounds") == 0) ? 0 : 1;
+    }
+    return pref == 1 && useRounds(s, P) && P.nSlots < (1 << 26) && P.traceLimit <= 16; // ray record: level << 26 | slot
+}
+// tickets the queue must hold: every slot can cast one closest-hit ray and one shadow ray per light at every level; plus the
+// tickets idle lanes hold beyond the last ray (one per resident lane at most)
+static size_t waveTicketCap(const FrameParams& P)
+{
+    return (size_t)std::max(P.nSlots, 1) * std::max(P.traceLimit, 1) * (1 + (size_t)std::max(P.nLights, 0)) + ((size_t)1 << 19);
+}
+
+// scheduling knobs / watchdog of the persistent wavefront (CGRT_WAVE="mode=0,group_below=600000,switch=100000,fin=5,timeout_ms=4000"; they
+// change speed only, never results). mode 0: the search form follows the size of this rank's share of the frame - one lane per
+// ray for large shares (throughput), eight lanes per ray for small ones (latency)
+static void waveTuning(WaveQ& Q, int nSlots)
+{
+    static int mode = 0, groupBelow = 600000, fin = 5, timeoutMs = 4000, switchBelow = 100000;
+    static bool loaded = false;
+    if (!loaded) {
+        loaded = true;
+        if (const char* e = getenv("CGRT_WAVE")) {
+            std::string t(e);
+            size_t pos = 0;
+            while (pos < t.size()) {
+                size_t c = t.find(',', pos);
+                if (c == std::string::npos) c = t.size();
+                const std::string kv = t.substr(pos, c - pos);
+                const size_t eq = kv.find('=');
+                if (eq != std::string::npos) {
+                    const std::string key = kv.substr(0, eq);
+                    const int v = atoi(kv.c_str() + eq + 1);
+                    if (key == "mode") mode = v;
+                    else if (key == "group_below") groupBelow = v;
+                    else if (key == "fin") fin = v;
+                    else if (key == "switch") switchBelow = v;
+                    else if (key == "timeout_ms") timeoutMs = v;
+                }
+                pos = c + 1;
+            }
+        }
+    }
+    Q.mode = mode == 1 || mode == 2 ? mode : (nSlots < groupBelow ? 2 : 1);
+    Q.finEvery = std::max(fin, 2);
+    Q.switchBelow = Q.mode == 2 ? 0 : std::max(switchBelow, 0); // (GROUP-only frames never change over)
+    Q.timeoutNs = (unsigned long long)std::max(timeoutMs, 1) * 1000000ull;
+}
+
 static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, FrameParams& P,
                         const int** dTileList, const int2** dTileSeq)
 {
@@ -1014,6 +1072,19 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
         RC(s->bounceQ.ensure(cap * 2));
         RC(s->lit.ensure(cap * nL));
         RC(s->pathState.ensure(cap * 2 * levels));
+    } else if (useWave(s, P)) { // persistent wavefront: records indexed by (pixel slot, level), one ticket-indexed ray array
+        RC(s->hitRec.ensure(cap * pathLevels * 3));
+        RC(s->pathDepth.ensure(cap));
+        RC(s->lit.ensure(cap * pathLevels * nL));
+        const size_t tickets = waveTicketCap(P);
+        if (tickets >= ((size_t)1 << 31)) return fail(CGRT_ERR_INVALID, "frame too large for the ray queue's 31-bit tickets");
+        if (!s->waveRays.p || s->waveRays.n < tickets * 3) { // (the records' tags compare against waveSeq >= 1: start from zero)
+            RC(s->waveRays.ensure(tickets * 3));
+            CK(cudaMemset(s->waveRays.p, 0, tickets * 3 * sizeof(float4)));
+            RC(s->waveFin.ensure(tickets * 2));
+            CK(cudaMemset(s->waveFin.p, 0, tickets * 2 * sizeof(float4)));
+        }
+        RC(s->waveCtl.ensure(WCTL_INTS));
     } else if (useRounds(s, P)) { // round pipeline: records indexed by (pixel slot, level), two ray lists per kind
         RC(s->hitRec.ensure(cap * pathLevels * 3));
         RC(s->pathDepth.ensure(cap));
@@ -1110,6 +1181,27 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
         launches = launchWavefront(s->dev, (const FrameParams*)s->dParamBlock.p, P,
                                    (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), B, dTiles, d_out,
                                    s->di.numSMs, true, &s->trace, st);
+    } else if (useWave(s, P)) {
+        RoundBuffers RB;
+        for (int k = 0; k < 2; k++) { RB.cRay[k] = nullptr; RB.cRes[k] = nullptr; RB.sRay[k] = nullptr; RB.sRes[k] = nullptr; }
+        RB.hitRec = s->hitRec.p;
+        RB.lit = s->lit.p;
+        RB.pathDepth = s->pathDepth.p;
+        RB.counts = s->counts.p;
+        RB.levels = std::max(P.traceLimit, 1);
+        WaveQ Q;
+        Q.rays = s->waveRays.p;
+        Q.fin = s->waveFin.p;
+        Q.ctl = s->waveCtl.p;
+        Q.seq = ++s->waveSeq;
+        if (Q.seq == 0u) Q.seq = ++s->waveSeq;
+        Q.cap = (int)std::min<size_t>(s->waveRays.n / 3, (size_t)0x7fffffff);
+        waveTuning(Q, P.nSlots);
+        launches = launchWavePipeline(s->dev, (const FrameParams*)s->dParamBlock.p, P,
+                                      (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), RB, Q, dSeq, d_out,
+                                      s->di.numSMs, &s->trace, st);
+        s->lastChains = 1;
+        s->lastPipeline = 3;
     } else if (useRounds(s, P)) {
         // chains: independent sub-frames (tiles dealt round-robin) on their own streams
         const int nChains = roundPipelineChains(P.nSlots);
@@ -1191,7 +1283,13 @@ int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
     // logical rays: primary = pixels of this rank inside the image
     const uint64_t primary = s->primaryPixels;
     stats->primary = primary;
-    if (s->lastPipeline == 2) {
+    if (s->lastPipeline == 3) { // persistent wavefront: the watchdog of k_wave (a warp waited for seconds) invalidates the frame
+        int err = 0;
+        CK(cudaMemcpy(&err, s->waveCtl.p + WCTL_ERR, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) return fail(CGRT_ERR_CUDA, "k_wave watchdog: the persistent wavefront did not complete; the frame is invalid");
+    }
+    stats->pipeline = (uint32_t)s->lastPipeline;
+    if (s->lastPipeline == 2 || s->lastPipeline == 3) {
         stats->primary_hit = (uint64_t)counts[CGRT_CNT_PATHS];
         for (int l = 0; l < P.traceLimit; l++) {
             stats->shadow += (uint64_t)counts[CGRT_CNT_HIT + l] * (uint64_t)P.nLights;

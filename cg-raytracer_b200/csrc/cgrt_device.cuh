@@ -598,12 +598,11 @@ RT_DEV float fastBound(const FastTrav& T, float maxDist)
     return (ANY ? fminf(T.t, maxDist) : T.t) * slack;
 }
 
-template <bool ANY>
-RT_DEV int fastStepWide(const DevScene& S, FastTrav& T, FastStack& K, float maxDist)
+RT_DEV int fastStepWideDyn(const DevScene& S, FastTrav& T, FastStack& K, bool any, float maxDist)
 {
     const float4* w = S.wide + CGRT_WIDE_STRIDE * (size_t)(T.node & CGRT_IDX_MASK);
     const float slack = 1.000001f;
-    const float bt = fastBound<ANY>(T, maxDist);
+    const float bt = (any ? fminf(T.t, maxDist) : T.t) * slack; // = fastBound<ANY>
     const V3 o = T.o, inv = T.inv;
     float tin[8];
     uint32_t cid[8];
@@ -650,6 +649,11 @@ RT_DEV int fastStepWide(const DevScene& S, FastTrav& T, FastStack& K, float maxD
     fastPrefetch(S, T.node);
     return TRAV_CONTINUE;
 }
+template <bool ANY>
+RT_DEV int fastStepWide(const DevScene& S, FastTrav& T, FastStack& K, float maxDist)
+{
+    return fastStepWideDyn(S, T, K, ANY, maxDist);
+}
 
 // One triangle against the search state, with the reference's accept arithmetic (same expression trees as leafCandidate).
 // Returns TRAV_CONTINUE (state possibly updated), TRAV_DEFER (the outcome depends on the reference's visiting order: exact
@@ -694,9 +698,8 @@ RT_DEV int fastTriangle(const DevScene& S, FastTrav& T, float& t2, int i, float 
     return TRAV_CONTINUE;
 }
 
-// the triangles of one fast-tree leaf
-template <bool ANY>
-RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps, float maxDist)
+// the triangles of one fast-tree leaf; `any` = shadow ray (early exit as soon as the shadow predicate holds for the best)
+RT_DEV int fastStepLeafDyn(const DevScene& S, FastTrav& T, FastStack& K, bool any, float eps, float maxDist)
 {
     const uint32_t id = T.node;
     const int first = (int)(id & CGRT_IDX_MASK);
@@ -731,9 +734,15 @@ RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps,
         if (T.hitTri >= 0) K.t2 = fminf(K.t2, T.t);        // the old best becomes the runner-up
         T.t = tt;
         T.hitTri = pos;
-        if (ANY && !(tt + eps >= maxDist)) return TRAV_FIRED;
+        if (any && !(tt + eps >= maxDist)) return TRAV_FIRED;
     }
-    return fastPop(S, T, K, fastBound<ANY>(T, maxDist));
+    // search bound: fminf(t, maxDist) for shadow rays; closest-hit rays carry maxDist = +inf or are bounded by t alone
+    return fastPop(S, T, K, (any ? fminf(T.t, maxDist) : T.t) * 1.000001f);
+}
+template <bool ANY>
+RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps, float maxDist)
+{
+    return fastStepLeafDyn(S, T, K, ANY, eps, maxDist);
 }
 
 // Closest hit: does the reference find tri* (position `pos`, distance tStar)? Until tri* is accepted the reference's ray.t is

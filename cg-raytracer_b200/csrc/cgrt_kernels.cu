@@ -468,6 +468,7 @@ struct Tuning {
                        // subset's launch is filled by the other subsets' work; 0 = by frame size (4 for a 1080p frame on one GPU)
     int coop = 0;      // round pipeline: rounds with fewer rays than this are searched by k_trace8 (8 lanes per ray: low
                        // latency), larger ones by k_trace (1 lane per ray: higher throughput)
+    int waveBlocks = 0; // persistent wavefront: CTAs per SM (0 = as many as fit)
 };
 static Tuning g_tune;
 static bool g_tuneLoaded = false;
@@ -496,6 +497,7 @@ static const Tuning& tuning()
                     else if (key == "blocks") g_tune.blocks = v;
                     else if (key == "coop") g_tune.coop = v;
                     else if (key == "chains") g_tune.chains = v;
+                    else if (key == "waveblocks") g_tune.waveBlocks = v;
                 }
                 pos = c + 1;
             }
@@ -961,6 +963,8 @@ __global__ void __launch_bounds__(128, CGRT_MINBLOCKS) k_shadow_replay(DevScene 
 }
 
 // direct colour of one hit record: shading(), src/main.cpp:160-235 (point-light loop :220-232)
+// CG: the lit flags were written by other SMs during this kernel (persistent wavefront): read them through L2
+template <bool CG = false>
 RT_DEV V3 directColour(const DevScene& S, const float4* __restrict__ lights, int nL, const float4& a, const float4& b,
                        const float4& c, const uint8_t* __restrict__ lit, V3& ks)
 {
@@ -975,7 +979,7 @@ RT_DEV V3 directColour(const DevScene& S, const float4* __restrict__ lights, int
     for (int l = 0; l < nL; l++) {
         const V3 lightPos = mk3(__ldg(lights + 2 * l)), lightCol = mk3(__ldg(lights + 2 * l + 1));
         const V3 fromPosToLight = normalize3(lightPos - P);
-        if (!lit[l]) continue;
+        if (!(CG ? __ldcg(lit + l) : lit[l])) continue;
         V3 diffuse = mk3(0.0f, 0.0f, 0.0f), specular = diffuse;
         const float diffuseCos = dot3(fromPosToLight, N); // diffuseOneLight, main.cpp:84-98
         if (!(diffuseCos <= 0)) diffuse = (lightCol * kd) * diffuseCos;
@@ -1384,6 +1388,146 @@ __global__ void __launch_bounds__(128, CGRT_TRACE8_MINBLOCKS) k_trace8(DevScene 
     }
 }
 
+// ---- after the search: per-ray completion shared by k_finish (round pipeline) and k_wave (persistent wavefront) ----------------
+// exact replays (<= 3e-5 of the rays): inline in the flat kernel, out of line in the persistent one (its register budget is
+// set by the search loop)
+__device__ __noinline__ bool replayAnyNI(const DevScene& S, const V3& o, const V3& d, float tIn, float eps, float maxDist)
+{
+    TraceResult R;
+    return traverseFast<true>(S, o, d, tIn, eps, maxDist, R);
+}
+__device__ __noinline__ bool replayClosestNI(const DevScene& S, const V3& o, const V3& d, float tIn, TraceResult& R)
+{
+    return traverseFast<false>(S, o, d, tIn, 0.0f, 0.0f, R);
+}
+
+// shadow ray (record a, b, c; search result res = state, t, tri, t2): certificate or exact replay, sphere loop.
+// Returns true iff the point is shadowed for this light (pointInShadow, main.cpp:104-135).
+template <bool NI>
+RT_DEV bool finishShadowRay(const DevScene& S, const float4& a, const float4& b, const float4& c, const float4& res, bool& replayS)
+{
+    const V3 o = mk3(a), d = mk3(b);
+    int state = f2i(res.x), tri = f2i(res.z);
+    const float eps = c.z, maxDist = b.w;
+    float tBest = res.y;
+    bool shadowed = false, settled = false;
+    if (state == TRAV_DONE && S.nAlways > 0) { // the triangles outside the tree, if the ray enters the reference tree
+        const float4 rq0 = __ldg(S.nodes + 0), rq1 = __ldg(S.nodes + 1);
+        float tmp;
+        if (startsInBox(o, mk3(rq0), mk3(rq1)) || slabTest(mk3(rq0), mk3(rq1), o, d, a.w, tmp)) {
+            FastTrav T;
+            float t2s = res.w;
+            T.o = o; T.d = d; T.t = tBest; T.hitTri = tri; T.sp = 0; T.node = 0u;
+            state = fastAlways<true>(S, T, t2s, eps, maxDist);
+            if (state == TRAV_CONTINUE) state = TRAV_DONE;
+            tBest = T.t;
+            tri = T.hitTri;
+        }
+    }
+    if (state == TRAV_FIRED) {
+        if (certifyAny(S, o, d, tri, tBest, eps, maxDist)) { shadowed = true; settled = true; }
+    } else if (state == TRAV_DONE) { // the tree does not shadow; spheres may (bvh.cpp:878-879)
+        settled = true;
+        float t = tBest;
+        for (int sp = 0; sp < S.nSpheres; sp++) {
+            const float4 sc = __ldg(S.spheres + 3 * sp);
+            float ts;
+            V3 sn;
+            if (sphereTest(mk3(sc), sc.w, o, d, t, ts, sn)) {
+                t = ts;
+                if (!(ts + eps >= maxDist)) { shadowed = true; break; }
+            }
+        }
+    }
+    if (!settled) { // not certifiable: the exact reference-order traversal decides
+        if (NI) shadowed = replayAnyNI(S, o, d, a.w, eps, maxDist);
+        else {
+            TraceResult R;
+            shadowed = traverseFast<true>(S, o, d, a.w, eps, maxDist, R);
+        }
+        replayS = true;
+    }
+    return shadowed;
+}
+
+// closest-hit ray: certificate or exact replay, sphere loop (bvh.cpp:878-879). Returns hit; R = the reference's result.
+template <bool NI>
+RT_DEV bool finishClosestRay(const DevScene& S, const float4& a, const float4& b, const float4& res, TraceResult& R, bool& replayC)
+{
+    const V3 o = mk3(a), d = mk3(b);
+    int state = f2i(res.x);
+    R.sphere = -1;
+    R.tri = f2i(res.z);
+    R.t = res.y;
+    float t2 = res.w;
+    if (state == TRAV_DONE && S.nAlways > 0) { // the triangles outside the tree, if the ray enters the reference tree
+        const float4 rq0 = __ldg(S.nodes + 0), rq1 = __ldg(S.nodes + 1);
+        float tmp;
+        if (startsInBox(o, mk3(rq0), mk3(rq1)) || slabTest(mk3(rq0), mk3(rq1), o, d, a.w, tmp)) {
+            FastTrav T;
+            T.o = o; T.d = d; T.t = R.t; T.hitTri = R.tri; T.sp = 0; T.node = 0u;
+            state = fastAlways<false>(S, T, t2, 0.0f, 0.0f);
+            if (state == TRAV_CONTINUE) state = TRAV_DONE;
+            R.t = T.t;
+            R.tri = T.hitTri;
+        }
+    }
+    const bool settled = state == TRAV_DONE && (R.tri < 0 || certifyClosest(S, o, d, R.tri, R.t, t2, a.w));
+    if (settled) {
+        float t = R.t;
+        for (int sp = 0; sp < S.nSpheres; sp++) {
+            const float4 sc = __ldg(S.spheres + 3 * sp);
+            float ts;
+            V3 sn;
+            if (sphereTest(mk3(sc), sc.w, o, d, t, ts, sn)) {
+                t = ts;
+                R.sphere = sp;
+                R.sphereN = sn;
+            }
+        }
+        R.t = t;
+        return R.tri >= 0 || R.sphere >= 0;
+    }
+    replayC = true;
+    if (NI) return replayClosestNI(S, o, d, a.w, R);
+    return traverseFast<false>(S, o, d, a.w, 0.0f, 0.0f, R);
+}
+
+// shading normal + material of a hit (intersectRayWithTriangle's epilogue, ray_tracing.cpp:92-107; spheres: bvh.cpp:878-879
+// leave the material of the last accepted triangle in place)
+RT_DEV void hitNormalAndMaterial(const DevScene& S, const TraceResult& R, const V3& o, const V3& d, V3& nn, int& mat)
+{
+    if (R.sphere >= 0) {
+        nn = R.sphereN;
+        mat = R.tri >= 0 ? f2i(__ldg(S.triV1 + R.tri).w) : -1;
+    } else {
+        const int k = R.tri;
+        const float4 v0 = __ldg(S.triV0 + k), v1 = __ldg(S.triV1 + k), v2 = __ldg(S.triV2 + k);
+        const float4 n0 = __ldg(S.triN0 + k), n1 = __ldg(S.triN1 + k), n2 = __ldg(S.triN2 + k);
+        const float4 pl = __ldg(S.triPl + k);
+        float al, be, ga;
+        hitEpilogue(mk3(v0), mk3(v1), mk3(v2), mk3(n0), mk3(n1), mk3(n2), mk3(pl), o, d, R.t, al, be, ga, nn);
+        mat = f2i(v1.w);
+    }
+}
+
+// the shadow ray of a hit towards light l (pointInShadow, src/main.cpp:104-135) and its reflection ray (ComputeReflectedRay,
+// main.cpp:252-256: t = |incoming direction|, origin offset along the reflection)
+RT_DEV void shadowRayOf(const float4* __restrict__ lights, int l, const V3& pointOn, V3& org, V3& dir, float& dist)
+{
+    const V3 lightPos = mk3(__ldg(lights + 2 * l));
+    const V3 fromPosToLight = lightPos - pointOn;
+    dir = normalize3(fromPosToLight);
+    org = pointOn + 0.001f * dir;
+    dist = length3(fromPosToLight);
+}
+RT_DEV void reflectionRayOf(const V3& pointOn, const V3& rd, const V3& nn, V3& org, V3& dir, float& tIn)
+{
+    dir = normalize3(reflect3(rd, nn));
+    org = pointOn + 0.001f * dir;
+    tIn = length3(rd);
+}
+
 // ---- after the search: one thread per ray ------------------------------------------------------------------------------------
 // Shadow rays (list A, produced by the hits of level `level - 1`): certificate or exact replay, sphere loop, lit flag.
 // Closest-hit rays (list B, level `level`): certificate or exact replay, sphere loop, hit epilogue, hit record; emits the
@@ -1407,87 +1551,15 @@ __global__ void __launch_bounds__(128) k_finish(DevScene S, const FrameParams* _
         if (i < nA) { // ---- shadow ray
             const float4* r = raysA + 3 * (size_t)i;
             const float4 a = r[0], b = r[1], c = r[2], res = resA[i];
-            const V3 o = mk3(a), d = mk3(b);
-            int state = f2i(res.x), tri = f2i(res.z);
-            const float eps = c.z, maxDist = b.w;
-            float tBest = res.y;
-            bool shadowed = false, settled = false;
-            if (state == TRAV_DONE && S.nAlways > 0) { // the triangles outside the tree, if the ray enters the reference tree
-                const float4 rq0 = __ldg(S.nodes + 0), rq1 = __ldg(S.nodes + 1);
-                float tmp;
-                if (startsInBox(o, mk3(rq0), mk3(rq1)) || slabTest(mk3(rq0), mk3(rq1), o, d, a.w, tmp)) {
-                    FastTrav T;
-                    float t2s = res.w;
-                    T.o = o; T.d = d; T.t = tBest; T.hitTri = tri; T.sp = 0; T.node = 0u;
-                    state = fastAlways<true>(S, T, t2s, eps, maxDist);
-                    if (state == TRAV_CONTINUE) state = TRAV_DONE;
-                    tBest = T.t;
-                    tri = T.hitTri;
-                }
-            }
-            if (state == TRAV_FIRED) {
-                if (certifyAny(S, o, d, tri, tBest, eps, maxDist)) { shadowed = true; settled = true; }
-            } else if (state == TRAV_DONE) { // the tree does not shadow; spheres may (bvh.cpp:878-879)
-                settled = true;
-                float t = tBest;
-                for (int sp = 0; sp < S.nSpheres; sp++) {
-                    const float4 sc = __ldg(S.spheres + 3 * sp);
-                    float ts;
-                    V3 sn;
-                    if (sphereTest(mk3(sc), sc.w, o, d, t, ts, sn)) {
-                        t = ts;
-                        if (!(ts + eps >= maxDist)) { shadowed = true; break; }
-                    }
-                }
-            }
-            if (!settled) { // not certifiable: the exact reference-order traversal decides
-                TraceResult R;
-                shadowed = traverseFast<true>(S, o, d, a.w, eps, maxDist, R);
-                replayS = true;
-            }
+            const bool shadowed = finishShadowRay<false>(S, a, b, c, res, replayS);
             B.lit[f2i(c.y) & 0x3fffffff] = shadowed ? 0 : 1;
         } else if (i < n) { // ---- closest-hit ray of `level`
             const float4* r = raysB + 3 * (size_t)(i - nA);
             const float4 a = r[0], b = r[1], c = r[2], res = resB[i - nA];
             const V3 o = mk3(a), d = mk3(b);
             slot = f2i(c.x);
-            int state = f2i(res.x);
             TraceResult R;
-            R.sphere = -1;
-            R.tri = f2i(res.z);
-            R.t = res.y;
-            float t2 = res.w;
-            if (state == TRAV_DONE && S.nAlways > 0) { // the triangles outside the tree, if the ray enters the reference tree
-                const float4 rq0 = __ldg(S.nodes + 0), rq1 = __ldg(S.nodes + 1);
-                float tmp;
-                if (startsInBox(o, mk3(rq0), mk3(rq1)) || slabTest(mk3(rq0), mk3(rq1), o, d, a.w, tmp)) {
-                    FastTrav T;
-                    T.o = o; T.d = d; T.t = R.t; T.hitTri = R.tri; T.sp = 0; T.node = 0u;
-                    state = fastAlways<false>(S, T, t2, 0.0f, 0.0f);
-                    if (state == TRAV_CONTINUE) state = TRAV_DONE;
-                    R.t = T.t;
-                    R.tri = T.hitTri;
-                }
-            }
-            bool settled = state == TRAV_DONE && (R.tri < 0 || certifyClosest(S, o, d, R.tri, R.t, t2, a.w));
-            if (settled) {
-                float t = R.t;
-                for (int sp = 0; sp < S.nSpheres; sp++) {
-                    const float4 sc = __ldg(S.spheres + 3 * sp);
-                    float ts;
-                    V3 sn;
-                    if (sphereTest(mk3(sc), sc.w, o, d, t, ts, sn)) {
-                        t = ts;
-                        R.sphere = sp;
-                        R.sphereN = sn;
-                    }
-                }
-                R.t = t;
-                hit = R.tri >= 0 || R.sphere >= 0;
-            } else {
-                hit = traverseFast<false>(S, o, d, a.w, 0.0f, 0.0f, R);
-                replayC = true;
-            }
+            hit = finishClosestRay<false>(S, a, b, res, R, replayC);
             if (!hit) {
                 if (level == 0) { // trace(): miss -> black, src/main.cpp:288-294
                     int x, y, outIdx, local;
@@ -1495,18 +1567,7 @@ __global__ void __launch_bounds__(128) k_finish(DevScene S, const FrameParams* _
                 }
             } else {
                 int mat;
-                if (R.sphere >= 0) {
-                    nn = R.sphereN;
-                    mat = R.tri >= 0 ? f2i(__ldg(S.triV1 + R.tri).w) : -1;
-                } else {
-                    const int k = R.tri;
-                    const float4 v0 = __ldg(S.triV0 + k), v1 = __ldg(S.triV1 + k), v2 = __ldg(S.triV2 + k);
-                    const float4 n0 = __ldg(S.triN0 + k), n1 = __ldg(S.triN1 + k), n2 = __ldg(S.triN2 + k);
-                    const float4 pl = __ldg(S.triPl + k);
-                    float al, be, ga;
-                    hitEpilogue(mk3(v0), mk3(v1), mk3(v2), mk3(n0), mk3(n1), mk3(n2), mk3(pl), o, d, R.t, al, be, ga, nn);
-                    mat = f2i(v1.w);
-                }
+                hitNormalAndMaterial(S, R, o, d, nn, mat);
                 pointOn = o + d * R.t; // main.cpp:164
                 rd = d;
                 rec = slot * B.levels + level;
@@ -1529,21 +1590,18 @@ __global__ void __launch_bounds__(128) k_finish(DevScene S, const FrameParams* _
             if (rs) atomicAdd(B.counts + CGRT_CNT_REPLAY_SHADOW, __popc(rs));
         }
         if (hit && nL > 0) {
-            for (int l = 0; l < nL; l++) { // pointInShadow, src/main.cpp:104-135
-                const V3 lightPos = mk3(__ldg(lights + 2 * l));
-                const V3 fromPosToLight = lightPos - pointOn;
-                const V3 dir = normalize3(fromPosToLight);
-                const float epsilon = 0.001f;
-                const V3 org = pointOn + epsilon * dir;
-                writeRay(nextS + 3 * ((size_t)sBase * nL + l), org, FLT_MAX, dir, length3(fromPosToLight), slot,
-                         CGRT_RAY_ANY | (rec * nL + l), epsilon);
+            for (int l = 0; l < nL; l++) {
+                V3 org, dir;
+                float dist;
+                shadowRayOf(lights, l, pointOn, org, dir, dist);
+                writeRay(nextS + 3 * ((size_t)sBase * nL + l), org, FLT_MAX, dir, dist, slot, CGRT_RAY_ANY | (rec * nL + l), 0.001f);
             }
         }
-        if (bounce) { // ComputeReflectedRay, main.cpp:252-256: t = |incoming direction|, origin offset along the reflection
-            const V3 reflected = normalize3(reflect3(rd, nn));
-            const float epsilon = 0.001f;
-            writeRay(nextC + 3 * (size_t)cPos, pointOn + epsilon * reflected, length3(rd), reflected, __int_as_float(0x7f800000),
-                     slot, level + 1, 0.0f);
+        if (bounce) {
+            V3 org, dir;
+            float tIn;
+            reflectionRayOf(pointOn, rd, nn, org, dir, tIn);
+            writeRay(nextC + 3 * (size_t)cPos, org, tIn, dir, __int_as_float(0x7f800000), slot, level + 1, 0.0f);
         }
     }
 }
@@ -1570,6 +1628,8 @@ __global__ void __launch_bounds__(128) k_shade_slots(DevScene S, const FramePara
         if (seqToPixel(P, tileSeq, slot, x, y, outIdx, local)) storeRGB(fb, outIdx, colour);
     }
 }
+
+#include "cgrt_wave.cuh"
 
 // ---- shading + bounce emission: one thread per hit.  shading/shade, src/main.cpp:61-98, 220-264 ---------------------------
 __global__ void __launch_bounds__(128) k_shade(DevScene S, const FrameParams* __restrict__ Pp,
@@ -2021,6 +2081,47 @@ int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FramePar
     traceEnd(tr, 3, st);
     launches++;
     return launches;
+}
+
+int waveGridBlocks(int numSMs)
+{
+    static int perSM[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (perSM[dev] == 0) {
+        cudaFuncSetAttribute(k_wave, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave, 128, 0) != cudaSuccess || nb < 1) nb = 1;
+        perSM[dev] = nb;
+    }
+    int b = perSM[dev];
+    const int cap = tuning().waveBlocks;
+    if (cap > 0 && cap < b) b = cap;
+    return numSMs * b;
+}
+
+int launchWavePipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
+                       const RoundBuffers& B, const WaveQ& Q, const int2* dTileSeq, float* fb, int numSMs, WaveTrace* tr,
+                       cudaStream_t st)
+{
+    cudaMemsetAsync(B.counts, 0, sizeof(int) * CGRT_CNT_TOTAL, st);
+    cudaMemsetAsync(Q.ctl, 0, sizeof(int) * WCTL_INTS, st);
+    if (hP.traceLimit <= 0) { // trace(0, ...) returns black for every pixel without casting a ray, src/main.cpp:267-272
+        if (hP.world > 1 && hP.screenLayout) {
+            k_clear_tiles<<<gridFor((size_t)hP.nSlots, 128, numSMs * 16), 128, 0, st>>>(dP, dTileSeq, fb);
+            return 1;
+        }
+        const size_t px = hP.world == 1 ? (size_t)hP.width * hP.height : (size_t)hP.nSlots;
+        cudaMemsetAsync(fb, 0, px * 3 * sizeof(float), st);
+        return 0;
+    }
+    // every CTA must be resident at once: warps wait for rays that other CTAs produce
+    const int grid = waveGridBlocks(numSMs);
+    traceBegin(tr, 2, st);
+    k_wave<<<grid, 128, 0, st>>>(S, dP, dLights, Q, B, dTileSeq, fb);
+    traceEnd(tr, 2, st);
+    return 1;
 }
 
 void launchAssemble(const float* gathered, size_t perRankFloats, const int* tileLists, const int* tileCounts, int maxTiles,

@@ -136,6 +136,32 @@ struct RoundBuffers {
     int levels;
 };
 
+// ---- persistent wavefront (cgrt_wave.cuh): control block + ticket queue of the single-kernel frame ----------------------------
+#define WCTL_PENDING 0  // u64 at int index 0: (CTAs done with phase A << 32) | rays in flight
+#define WCTL_ERR 2      // watchdog: a warp waited longer than WaveQ::timeoutNs
+#define WCTL_HEAD 32    // ray queue: tickets handed out           (every counter on its own 128-byte line)
+#define WCTL_TAIL 64    // ray queue: tickets reserved by producers
+#define WCTL_FHEAD 96   // finish queue: tickets handed out
+#define WCTL_FTAIL 128  // finish queue: tickets reserved
+#define WCTL_HEAD2 160  // ray queue, second part (after the change-over to the cooperative search form): own counters
+#define WCTL_TAIL2 192
+#define WCTL_CLOSEAT 224 // 1 + the first ticket of the first part that will never be served (0 = the first part is open)
+#define WCTL_DONE 256   // 32 copies of the done flag, one per 128-byte line (ctl[WCTL_DONE + 32 k])
+#define WCTL_SCRATCH (WCTL_DONE + 32 * 32) // 32 words, one per 128-byte line: targets of the release reductions (waveRelease)
+#define WCTL_INTS (WCTL_SCRATCH + 32 * 32)
+
+struct WaveQ {
+    float4* rays;   // ray queue: 3 x float4 per ticket (layout in cgrt_wave.cuh)
+    float4* fin;    // finish queue: 2 x float4 per ticket
+    int* ctl;       // WCTL_INTS ints, zeroed before every frame
+    uint32_t seq;   // sequence number of this frame on these queues (never 0)
+    int cap;        // tickets each array can hold
+    int mode;       // search form of the frame: 1 LANE (one lane per ray) first, 2 GROUP (eight lanes per ray) throughout
+    int switchBelow; // mode 1: change over to GROUP when fewer rays than this are in flight (0 = never)
+    int finEvery;   // SMs with %smid % finEvery == 0 run the finish warps, the others the search warps
+    unsigned long long timeoutNs;
+};
+
 #define CGRT_TRACE_MAX_KERNELS (8 * (2 * (CGRT_MAX_LEVELS + 1) + 1) + 2) // chains x (k_gen + 2 per round) + shade
 // optional per-kernel event trace of one wavefront (classes: 0 primary, 1 bounce closest-hit, 2 shadow, 3 shade)
 struct WaveTrace {
@@ -176,6 +202,11 @@ int roundPipelineChains(int nSlots); // number of chains the round pipeline uses
 int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
                         const RoundBuffers* chains, int nChains, const ChainSync& sync, const int2* dTileSeq, float* fb,
                         int numSMs, WaveTrace* tr, cudaStream_t st);
+// one kernel per frame: phase A ray generation, phase B search + finish over the device-side queue, phase C shading
+int waveGridBlocks(int numSMs); // co-resident CTAs of k_wave on this device (occupancy x SMs; CGRT_TUNE blocks=N caps the per-SM count)
+int launchWavePipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
+                       const RoundBuffers& B, const WaveQ& Q, const int2* dTileSeq, float* fb, int numSMs, WaveTrace* tr,
+                       cudaStream_t st);
 void launchAssemble(const float* gathered, size_t perRankFloats, const int* tileLists, const int* tileCounts, int maxTiles,
                     int world, int tileW, int tileH, int tilesX, int width, int height, float* frame, int numSMs,
                     cudaStream_t st);

@@ -133,7 +133,9 @@ typedef struct cgrt_render_stats {
     uint32_t class_launches[4];                    /* kernels launched per class */
     uint32_t replayed_closest, replayed_shadow;    /* rays the speculative traversal could not certify and handed to the
                                                       exact reference-order traversal (same results, more work) */
-    float reserved[1];
+    uint32_t pipeline;                             /* which kernel set rendered the frame: 0 counting wavefront (CGRT_RENDER_COUNT),
+                                                      1 path pipeline (scenes without a fast tree), 2 round pipeline
+                                                      (CGRT_PIPELINE=rounds), 3 persistent wavefront k_wave (default) */
 } cgrt_render_stats;
 
 typedef struct cgrt_scene cgrt_scene; /* opaque: flattened scene + BVH resident in HBM */
