@@ -260,7 +260,7 @@ struct cgrt_scene {
     DevBuf<float4> replayQ;
     DevBuf<float4> cRay[2], cRes[2], sRay[2], sRes[2];
     DevBuf<float4> waveRays, waveFin; // persistent wavefront: ticket-indexed ray records / finished-search records
-    DevBuf<int> waveCtl;
+    DevBuf<int> waveCtl, waveTrace;
     uint32_t waveSeq = 0;
     int lastPipeline = 0; // 0 counting wavefront, 1 path pipeline, 2 round pipeline
     int lastChains = 1;
@@ -315,7 +315,7 @@ static void destroyScene(cgrt_scene* s)
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->tileSeq.release(); s->frame.release();
     s->tests.release(); s->hitRec.release(); s->hitList.release(); s->pathDepth.release(); s->replayShadow.release(); s->replayQ.release();
     for (int k = 0; k < 2; k++) { s->cRay[k].release(); s->cRes[k].release(); s->sRay[k].release(); s->sRes[k].release(); }
-    s->waveRays.release(); s->waveFin.release(); s->waveCtl.release();
+    s->waveRays.release(); s->waveFin.release(); s->waveCtl.release(); s->waveTrace.release();
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->hParamRing) cudaFreeHost(s->hParamRing);
     if (s->hFramePinned) cudaFreeHost(s->hFramePinned);
@@ -1077,7 +1077,7 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
         RC(s->pathDepth.ensure(cap));
         RC(s->lit.ensure(cap * pathLevels * nL));
         const size_t tickets = waveTicketCap(P);
-        if (tickets >= ((size_t)1 << 31)) return fail(CGRT_ERR_INVALID, "frame too large for the ray queue's 31-bit tickets");
+        if (tickets >= ((size_t)1 << 30)) return fail(CGRT_ERR_INVALID, "frame too large for the ray queue's 30-bit tickets");
         if (!s->waveRays.p || s->waveRays.n < tickets * 3) { // (the records' tags compare against waveSeq >= 1: start from zero)
             RC(s->waveRays.ensure(tickets * 3));
             CK(cudaMemset(s->waveRays.p, 0, tickets * 3 * sizeof(float4)));
@@ -1195,7 +1195,13 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
         Q.ctl = s->waveCtl.p;
         Q.seq = ++s->waveSeq;
         if (Q.seq == 0u) Q.seq = ++s->waveSeq;
-        Q.cap = (int)std::min<size_t>(s->waveRays.n / 3, (size_t)0x7fffffff);
+        Q.cap = (int)std::min<size_t>(s->waveRays.n / 3, (size_t)0x3fffffff);
+        Q.trace = nullptr;
+        if (getenv("CGRT_WAVE_TRACE")) { // timeline of the frame's counters (cgrt_debug_wave_timeline); off by default
+            RC(s->waveTrace.ensure((size_t)WAVE_TRACE_SAMPLES * 8));
+            CK(cudaMemsetAsync(s->waveTrace.p, 0, (size_t)WAVE_TRACE_SAMPLES * 8 * sizeof(int), st));
+            Q.trace = s->waveTrace.p;
+        }
         waveTuning(Q, P.nSlots);
         launches = launchWavePipeline(s->dev, (const FrameParams*)s->dParamBlock.p, P,
                                       (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), RB, Q, dSeq, d_out,
@@ -1557,6 +1563,17 @@ int cgrt_quantize_rgba8(int device, const float* d_frame, size_t n_pixels, uint8
     launchQuantize(d_frame, n_pixels, d_rgba8, (cudaStream_t)stream);
     CK(cudaGetLastError());
     return CGRT_OK;
+}
+
+// timeline of the last k_wave frame (CGRT_WAVE_TRACE=1): out[k][8] = {valid, rays in flight, ray queue head, tail, finish queue
+// head, tail, second-part head, tail} for the k-th 4.096 us bucket since the kernel started; returns the number of buckets copied
+int cgrt_debug_wave_timeline(cgrt_scene* s, int32_t* out, int32_t cap)
+{
+    if (!s || !out || !s->waveTrace.p) return 0;
+    if (useSceneDevice(s) != CGRT_OK) return 0;
+    const int n = std::min<int>(cap, WAVE_TRACE_SAMPLES);
+    if (cudaMemcpy(out, s->waveTrace.p, (size_t)n * 8 * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
 }
 
 #ifdef CGRT_INSTRUMENT

@@ -2116,6 +2116,7 @@ int launchWavePipeline(const DevScene& S, const FrameParams* dP, const FramePara
         cudaMemsetAsync(fb, 0, px * 3 * sizeof(float), st);
         return 0;
     }
+    if (hP.nSlots <= 0) return 0; // this rank owns no pixel of the frame
     // every CTA must be resident at once: warps wait for rays that other CTAs produce
     const int grid = waveGridBlocks(numSMs);
     traceBegin(tr, 2, st);

@@ -145,8 +145,11 @@ struct RoundBuffers {
 #define WCTL_FTAIL 128  // finish queue: tickets reserved
 #define WCTL_HEAD2 160  // ray queue, second part (after the change-over to the cooperative search form): own counters
 #define WCTL_TAIL2 192
+#define WCTL_FINCOUNT 288 // finish warps of the frame / finish warps that have left their loop (phase C waits for equality);
+#define WCTL_FINEXIT 289  // own 128-byte line
+#define WCTL_T0 4       // low 32 bits of %globaltimer of the first CTA that started (timeline origin)
 #define WCTL_CLOSEAT 224 // 1 + the first ticket of the first part that will never be served (0 = the first part is open)
-#define WCTL_DONE 256   // 32 copies of the done flag, one per 128-byte line (ctl[WCTL_DONE + 32 k])
+#define WCTL_DONE 320   // 32 copies of the done flag, one per 128-byte line (ctl[WCTL_DONE + 32 k])
 #define WCTL_SCRATCH (WCTL_DONE + 32 * 32) // 32 words, one per 128-byte line: targets of the release reductions (waveRelease)
 #define WCTL_INTS (WCTL_SCRATCH + 32 * 32)
 
@@ -160,7 +163,9 @@ struct WaveQ {
     int switchBelow; // mode 1: change over to GROUP when fewer rays than this are in flight (0 = never)
     int finEvery;   // SMs with %smid % finEvery == 0 run the finish warps, the others the search warps
     unsigned long long timeoutNs;
+    int* trace;     // optional (CGRT_WAVE_TRACE=1): WAVE_TRACE_SAMPLES x 8 ints, one sample of the counters per 4.096 us of the frame
 };
+#define WAVE_TRACE_SAMPLES 1024
 
 #define CGRT_TRACE_MAX_KERNELS (8 * (2 * (CGRT_MAX_LEVELS + 1) + 1) + 2) // chains x (k_gen + 2 per round) + shade
 // optional per-kernel event trace of one wavefront (classes: 0 primary, 1 bounce closest-hit, 2 shadow, 3 shade)

@@ -233,6 +233,26 @@ RT_DEV void wavePending(const WaveQ& Q, long long delta)
         }
     }
 }
+// fire-and-forget form for increments (a reduction: nothing waits for it). It is issued before the atomic that reserves the
+// children's records, whose result the warp does wait for, so it is performed long before a child can be finished.
+RT_DEV void wavePendingAdd(const WaveQ& Q, int created) { atomicAdd((unsigned long long*)Q.ctl, (unsigned long long)created); }
+// the decrement in two halves: issue now, look at the result later (on the next trip round the finish loop), so that the round
+// trip overlaps the next batch's loads
+RT_DEV unsigned long long wavePendingIssue(const WaveQ& Q, long long delta)
+{
+    return atomicAdd((unsigned long long*)Q.ctl, (unsigned long long)delta) + (unsigned long long)delta;
+}
+RT_DEV void wavePendingCheck(const WaveQ& Q, unsigned long long now)
+{
+    if (now == ((unsigned long long)gridDim.x << 32)) {
+        waveRaiseDone(Q);
+    } else if (Q.switchBelow > 0 && (now >> 32) == (unsigned long long)gridDim.x && (unsigned)now < (unsigned)Q.switchBelow) {
+        if (ldRelaxedGpu((const unsigned*)Q.ctl + WCTL_CLOSEAT) == 0u) {
+            const int old = atomicOr(Q.ctl + WCTL_TAIL, WAVE_CLOSED);
+            if (!(old & WAVE_CLOSED)) stRelaxedGpu((unsigned*)Q.ctl + WCTL_CLOSEAT, (unsigned)old + 1u);
+        }
+    }
+}
 // warp-converged and warp-uniform (phase C reads the other CTAs' records through L2 afterwards)
 RT_DEV bool waveDone(const WaveQ& Q)
 {
@@ -252,6 +272,25 @@ RT_DEV void waveIdle(const WaveQ& Q, unsigned long long t0, int& idlePolls)
     }
 }
 
+// optional timeline of the frame (CGRT_WAVE_TRACE=1): a few finish warps sample the counters once per 4.096 us bucket
+RT_DEV void waveTraceSample(const WaveQ& Q, int& lastBucket)
+{
+    if (Q.trace == nullptr || (blockIdx.x & 15) != 0 || (threadIdx.x & 127) != 0) return;
+    const unsigned t0 = ldRelaxedGpu((const unsigned*)Q.ctl + WCTL_T0);
+    const int bucket = (int)(((unsigned)globalTimerNs() - t0) >> 12);
+    if (bucket == lastBucket || bucket < 0 || bucket >= WAVE_TRACE_SAMPLES) return;
+    lastBucket = bucket;
+    int* o = Q.trace + 8 * bucket;
+    o[1] = (int)ldRelaxedGpu((const unsigned*)Q.ctl + WCTL_PENDING);
+    o[2] = (int)ldRelaxedGpu((const unsigned*)Q.ctl + WCTL_HEAD);
+    o[3] = (int)ldRelaxedGpu((const unsigned*)Q.ctl + WCTL_TAIL);
+    o[4] = (int)ldRelaxedGpu((const unsigned*)Q.ctl + WCTL_FHEAD);
+    o[5] = (int)ldRelaxedGpu((const unsigned*)Q.ctl + WCTL_FTAIL);
+    o[6] = (int)ldRelaxedGpu((const unsigned*)Q.ctl + WCTL_HEAD2);
+    o[7] = (int)ldRelaxedGpu((const unsigned*)Q.ctl + WCTL_TAIL2);
+    o[0] = 1;
+}
+
 // ---- FINISH warps ---------------------------------------------------------------------------------------------------------------
 // Every lane holds a ticket of the finish queue; tickets are handed out in order, so the 32 tickets of a warp are served by 32
 // consecutively finished searches - under load within a poll interval, and the batch then runs fully converged. A partly
@@ -269,26 +308,48 @@ RT_DEV void waveFinishLoop(const DevScene& S, const FrameParams& P, const float4
     int ftk = -1;        // ticket of the finish queue held by this lane
     int waited = 0, idlePolls = 0;
     bool closedSeen = false; // lane 0: this warp has seen the ray queue's change-over
+    int traceBucket = -1;
+    // round trips to L2 are what a batch costs (the finish warps are latency-bound), so: the tickets that replace a batch's are
+    // claimed while the batch is processed (nextBase), the counter decrement of a batch is looked at one trip later (pendNow),
+    // and the cheap look before the full poll is skipped while every poll finds a full batch (busy)
+    int nextBase = 0, nextCount = 0; // lane 0 issued the claim; everyone knows the count
+    unsigned long long pendNow = 0ull;
+    bool havePend = false, busy = false;
+    {
+        const int base = waveClaim(Q, WCTL_FHEAD, 32);
+        ftk = base + lane;
+    }
     while (true) {
-        // ---- tickets for the lanes that have none
-        const unsigned noneMask = __ballot_sync(0xffffffffu, ftk < 0);
-        if (noneMask != 0u) {
-            const int base = waveClaim(Q, WCTL_FHEAD, __popc(noneMask));
+        waveTraceSample(Q, traceBucket);
+        // ---- the tickets claimed during the last batch go to the lanes that have none
+        if (nextCount) {
+            const unsigned noneMask = __ballot_sync(0xffffffffu, ftk < 0);
+            const int base = __shfl_sync(0xffffffffu, nextBase, 0);
             if (ftk < 0) ftk = base + __popc(noneMask & ltMask);
+            nextCount = 0;
         }
         // ---- which of the warp's tickets have been served? (a cheap look first: see wavePeekRay)
         int tk = -1;
         float4 res = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        const bool ready = (waited > 0 || wavePeekFin(Q, true, ftk)) && waveLoadFin(Q, ftk, tk, res);
+        const bool ready = (busy || waited > 0 || wavePeekFin(Q, true, ftk)) && waveLoadFin(Q, ftk, tk, res);
+        if (havePend) { // (lane 0) the result of the last batch's decrement: frame complete? change-over due?
+            wavePendingCheck(Q, pendNow);
+            havePend = false;
+        }
         const unsigned readyMask = __ballot_sync(0xffffffffu, ready);
         if (readyMask == 0u) {
-            if (waveDone(Q)) return;
+            busy = false;
+            if (waveDone(Q)) break;
             waveIdle(Q, t0, idlePolls);
             continue;
         }
         idlePolls = 0;
         if (readyMask != 0xffffffffu && ++waited < CGRT_WAVE_FIN_WAIT) continue; // give the rest of the batch a moment
+        busy = readyMask == 0xffffffffu && waited == 0;
         waited = 0;
+        // replacement tickets for the lanes of this batch: issued now, used on the next trip
+        nextCount = __popc(readyMask);
+        if (lane == 0) nextBase = atomicAdd(Q.ctl + WCTL_FHEAD, nextCount);
         // ---- the batch: one lane per finished search
         const int n = __popc(readyMask);
         bool hit = false, bounce = false, replayC = false, replayS = false;
@@ -347,7 +408,7 @@ RT_DEV void waveFinishLoop(const DevScene& S, const FrameParams& P, const float4
         int base = 0;
         unsigned tagBits = 0u;
         if (lane == 0 && totS + totB > 0) {
-            wavePending(Q, (long long)(totS + totB)); // the children are counted before they can become visible
+            wavePendingAdd(Q, totS + totB); // the children are counted before they can become visible
             base = waveReserve(Q, totS + totB, closedSeen, tagBits);
         }
         base = __shfl_sync(0xffffffffu, base, 0);
@@ -367,12 +428,17 @@ RT_DEV void waveFinishLoop(const DevScene& S, const FrameParams& P, const float4
             reflectionRayOf(pointOn, rd, nn, org, dir, tIn);
             waveStoreRay(Q, base + totS + bIncl - 1, tagBits, org, dir, tIn, ((level + 1) << WAVE_SLOT_BITS) | slot);
         }
-        // (the children are visible as soon as their records are complete; no flag, no fence.) What this batch wrote for phase C
-        // - hit records, lit flags, black pixels - must be visible GPU-wide before the counter decrement that may complete the frame
-        waveRelease(Q);
-        __syncwarp();
-        if (lane == 0) wavePending(Q, -(long long)n);
+        // (the children are visible as soon as their records are complete; no flag, no fence. What the batch wrote for phase C -
+        // hit records, lit flags, black pixels - is released once, when this warp leaves the loop.)
+        if (lane == 0) {
+            pendNow = wavePendingIssue(Q, -(long long)n);
+            havePend = true;
+        }
     }
+    // everything this warp wrote for phase C is visible GPU-wide before it reports out; phase C starts when every finish warp has
+    waveRelease(Q);
+    __syncwarp();
+    if (lane == 0) atomicAdd(Q.ctl + WCTL_FINEXIT, 1);
 }
 
 // ---- SEARCH warps, LANE form: one lane per ray (the loop of k_trace on tickets) -------------------------------------------
@@ -681,6 +747,7 @@ __global__ void __launch_bounds__(128, CGRT_WAVE_MINBLOCKS) k_wave(DevScene S, c
     const FrameParams& P = Psh;
     const int lane = threadIdx.x & 31;
     const unsigned long long t0 = globalTimerNs();
+    if (threadIdx.x == 0 && Q.trace != nullptr) atomicCAS((unsigned*)Q.ctl + WCTL_T0, 0u, (unsigned)t0 | 1u);
 
     // ---- phase A: primary rays (level 0). Rays that cannot enter the tree are black (trace(): miss, main.cpp:288-294)
     {
@@ -731,6 +798,7 @@ __global__ void __launch_bounds__(128, CGRT_WAVE_MINBLOCKS) k_wave(DevScene S, c
 
     // ---- phase B: one role per SM (see the header): finish warps on every Q.finEvery-th SM, search warps on the others
     if (smId() % (unsigned)Q.finEvery == 0u) {
+        if ((threadIdx.x & 31) == 0) atomicAdd(Q.ctl + WCTL_FINCOUNT, 1);
         waveFinishLoop(S, P, lights, Q, B, tileSeq, fb, sh, t0);
     } else if (Q.mode == 2) {
         waveGroupLoop(S, Q, sh, t0, WCTL_HEAD, 0, Q.seq);
@@ -739,6 +807,19 @@ __global__ void __launch_bounds__(128, CGRT_WAVE_MINBLOCKS) k_wave(DevScene S, c
         waveGroupLoop(S, Q, sh, t0, WCTL_HEAD2, closeAt, Q.seq | WAVE_TAG2);
     }
 
+    // Finish warps register before they process anything and release their writes when they leave their loop; phase C waits
+    // until every registered finish warp has left (one thread per CTA looks, on a line of its own)
+    if (threadIdx.x == 0) {
+        int polls = 0;
+        while (ldRelaxedGpu((const unsigned*)Q.ctl + WCTL_FINCOUNT) != ldRelaxedGpu((const unsigned*)Q.ctl + WCTL_FINEXIT)) {
+            __nanosleep(200);
+            if ((++polls & 1023) == 0 && globalTimerNs() - t0 > Q.timeoutNs) {
+                atomicExch(Q.ctl + WCTL_ERR, 1);
+                break;
+            }
+        }
+    }
+    __syncthreads();
     // ---- phase C: shading(), shade() per pixel slot (the hit records / lit flags of other CTAs were released before the done
     // flag was raised; they are read through L2)
     {
