@@ -959,16 +959,20 @@ static bool useRounds(const cgrt_scene* s, const FrameParams& P)
     return flags < ((uint64_t)1 << 30);
 }
 
-// the persistent wavefront (one kernel per frame) is the production pipeline wherever the round pipeline applies;
-// CGRT_PIPELINE=rounds selects the round pipeline (one kernel per level and chain) for A/B runs
+// Two pipelines render the same frame bit for bit; which one runs is a question of speed only (CGRT_PIPELINE=wave|rounds forces
+// one for A/B runs). The persistent wavefront (k_wave, one kernel per frame, levels overlapped) wins where the frame is a chain
+// of dependent levels or small: trace limit >= 3, or a share of fewer than 400 K pixel slots (C3 1080p 1.35 vs 1.40 ms, its 1/8
+// share 0.50 vs 0.75 ms, C1 0.13 vs 0.17 ms). The round pipeline (one flat kernel per level) wins on large shallow frames whose
+// cost is streaming pixels and finishing many cheap rays (C2 1080p limit 1: 0.31 vs 0.40 ms; C5 2160p limit 2: 0.89 vs 1.25 ms).
 static bool useWave(const cgrt_scene* s, const FrameParams& P)
 {
-    static int pref = -1;
+    static int pref = -1; // 0 rounds, 1 wave, 2 automatic
     if (pref < 0) {
         const char* e = getenv("CGRT_PIPELINE");
-        pref = (e && std::strcmp(e, "rounds") == 0) ? 0 : 1;
+        pref = (e && std::strcmp(e, "rounds") == 0) ? 0 : ((e && std::strcmp(e, "wave") == 0) ? 1 : 2);
     }
-    return pref == 1 && useRounds(s, P) && P.nSlots < (1 << 26) && P.traceLimit <= 16; // ray record: level << 26 | slot
+    if (pref == 0 || !useRounds(s, P) || P.nSlots >= (1 << 26) || P.traceLimit > 16) return false; // ray record: level << 26 | slot
+    return pref == 1 || P.traceLimit >= 3 || P.nSlots < 400000;
 }
 // tickets the queue must hold: every slot can cast one closest-hit ray and one shadow ray per light at every level; plus the
 // tickets idle lanes hold beyond the last ray (one per resident lane at most)
@@ -977,12 +981,12 @@ static size_t waveTicketCap(const FrameParams& P)
     return (size_t)std::max(P.nSlots, 1) * std::max(P.traceLimit, 1) * (1 + (size_t)std::max(P.nLights, 0)) + ((size_t)1 << 19);
 }
 
-// scheduling knobs / watchdog of the persistent wavefront (CGRT_WAVE="mode=0,group_below=600000,switch=100000,fin=5,timeout_ms=4000"; they
+// scheduling knobs / watchdog of the persistent wavefront (CGRT_WAVE="mode=0,group_below=400000,switch=0,fin=0,timeout_ms=4000"; 0 = automatic; they
 // change speed only, never results). mode 0: the search form follows the size of this rank's share of the frame - one lane per
 // ray for large shares (throughput), eight lanes per ray for small ones (latency)
-static void waveTuning(WaveQ& Q, int nSlots)
+static void waveTuning(WaveQ& Q, int nSlots, int nLights)
 {
-    static int mode = 0, groupBelow = 600000, fin = 5, timeoutMs = 4000, switchBelow = 100000;
+    static int mode = 0, groupBelow = 400000, fin = 0, timeoutMs = 4000, switchBelow = 0;
     static bool loaded = false;
     if (!loaded) {
         loaded = true;
@@ -1008,8 +1012,12 @@ static void waveTuning(WaveQ& Q, int nSlots)
         }
     }
     Q.mode = mode == 1 || mode == 2 ? mode : (nSlots < groupBelow ? 2 : 1);
-    Q.finEvery = std::max(fin, 2);
-    Q.switchBelow = Q.mode == 2 ? 0 : std::max(switchBelow, 0); // (GROUP-only frames never change over)
+    // share of the SMs that run the finish warps: every hit costs one hit epilogue plus one shadow ray to emit and to finish per
+    // light (measured: C3, 1 light, 1/5 of the SMs; C5, 3 lights, 1/3)
+    Q.finEvery = fin > 0 ? std::max(fin, 2) : (nLights >= 3 ? 3 : (nLights == 2 ? 4 : 5));
+    // (GROUP-only frames never change over; measured on the C3 frame and its 1/2, 1/4 shares: 100 K in flight for a whole 1080p
+    // frame, 60 K for smaller shares)
+    Q.switchBelow = Q.mode == 2 ? 0 : (switchBelow > 0 ? switchBelow : (nSlots >= 1500000 ? 100000 : 60000));
     Q.timeoutNs = (unsigned long long)std::max(timeoutMs, 1) * 1000000ull;
 }
 
@@ -1202,7 +1210,7 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
             CK(cudaMemsetAsync(s->waveTrace.p, 0, (size_t)WAVE_TRACE_SAMPLES * 8 * sizeof(int), st));
             Q.trace = s->waveTrace.p;
         }
-        waveTuning(Q, P.nSlots);
+        waveTuning(Q, P.nSlots, P.nLights);
         launches = launchWavePipeline(s->dev, (const FrameParams*)s->dParamBlock.p, P,
                                       (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), RB, Q, dSeq, d_out,
                                       s->di.numSMs, &s->trace, st);

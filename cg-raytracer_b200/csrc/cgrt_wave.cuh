@@ -265,7 +265,7 @@ RT_DEV bool waveDone(const WaveQ& Q)
 // bug must not hang the GPU)
 RT_DEV void waveIdle(const WaveQ& Q, unsigned long long t0, int& idlePolls)
 {
-    __nanosleep(idlePolls < 4 ? 100 : (idlePolls < 12 ? 300 : (idlePolls < 40 ? 800 : 2000)));
+    __nanosleep(idlePolls < 8 ? 100 : (idlePolls < 32 ? 250 : (idlePolls < 128 ? 500 : 1000)));
     if ((++idlePolls & 63) == 0 && (threadIdx.x & 31) == 0 && globalTimerNs() - t0 > Q.timeoutNs) {
         atomicExch(Q.ctl + WCTL_ERR, 1);
         waveRaiseDone(Q);
@@ -344,7 +344,8 @@ RT_DEV void waveFinishLoop(const DevScene& S, const FrameParams& P, const float4
             continue;
         }
         idlePolls = 0;
-        if (readyMask != 0xffffffffu && ++waited < CGRT_WAVE_FIN_WAIT) continue; // give the rest of the batch a moment
+        // under load the rest of a partly served batch arrives within a poll or two: wait for it; otherwise finish at once
+        if (readyMask != 0xffffffffu && busy && ++waited < CGRT_WAVE_FIN_WAIT) continue;
         busy = readyMask == 0xffffffffu && waited == 0;
         waited = 0;
         // replacement tickets for the lanes of this batch: issued now, used on the next trip

@@ -52,10 +52,11 @@ def worker():
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "worker":
         return worker()
-    runs = [("rounds", {"CGRT_PIPELINE": "rounds"}), ("wave auto", {"CGRT_WAVE": "mode=0"}), ("wave lane", {"CGRT_WAVE": "mode=1,switch=0"}),
-            ("wave group", {"CGRT_WAVE": "mode=2"})]
+    runs = [("rounds", {"CGRT_PIPELINE": "rounds"}), ("wave auto", {"CGRT_PIPELINE": "wave", "CGRT_WAVE": "mode=0"}),
+            ("wave lane", {"CGRT_PIPELINE": "wave", "CGRT_WAVE": "mode=1,switch=0"}), ("wave group", {"CGRT_PIPELINE": "wave", "CGRT_WAVE": "mode=2"}),
+            ("automatic", {})]
     for extra in filter(None, os.environ.get("WAVE_CHECK_EXTRA", "").split(";")):  # e.g. "mode=1,fin=12;mode=2,fin=12"
-        runs.append((f"wave {extra}", {"CGRT_WAVE": extra}))
+        runs.append((f"wave {extra}", {"CGRT_PIPELINE": "wave", "CGRT_WAVE": extra}))
     res = {}
     for label, env in runs:
         e = dict(os.environ)
