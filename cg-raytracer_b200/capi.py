@@ -324,12 +324,12 @@ class Scene:
         check(self.lib.cgrt_render(self.h, C.byref(cam), C.byref(p), _vp(rgb), C.byref(st)))
         return rgb, st.as_dict()
 
-    def render_effects(self, cam, W, H, trace_limit=2, antialias=False, motion_blur=False):
-        """renderRayTracing's anti-aliasing / motion-blur passes (cgrt_render_effects): (rgb[H,W,3], stats dict)."""
+    def render_effects(self, cam, W, H, trace_limit=2, antialias=False, motion_blur=False, bloom=False):
+        """renderRayTracing's anti-aliasing / motion-blur / bloom passes (cgrt_render_effects): (rgb[H,W,3], stats dict)."""
         p = render_params(W, H, trace_limit)
         rgb = np.zeros((H, W, 3), np.float32)
         st = RenderStats()
-        check(self.lib.cgrt_render_effects(self.h, C.byref(cam), C.byref(p), (1 if antialias else 0) | (2 if motion_blur else 0),
+        check(self.lib.cgrt_render_effects(self.h, C.byref(cam), C.byref(p), (1 if antialias else 0) | (2 if motion_blur else 0) | (4 if bloom else 0),
                                            _vp(rgb), C.byref(st)))
         return rgb, st.as_dict()
 

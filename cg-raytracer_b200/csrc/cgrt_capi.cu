@@ -228,7 +228,10 @@ static void fastTreeSelfCheck(const std::vector<MeshView>& views, const BuiltBVH
 struct cgrt_scene {
     int device = 0;
     DeviceInfo di;
-    std::mutex mu;
+    std::mutex mu;    // renders: the per-scene queues and the parameter ring are shared by the frames of one scene
+    std::mutex hostMu; // the host-pointer render forms (cgrt_render, _effects, _submit): one frame of a scene at a time through its
+                       // internal frame buffer and stream
+    std::mutex devMu; // the pointer table `dev` (queries take a snapshot; set_spheres replaces the sphere entries)
     cudaStream_t stream = nullptr;
 
     BuiltBVH bvh;
@@ -268,7 +271,8 @@ struct cgrt_scene {
     cudaStream_t copyStream = nullptr;
     cudaEvent_t renderDone[2] = {nullptr, nullptr}, copyDone[2] = {nullptr, nullptr};
     DevBuf<float> streamFrame[2];
-    DevBuf<float> fxA, fxB; // cgrt_render_effects: supersampled / shifted frame, accumulator
+    DevBuf<float> fxA, fxB, fxC, fxM; // cgrt_render_effects: supersampled / shifted frame, accumulator, bloom output, bloom matrix
+    DevBuf<int> fxProg;               // bloom: finished columns per image row
     bool slotUsed[2] = {false, false};
     uint64_t submitSeq = 0;
     int64_t fastStats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -283,6 +287,7 @@ struct cgrt_scene {
     uint64_t primaryPixels = 0; // pixels of this rank inside the image
     int tileKey[6] = {0, 0, 0, 0, 0, 0};
     DevBuf<float> frame; // internal framebuffer for the host-pointer render
+    DevBuf<float> zeroFrame; // all zeros: source of the copy-engine transfer that blanks a page-locked destination while it renders
     float* hFramePinned = nullptr;
     size_t hFramePinnedFloats = 0;
 
@@ -331,7 +336,8 @@ static void destroyScene(cgrt_scene* s)
         for (int k = 0; k < 2; k++) { cudaEventDestroy(s->renderDone[k]); cudaEventDestroy(s->copyDone[k]); }
     }
     s->streamFrame[0].release(); s->streamFrame[1].release();
-    s->fxA.release(); s->fxB.release();
+    s->zeroFrame.release();
+    s->fxA.release(); s->fxB.release(); s->fxC.release(); s->fxM.release(); s->fxProg.release();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -631,6 +637,7 @@ int cgrt_scene_set_spheres(cgrt_scene* s, const float* spheres, int32_t n)
 {
     if (!s || n < 0 || (n > 0 && !spheres)) return fail(CGRT_ERR_INVALID, "bad spheres");
     std::lock_guard<std::mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lk2(s->devMu);
     int rc = useSceneDevice(s);
     if (rc) return rc;
     CK(cudaDeviceSynchronize());
@@ -676,8 +683,9 @@ int cgrt_intersect_closest_device(cgrt_scene* s, const cgrt_ray* d_rays, size_t 
     int rc = useSceneDevice(s);
     if (rc) return rc;
     DevScene S;
-    {
-        std::lock_guard<std::mutex> lk(s->mu);
+    { // (the only shared state on the query path: a snapshot of the scene's pointer table, taken under the lock that
+      // cgrt_scene_set_spheres holds while it replaces the sphere list; renders hold it for the enqueue of a frame)
+        std::lock_guard<std::mutex> lk(s->devMu);
         S = s->dev;
     }
     launchClosestBatch(S, (const float4*)d_rays, n, (float4*)d_hits, d_counts, s->di.numSMs, (cudaStream_t)stream);
@@ -693,7 +701,7 @@ int cgrt_intersect_any_device(cgrt_scene* s, const cgrt_ray* d_rays, const float
     if (rc) return rc;
     DevScene S;
     {
-        std::lock_guard<std::mutex> lk(s->mu);
+        std::lock_guard<std::mutex> lk(s->devMu);
         S = s->dev;
     }
     launchAnyBatch(S, (const float4*)d_rays, d_max_dist, eps, n, d_occluded, s->di.numSMs, (cudaStream_t)stream);
@@ -701,7 +709,56 @@ int cgrt_intersect_any_device(cgrt_scene* s, const cgrt_ray* d_rays, const float
     return CGRT_OK;
 }
 
-// scratch helper for the host-pointer forms: device copies of inputs/outputs, freed on scope exit
+// Scratch of the host-pointer query forms: per HOST THREAD and device, kept between calls - a stream and three growable device
+// buffers. The reference's intersect() is called concurrently from every OpenMP thread (src/main.cpp:653-656 -> :276, :115):
+// here the threads share nothing on the query path (no scene-wide lock, no per-call cudaMalloc / cudaFree - cudaFree
+// synchronises the whole device - no stream creation), so their copies and kernels overlap on the device.
+struct ThreadScratch {
+    int device = -1;
+    cudaStream_t st = nullptr;
+    void* buf[3] = {nullptr, nullptr, nullptr};
+    size_t cap[3] = {0, 0, 0};
+    ~ThreadScratch() { release(); }
+    void release()
+    {
+        if (device < 0) return;
+        if (cudaSetDevice(device) == cudaSuccess) { // (at thread exit the context may already be gone: errors are ignored)
+            for (int k = 0; k < 3; k++)
+                if (buf[k]) cudaFree(buf[k]);
+            if (st) cudaStreamDestroy(st);
+        }
+        cudaGetLastError();
+        for (int k = 0; k < 3; k++) { buf[k] = nullptr; cap[k] = 0; }
+        st = nullptr;
+        device = -1;
+    }
+    int use(int dev)
+    {
+        if (device == dev && st) return CGRT_OK;
+        release();
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        device = dev;
+        return CGRT_OK;
+    }
+    int get(int k, size_t bytes, void** out)
+    {
+        if (bytes > cap[k]) {
+            if (buf[k]) CK(cudaFree(buf[k]));
+            buf[k] = nullptr;
+            cap[k] = 0;
+            const size_t want = std::max(bytes + bytes / 4, (size_t)4096);
+            cudaError_t e = cudaMalloc(&buf[k], want);
+            if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? CGRT_ERR_OOM : CGRT_ERR_CUDA,
+                                              std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+            cap[k] = want;
+        }
+        *out = buf[k];
+        return CGRT_OK;
+    }
+};
+static thread_local ThreadScratch g_scratch;
+
+// scratch helper for the remaining host-pointer forms (brute force, unit predicates): freed on scope exit
 struct Scratch {
     std::vector<void*> ptrs;
     cudaStream_t st = nullptr;
@@ -735,12 +792,12 @@ int cgrt_intersect_closest(cgrt_scene* s, const cgrt_ray* rays, size_t n, cgrt_h
     if (!s || (n && (!rays || !hits))) return fail(CGRT_ERR_INVALID, "null argument");
     RC(useSceneDevice(s));
     if (n == 0) return CGRT_OK;
-    Scratch sc;
-    RC(sc.stream());
+    ThreadScratch& sc = g_scratch;
+    RC(sc.use(s->device));
     void *dR, *dH, *dC = nullptr;
-    RC(sc.alloc(&dR, n * sizeof(cgrt_ray)));
-    RC(sc.alloc(&dH, n * sizeof(cgrt_hit)));
-    if (counts) RC(sc.alloc(&dC, n * 2 * sizeof(uint32_t)));
+    RC(sc.get(0, n * sizeof(cgrt_ray), &dR));
+    RC(sc.get(1, n * sizeof(cgrt_hit), &dH));
+    if (counts) RC(sc.get(2, n * 2 * sizeof(uint32_t), &dC));
     CK(cudaMemcpyAsync(dR, rays, n * sizeof(cgrt_ray), cudaMemcpyHostToDevice, sc.st));
     RC(cgrt_intersect_closest_device(s, (const cgrt_ray*)dR, n, (cgrt_hit*)dH, (uint32_t*)dC, sc.st));
     CK(cudaMemcpyAsync(hits, dH, n * sizeof(cgrt_hit), cudaMemcpyDeviceToHost, sc.st));
@@ -754,12 +811,12 @@ int cgrt_intersect_any(cgrt_scene* s, const cgrt_ray* rays, const float* max_dis
     if (!s || (n && (!rays || !max_dist || !occluded))) return fail(CGRT_ERR_INVALID, "null argument");
     RC(useSceneDevice(s));
     if (n == 0) return CGRT_OK;
-    Scratch sc;
-    RC(sc.stream());
+    ThreadScratch& sc = g_scratch;
+    RC(sc.use(s->device));
     void *dR, *dM, *dO;
-    RC(sc.alloc(&dR, n * sizeof(cgrt_ray)));
-    RC(sc.alloc(&dM, n * sizeof(float)));
-    RC(sc.alloc(&dO, n));
+    RC(sc.get(0, n * sizeof(cgrt_ray), &dR));
+    RC(sc.get(1, n * sizeof(float), &dM));
+    RC(sc.get(2, n, &dO));
     CK(cudaMemcpyAsync(dR, rays, n * sizeof(cgrt_ray), cudaMemcpyHostToDevice, sc.st));
     CK(cudaMemcpyAsync(dM, max_dist, n * sizeof(float), cudaMemcpyHostToDevice, sc.st));
     RC(cgrt_intersect_any_device(s, (const cgrt_ray*)dR, (const float*)dM, eps, n, (uint8_t*)dO, sc.st));
@@ -1378,12 +1435,54 @@ int cgrt_render(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params*
         return fail(CGRT_ERR_INVALID, "CGRT_RENDER_SCREEN_LAYOUT is a device-pointer mode (cgrt_render_device)");
     const size_t frameFloats = (size_t)p->width * p->height * 3;
     const size_t outFloats = cgrt_tile_buffer_floats(p);
+    std::lock_guard<std::mutex> hostLock(s->hostMu);
     {
         std::lock_guard<std::mutex> lk(s->mu);
         RC(s->frame.ensure(std::max(frameFloats, outFloats)));
     }
+    // Overlapped delivery (whole frame, page-locked destination, a pipeline that keeps pathDepth per pixel slot): the caller's
+    // frame is blanked by a copy-engine transfer of zeros on a second stream WHILE the frame renders - most pixels of these
+    // scenes are black - and the bounding box of the pixels the shading pass coloured is then written straight into it by a
+    // small kernel (zero-copy stores in full 128-byte runs). The synchronous call costs the device time plus that last step instead of the device time plus a
+    // 25 MB copy.
+    float* dHost = nullptr;
+    bool overlapped = false;
+    if (p->world == 1 && p->trace_limit > 0 && s->dev.fastRoot != 0u && !(p->flags & CGRT_RENDER_COUNT) && !getenv("CGRT_PLAIN_D2H")) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, rgb) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            dHost = (float*)at.devicePointer;
+        else
+            cudaGetLastError();
+    }
+    if (dHost) {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!s->copyStream) {
+            CK(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; k++) {
+                CK(cudaEventCreateWithFlags(&s->renderDone[k], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&s->copyDone[k], cudaEventDisableTiming));
+            }
+        }
+        // (a copy-engine transfer: a memset kernel would queue behind the persistent render kernel, which owns every SM)
+        if (!s->zeroFrame.p || s->zeroFrame.n < frameFloats) {
+            RC(s->zeroFrame.ensure(frameFloats));
+            CK(cudaMemset(s->zeroFrame.p, 0, frameFloats * sizeof(float)));
+        }
+        CK(cudaMemcpyAsync(rgb, s->zeroFrame.p, frameFloats * sizeof(float), cudaMemcpyDeviceToHost, s->copyStream));
+        CK(cudaEventRecord(s->copyDone[0], s->copyStream));
+        overlapped = true;
+    }
     RC(cgrt_render_device(s, cam, p, s->frame.p, s->stream));
-    if (p->world == 1) {
+    if (overlapped && !(s->lastPipeline == 2 || s->lastPipeline == 3)) { // (path pipeline: no per-slot depth) plain copy after all
+        CK(cudaStreamSynchronize(s->copyStream));
+        overlapped = false;
+    }
+    if (overlapped) {
+        CK(cudaStreamWaitEvent(s->stream, s->copyDone[0], 0));
+        launchDeliverBox(s->counts.p + CGRT_CNT_BBOX, p->width, p->height, s->frame.p, dHost, s->di.numSMs, s->stream);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(s->stream));
+    } else if (p->world == 1) {
         CK(cudaMemcpyAsync(rgb, s->frame.p, frameFloats * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
     } else {
@@ -1417,9 +1516,13 @@ int cgrt_render_effects(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
     if (!s || !cam || !rgb) return fail(CGRT_ERR_INVALID, "null argument");
     RC(checkRenderParams(p));
     if (p->world != 1) return fail(CGRT_ERR_INVALID, "cgrt_render_effects renders whole frames (world == 1)");
-    if (effects & ~(CGRT_EFFECT_ANTIALIAS | CGRT_EFFECT_MOTION_BLUR)) return fail(CGRT_ERR_INVALID, "unknown effect bits");
+    if (effects & ~(CGRT_EFFECT_ANTIALIAS | CGRT_EFFECT_MOTION_BLUR | CGRT_EFFECT_BLOOM)) return fail(CGRT_ERR_INVALID, "unknown effect bits");
+    if ((effects & CGRT_EFFECT_BLOOM) && (effects & CGRT_EFFECT_ANTIALIAS))
+        return fail(CGRT_ERR_INVALID, "bloom with anti-aliasing is not offered: the reference's combination thresholds on an uninitialised "
+                                      "accumulator (src/main.cpp:663-687)");
     if (!effects) return cgrt_render(s, cam, p, rgb, stats);
     RC(useSceneDevice(s));
+    std::lock_guard<std::mutex> hostLock(s->hostMu);
     const int W = p->width, H = p->height;
     const size_t n = (size_t)W * H * 3;
     cudaStream_t st = s->stream;
@@ -1430,18 +1533,48 @@ int cgrt_render_effects(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
         total.kernel_launches += a.kernel_launches; total.device_ms += a.device_ms;
         total.replayed_closest += a.replayed_closest; total.replayed_shadow += a.replayed_shadow;
     };
+    bool haveBloom = false; // fxC = bloom output of the un-shifted frame, fxA = that frame
+    if (effects & CGRT_EFFECT_BLOOM) {
+        // the pixel loop's frame, then bloomEffect (main.cpp:698-705, 586-628) on the device
+        if ((int64_t)H > (int64_t)s->di.numSMs * 16 * 4) return fail(CGRT_ERR_INVALID, "frame too tall for the bloom pass");
+        RC(s->fxA.ensure(n));
+        RC(s->fxC.ensure(n));
+        RC(s->fxM.ensure(n));
+        RC(s->fxProg.ensure((size_t)H));
+        RC(cgrt_render_device(s, cam, p, s->fxA.p, st));
+        launchBloom(s->fxA.p, W, H, s->fxM.p, s->fxProg.p, s->fxC.p, s->di.numSMs, st);
+        CK(cudaGetLastError());
+        if (stats) {
+            cgrt_render_stats one;
+            RC(cgrt_render_collect_stats(s, &one));
+            addStats(one);
+            total.kernel_launches += 2;
+        }
+        haveBloom = true;
+        if (!(effects & CGRT_EFFECT_MOTION_BLUR)) {
+            CK(cudaMemcpyAsync(rgb, s->fxC.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (stats) *stats = total;
+            return CGRT_OK;
+        }
+    }
     if (effects & CGRT_EFFECT_MOTION_BLUR) {
         // blurEffect runs after the pixel loop and overwrites every pixel (main.cpp:716-719, :581), whatever the loop drew
         static const double shift[15] = {0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08, 0.09, 0.10, 0.11, 0.12, 0.13, 0.14, 0.15};
         RC(s->fxA.ensure(n));
         RC(s->fxB.ensure(n));
+        if (haveBloom) { // with bloom, matrixPixels enters blurEffect as colour + (bloom matrix + colour) (main.cpp:700, :622)
+            launchAccumulate(s->fxB.p, s->fxA.p, n, true, st);
+            launchAccumulate(s->fxB.p, s->fxC.p, n, false, st);
+            total.kernel_launches += 2;
+        }
         for (int k = 0; k < 15; k++) {
             cgrt_camera c = *cam;
             c.look_at[0] = (float)shift[k]; // cameraNew.setLookAt(glm::vec3(0.0k, 0, 0)), main.cpp:344-568
             c.look_at[1] = 0.0f;
             c.look_at[2] = 0.0f;
             RC(cgrt_render_device(s, &c, p, s->fxA.p, st));
-            launchAccumulate(s->fxB.p, s->fxA.p, n, k == 0, st);
+            launchAccumulate(s->fxB.p, s->fxA.p, n, k == 0 && !haveBloom, st);
             if (stats) {
                 cgrt_render_stats one;
                 RC(cgrt_render_collect_stats(s, &one));
@@ -1483,6 +1616,7 @@ int cgrt_render_submit(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
     RC(checkRenderParams(p));
     if (p->world != 1) return fail(CGRT_ERR_INVALID, "cgrt_render_submit renders whole frames (world == 1)");
     RC(useSceneDevice(s));
+    std::lock_guard<std::mutex> hostLock(s->hostMu);
     const size_t frameFloats = (size_t)p->width * p->height * 3;
     int slot;
     {

@@ -278,6 +278,20 @@ RT_DEV int warpPush(int* counter, bool want)
     return want ? base + __popc(mask & ((1u << lane) - 1u)) : -1;
 }
 
+// bounding box of the coloured pixels (CGRT_CNT_BBOX): one atomic per warp and bound
+RT_DEV void noteColoured(int* bbox, bool wrote, int x, int row, int W, int H)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, wrote);
+    if (m == 0u) return;
+    const int a = __reduce_max_sync(0xffffffffu, wrote ? x + 1 : 0), b = __reduce_max_sync(0xffffffffu, wrote ? row + 1 : 0);
+    const int c = __reduce_max_sync(0xffffffffu, wrote ? W - x : 0), d = __reduce_max_sync(0xffffffffu, wrote ? H - row : 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (a > bbox[0]) atomicMax(bbox + 0, a);
+        if (b > bbox[1]) atomicMax(bbox + 1, b);
+        if (c > bbox[2]) atomicMax(bbox + 2, c);
+        if (d > bbox[3]) atomicMax(bbox + 3, d);
+    }
+}
 RT_DEV void storeRGB(float* fb, int idx, const V3& c)
 {
     fb[3 * (size_t)idx + 0] = c.x;
@@ -1612,20 +1626,26 @@ __global__ void __launch_bounds__(128) k_shade_slots(DevScene S, const FramePara
 {
     const FrameParams P = *Pp;
     const int nL = P.nLights;
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < P.nSlots; slot += gridDim.x * blockDim.x) {
-        const int depth = B.pathDepth[slot];
-        if (depth <= 0) continue; // the pixel is already final (black)
-        V3 direct[CGRT_MAX_LEVELS], ksv[CGRT_MAX_LEVELS];
-        for (int k = 0; k < depth; k++) {
-            const int rec = slot * B.levels + k;
-            const float4* r = B.hitRec + 3 * (size_t)rec;
-            direct[k] = directColour(S, lights, nL, r[0], r[1], r[2], B.lit + (size_t)rec * nL, ksv[k]);
+    for (int base = blockIdx.x * blockDim.x; base < P.nSlots; base += gridDim.x * blockDim.x) {
+        const int slot = base + threadIdx.x;
+        const int depth = slot < P.nSlots ? B.pathDepth[slot] : 0;
+        bool wrote = false;
+        int x = 0, y = 0;
+        if (depth > 0) { // (else the pixel is already final: black)
+            V3 direct[CGRT_MAX_LEVELS], ksv[CGRT_MAX_LEVELS];
+            for (int k = 0; k < depth; k++) {
+                const int rec = slot * B.levels + k;
+                const float4* r = B.hitRec + 3 * (size_t)rec;
+                direct[k] = directColour(S, lights, nL, r[0], r[1], r[2], B.lit + (size_t)rec * nL, ksv[k]);
+            }
+            int k = depth - 1;
+            V3 colour = (ksv[k].z <= 0.01f) ? direct[k] : direct[k] + mk3(0.0f, 0.0f, 0.0f) * ksv[k];
+            for (k = depth - 2; k >= 0; k--) colour = direct[k] + colour * ksv[k];
+            int outIdx, local;
+            wrote = seqToPixel(P, tileSeq, slot, x, y, outIdx, local);
+            if (wrote) storeRGB(fb, outIdx, colour);
         }
-        int k = depth - 1;
-        V3 colour = (ksv[k].z <= 0.01f) ? direct[k] : direct[k] + mk3(0.0f, 0.0f, 0.0f) * ksv[k];
-        for (k = depth - 2; k >= 0; k--) colour = direct[k] + colour * ksv[k];
-        int x, y, outIdx, local;
-        if (seqToPixel(P, tileSeq, slot, x, y, outIdx, local)) storeRGB(fb, outIdx, colour);
+        noteColoured(B.counts + CGRT_CNT_BBOX, wrote, x, P.height - 1 - y, P.width, P.height);
     }
 }
 
@@ -1719,6 +1739,28 @@ __global__ void k_generate_rays(const FrameParams* __restrict__ Pp, float4* __re
     rays[2 * (size_t)i + 1] = make_float4(d.x, d.y, d.z, 0.0f);
 }
 
+// ---- synchronous host render, overlapped delivery: the bounding box of the pixels the shading pass coloured (counts[CGRT_CNT_BBOX],
+// kept by the shading pass), copied from the device frame straight into the caller's page-locked frame in full 128-byte runs;
+// every other pixel of that frame was blanked by a copy-engine transfer while the frame rendered
+__global__ void __launch_bounds__(256) k_deliver_box(const int* __restrict__ bbox, int W, int H, const float* __restrict__ frame,
+                                                     float* __restrict__ hostFrame)
+{
+    const int x1 = bbox[0] - 1, r1 = bbox[1] - 1, x0 = W - bbox[2], r0 = H - bbox[3];
+    if (bbox[0] <= 0 || x1 < x0 || r1 < r0) return; // nothing was coloured
+    const int f0 = (3 * x0) & ~31, f1 = 3 * x1 + 3; // floats of a row, start rounded down to a 128-byte run
+    const int perRow = f1 - f0;
+    const long long total = (long long)perRow * (r1 - r0 + 1);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int row = r0 + (int)(i / perRow), f = f0 + (int)(i % perRow);
+        const size_t o = (size_t)row * W * 3 + f;
+        hostFrame[o] = frame[o];
+    }
+}
+void launchDeliverBox(const int* bbox, int W, int H, const float* frame, float* hostFrame, int numSMs, cudaStream_t st)
+{
+    k_deliver_box<<<numSMs * 8, 256, 0, st>>>(bbox, W, H, frame, hostFrame);
+}
+
 // ---- rank 0: de-interleave gathered tile buffers into the Screen layout -----------------------------------------------------
 __global__ void k_assemble(const float* __restrict__ gathered, size_t perRankFloats, const int* __restrict__ tileLists,
                            const int* __restrict__ tileCounts, int maxTiles, int world, int tileW, int tileH, int tilesX,
@@ -1798,6 +1840,105 @@ __global__ void k_divide(const float* __restrict__ acc, size_t n, float div, flo
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[i] = acc[i] / div;
+}
+
+// ---- bloom (bloomEffect, src/main.cpp:586-628; bookkeeping :698-705) --------------------------------------------------------------
+// The reference keeps the pixels whose colour sums to more than 1 (matrixColorsScreen, else black) and then replaces every entry,
+// IN PLACE and in scan order (y outer, x inner, y = 0 at the bottom), by the average of its 21 x 21 neighbourhood (clipped at the
+// borders; the entry itself first, then rows i = -10..10, columns j = -10..10 in that order) - so an entry sees the NEW values of
+// the rows below it in the image (y + i < y) and of its left neighbours, and the OLD values of everything else. The pixel becomes
+// that average plus the ray-traced colour.
+// That is a recurrence, but one with a wavefront: entry (x, y) needs row y - 1 finished up to column x + 10 only. One warp per
+// row, rows chasing each other 11 columns apart (~W / 11 rows in flight), each warp keeping its 21 x 21 window in shared memory
+// (one new column per step) and adding the up to 440 terms of an entry in the reference's order - the additions of one entry
+// are a dependent chain by definition (float addition is not associative), the three channels are three lanes.
+// k_bloom_init: M[y * W + x] = thresholded colour in the reference's index order (ray space: image row H - 1 - y), progress = 0.
+__global__ void k_bloom_init(const float* __restrict__ frame, int W, int H, float* __restrict__ M, int* __restrict__ progress)
+{
+    const size_t n = (size_t)W * H;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+        const float* c = frame + 3 * ((size_t)(H - 1 - y) * W + x);
+        const bool keep = c[0] + c[1] + c[2] > 1; // color.x + color.y + color.z > 1, main.cpp:700
+        M[3 * p + 0] = keep ? c[0] : 0.0f;
+        M[3 * p + 1] = keep ? c[1] : 0.0f;
+        M[3 * p + 2] = keep ? c[2] : 0.0f;
+        if (x == 0) progress[y] = 0;
+    }
+}
+#define BLOOM_R 10
+#define BLOOM_D (2 * BLOOM_R + 1)
+__global__ void __launch_bounds__(128) k_bloom(float* M, const float* __restrict__ frame, int W, int H, float* __restrict__ out,
+                                               int* progress)
+{
+    __shared__ float win[4][3][BLOOM_D][BLOOM_D]; // [warp][channel][window row i + 10][column mod 21]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = blockIdx.x * 4 + warp;
+    if (y >= H) return;
+    float(*w)[BLOOM_D][BLOOM_D] = win[warp];
+    const int i0 = y - BLOOM_R < 0 ? -y : -BLOOM_R, i1 = y + BLOOM_R > H - 1 ? H - 1 - y : BLOOM_R; // valid rows of the window
+    int seen = y == 0 ? W : 0; // columns of row y - 1 known to be finished
+    // lane r < 21 loads window row r - 10 of one column (three channels), through L2: other warps write M while this one reads
+    auto loadColumn = [&](int xx) {
+        const int i = lane - BLOOM_R;
+        if (lane < BLOOM_D && i >= i0 && i <= i1) {
+            const float* src = M + 3 * ((size_t)(y + i) * W + xx);
+            w[0][lane][xx % BLOOM_D] = __ldcg(src);
+            w[1][lane][xx % BLOOM_D] = __ldcg(src + 1);
+            w[2][lane][xx % BLOOM_D] = __ldcg(src + 2);
+        }
+    };
+    auto waitFor = [&](int need) { // row y - 1 finished up to column `need` (exclusive)
+        if (seen >= need) return;
+        int v = seen;
+        if (lane == 0) {
+            while ((v = *(volatile int*)(progress + y - 1)) < need) __nanosleep(64);
+        }
+        seen = __shfl_sync(0xffffffffu, v, 0);
+        __threadfence(); // (the loads of row y - 1's entries come after the progress value that announced them)
+    };
+    waitFor(BLOOM_R < W ? BLOOM_R : W);
+    for (int xx = 0; xx < BLOOM_R && xx < W; xx++) loadColumn(xx);
+    for (int x = 0; x < W; x++) {
+        if (x + BLOOM_R < W) {
+            waitFor(x + BLOOM_R + 1);
+            loadColumn(x + BLOOM_R);
+        }
+        __syncwarp();
+        if (lane < 3) {
+            const int j0 = x - BLOOM_R < 0 ? -x : -BLOOM_R, j1 = x + BLOOM_R > W - 1 ? W - 1 - x : BLOOM_R;
+            float acc = w[lane][BLOOM_R][x % BLOOM_D];
+            const int s0 = (x + j0) % BLOOM_D;
+            for (int i = i0; i <= i1; i++) {
+                const float* row = w[lane][i + BLOOM_R];
+                int s = s0;
+                for (int j = j0; j <= j1; j++) {
+                    if (i != 0 || j != 0) acc += row[s];
+                    s = s + 1 == BLOOM_D ? 0 : s + 1;
+                }
+            }
+            const int counter = (i1 - i0 + 1) * (j1 - j0 + 1); // 1 + the number of terms added
+            const float m = acc / counter;
+            w[lane][BLOOM_R][x % BLOOM_D] = m; // the entries to the right see the new value
+            M[3 * ((size_t)y * W + x) + lane] = m;
+            const size_t o = 3 * ((size_t)(H - 1 - y) * W + x) + lane;
+            out[o] = m + frame[o]; // screen.setPixel(x, y, matrixColorsScreen + color), main.cpp:621
+        }
+        if ((x & 7) == 7 || x == W - 1) { // announce progress every 8 columns: the writes above first, then the counter
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) *(volatile int*)(progress + y) = x + 1;
+        }
+        __syncwarp();
+    }
+}
+void launchBloom(const float* frame, int W, int H, float* M, int* progress, float* out, int numSMs, cudaStream_t st)
+{
+    const size_t n = (size_t)W * H;
+    int blocks = (int)((n + 255) / 256);
+    blocks = blocks > numSMs * 16 ? numSMs * 16 : blocks;
+    k_bloom_init<<<blocks, 256, 0, st>>>(frame, W, H, M, progress);
+    k_bloom<<<(H + 3) / 4, 128, 0, st>>>(M, frame, W, H, out, progress);
 }
 
 void launchAADownsample(const float* big, int W, int H, float* out, cudaStream_t st)

@@ -69,7 +69,9 @@ namespace cgrt {
 #define CGRT_CNT_BOUNCES (CGRT_CNT_PATHS + 2)                   // path pipeline: reflection rays traced
 #define CGRT_CNT_REPLAY_PATHS (CGRT_CNT_PATHS + 3)              // rays the speculative closest-hit kernel deferred to the exact one
 #define CGRT_CNT_REPLAY_SHADOW (CGRT_CNT_PATHS + 4)             // shadow rays deferred to the exact any-hit kernel
-#define CGRT_CNT_TOTAL (CGRT_CNT_PATHS + 5)
+#define CGRT_CNT_BBOX (CGRT_CNT_PATHS + 5) // 4 ints, bounding box of the pixels the shading pass coloured (whole frames in Screen
+                                          // layout): max of x + 1, row + 1, W - x, H - row; 0 = no pixel (counters start at zero)
+#define CGRT_CNT_TOTAL (CGRT_CNT_PATHS + 9)
 #define CGRT_MAX_PEERS 32                       // flags one signal launch can write (GPUs of one box)
 #define CGRT_PARAM_BLOCK_HEADER 128             // bytes reserved for FrameParams in the per-frame block; lights follow
 
@@ -212,11 +214,13 @@ int waveGridBlocks(int numSMs); // co-resident CTAs of k_wave on this device (oc
 int launchWavePipeline(const DevScene& S, const FrameParams* dP, const FrameParams& hP, const float4* dLights,
                        const RoundBuffers& B, const WaveQ& Q, const int2* dTileSeq, float* fb, int numSMs, WaveTrace* tr,
                        cudaStream_t st);
+void launchDeliverBox(const int* bbox, int W, int H, const float* frame, float* hostFrame, int numSMs, cudaStream_t st);
 void launchAssemble(const float* gathered, size_t perRankFloats, const int* tileLists, const int* tileCounts, int maxTiles,
                     int world, int tileW, int tileH, int tilesX, int width, int height, float* frame, int numSMs,
                     cudaStream_t st);
 void launchFlagSignal(uint32_t* const* flags, int n, uint32_t seq, cudaStream_t st);
 void launchFlagWait(const uint32_t* flags, int n, uint32_t seq, unsigned long long timeoutNs, uint32_t* status, cudaStream_t st);
+void launchBloom(const float* frame, int W, int H, float* M, int* progress, float* out, int numSMs, cudaStream_t st);
 void launchAADownsample(const float* big, int W, int H, float* out, cudaStream_t st);
 void launchAccumulate(float* acc, const float* frame, size_t n, bool first, cudaStream_t st);
 void launchDivide(const float* acc, size_t n, float div, float* out, cudaStream_t st);

@@ -825,20 +825,26 @@ __global__ void __launch_bounds__(128, CGRT_WAVE_MINBLOCKS) k_wave(DevScene S, c
     // flag was raised; they are read through L2)
     {
         const int nL = P.nLights;
-        for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < P.nSlots; slot += gridDim.x * blockDim.x) {
-            const int depth = __ldcg(B.pathDepth + slot);
-            if (depth <= 0) continue; // the pixel is already final (black)
-            V3 direct[CGRT_MAX_LEVELS], ksv[CGRT_MAX_LEVELS];
-            for (int k = 0; k < depth; k++) {
-                const int rec = slot * B.levels + k;
-                const float4* r = B.hitRec + 3 * (size_t)rec;
-                direct[k] = directColour<true>(S, lights, nL, __ldcg(r), __ldcg(r + 1), __ldcg(r + 2), B.lit + (size_t)rec * nL, ksv[k]);
+        for (int base = blockIdx.x * blockDim.x; base < P.nSlots; base += gridDim.x * blockDim.x) {
+            const int slot = base + threadIdx.x;
+            const int depth = slot < P.nSlots ? __ldcg(B.pathDepth + slot) : 0;
+            bool wrote = false;
+            int x = 0, y = 0;
+            if (depth > 0) { // (else the pixel is already final: black)
+                V3 direct[CGRT_MAX_LEVELS], ksv[CGRT_MAX_LEVELS];
+                for (int k = 0; k < depth; k++) {
+                    const int rec = slot * B.levels + k;
+                    const float4* r = B.hitRec + 3 * (size_t)rec;
+                    direct[k] = directColour<true>(S, lights, nL, __ldcg(r), __ldcg(r + 1), __ldcg(r + 2), B.lit + (size_t)rec * nL, ksv[k]);
+                }
+                int k = depth - 1;
+                V3 colour = (ksv[k].z <= 0.01f) ? direct[k] : direct[k] + mk3(0.0f, 0.0f, 0.0f) * ksv[k];
+                for (k = depth - 2; k >= 0; k--) colour = direct[k] + colour * ksv[k];
+                int outIdx, local;
+                wrote = seqToPixel(P, tileSeq, slot, x, y, outIdx, local);
+                if (wrote) storeRGB(fb, outIdx, colour);
             }
-            int k = depth - 1;
-            V3 colour = (ksv[k].z <= 0.01f) ? direct[k] : direct[k] + mk3(0.0f, 0.0f, 0.0f) * ksv[k];
-            for (k = depth - 2; k >= 0; k--) colour = direct[k] + colour * ksv[k];
-            int x, y, outIdx, local;
-            if (seqToPixel(P, tileSeq, slot, x, y, outIdx, local)) storeRGB(fb, outIdx, colour);
+            noteColoured(B.counts + CGRT_CNT_BBOX, wrote, x, P.height - 1 - y, P.width, P.height);
         }
     }
     // ---- statistics of the frame (cgrt_render_stats)

@@ -195,8 +195,8 @@ private:
 // Renders screen.resolution() pixels (the reference hard-codes 800x800, main.cpp:29) with the given recursion limit
 // (reference literal 2, main.cpp:267). Point lights are read from `scene` at call time, as the reference does.
 // the reference's UI toggles (src/main.cpp:33-35, ImGui check boxes :878-882); renderRayTracing reads them like the reference
-// does. `bloom` exists for source compatibility only: its in-place 21 x 21 recurrence (main.cpp:586-628) is not part of this
-// path and setting it makes renderRayTracing throw.
+// does: anti-aliasing (:663-687), bloom (:586-628, the in-place 21 x 21 recurrence, run as a wavefront on the device) and
+// motion blur (:318-584). bloom together with antiAliasing is refused (the reference's combination reads an uninitialised sum).
 extern bool bloom, blur, antiAliasing;
 
 struct RenderOptions {

@@ -355,9 +355,8 @@ RenderReport renderRayTracing(const Scene& scene, const Trackball& camera, const
     p.rank = opt.rank;
     p.world = opt.world;
     cgrt_render_stats st;
-    if (bloom) throw std::runtime_error("renderRayTracing: the bloom pass (src/main.cpp:586-628) is outside the accelerated path");
-    const int32_t effects = (antiAliasing ? CGRT_EFFECT_ANTIALIAS : 0) | (blur ? CGRT_EFFECT_MOTION_BLUR : 0);
-    if (effects && opt.world == 1) { // anti-aliasing / motion blur around the same renderer (main.cpp:663-687, :318-584)
+    const int32_t effects = (antiAliasing ? CGRT_EFFECT_ANTIALIAS : 0) | (blur ? CGRT_EFFECT_MOTION_BLUR : 0) | (bloom ? CGRT_EFFECT_BLOOM : 0);
+    if (effects && opt.world == 1) { // anti-aliasing / bloom / motion blur around the same renderer (main.cpp:663-687, :586-628, :318-584)
         if (cgrt_render_effects(bvh.handle(), &cam, &p, effects, screen.data(), &st) != CGRT_OK) throwLast("renderRayTracing");
     } else if (cgrt_render(bvh.handle(), &cam, &p, screen.data(), &st) != CGRT_OK) throwLast("renderRayTracing");
     RenderReport r;

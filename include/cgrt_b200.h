@@ -12,7 +12,12 @@
  * Conventions: return 0 (CGRT_OK) on success, non-zero error code otherwise; never throws; cgrt_last_error() returns a
  * thread-local human-readable message for the last failing call on this thread. Host callers own host buffers, the
  * library owns device memory. All entry points may be called concurrently from several host threads on the same scene
- * (the reference's intersect() is const and called from all OpenMP threads, src/main.cpp:653-656 -> :276).
+ * (the reference's intersect() is const and called from all OpenMP threads, src/main.cpp:653-656 -> :276). The query entries
+ * (cgrt_intersect_closest / _any and their _device forms) share nothing between threads: each host thread has its own stream
+ * and device scratch, kept between calls, so concurrent queries overlap on the device. Renders of ONE scene are serialised
+ * (they share the scene's ray queues; the reference calls renderRayTracing from the UI thread only), renders of different
+ * scenes are not. cgrt_render_device enqueues on the caller's stream: frames of one scene must be enqueued on one stream
+ * (or ordered by the caller) - the next frame reuses the queues of the previous one.
  */
 #ifndef CGRT_B200_H
 #define CGRT_B200_H
@@ -231,11 +236,18 @@ int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats);
  *   CGRT_EFFECT_MOTION_BLUR blurEffect, src/main.cpp:318-584: the frames of 15 cameras whose look-at point is REPLACED by
  *                           (0.01 k, 0, 0), k = 1..15, added in that order and divided by 16; as in the reference it overwrites
  *                           whatever the pixel loop drew, so it wins over CGRT_EFFECT_ANTIALIAS.
- * The bloom pass (src/main.cpp:586-628) is not offered: its 21 x 21 box average runs in place, every pixel reading neighbours
- * that the same loop has already overwritten, i.e. it is a sequential recurrence over the image. world must be 1.
- * stats (optional): sums over the rendered frames. */
+ *   CGRT_EFFECT_BLOOM       bloomEffect, src/main.cpp:586-628 with the bookkeeping of :698-705: pixels whose colour sums to more
+ *                           than 1 are kept (else black), every entry is then replaced IN PLACE, in scan order, by the average of its
+ *                           clipped 21 x 21 neighbourhood (so it sees the new values below / left of it and the old ones elsewhere),
+ *                           and the pixel becomes that average + the ray-traced colour. Bit-exact to the sequential loop: the
+ *                           recurrence is run as a wavefront, one warp per image row, rows 11 columns apart, every entry's terms
+ *                           added in the reference's order. With CGRT_EFFECT_MOTION_BLUR the running sum starts from
+ *                           colour + (bloom + colour) as in the reference (:700, :622, :581). Not offered together with
+ *                           CGRT_EFFECT_ANTIALIAS (the reference's combination thresholds on an uninitialised accumulator).
+ * world must be 1. stats (optional): sums over the rendered frames. */
 #define CGRT_EFFECT_ANTIALIAS 1
 #define CGRT_EFFECT_MOTION_BLUR 2
+#define CGRT_EFFECT_BLOOM 4
 int cgrt_render_effects(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, int32_t effects, float* rgb,
                         cgrt_render_stats* stats);
 /* Streaming form of cgrt_render for hosts that render frame after frame (the reference re-renders every UI frame in

@@ -191,6 +191,16 @@ class _CpuChecker:
     def max_threads(self):
         return int(self.fn("max_threads")())
 
+    def bloom(self, rgb):
+        """bloomEffect (main.cpp:586-628) on a frame in Screen layout; restated in the oracle library only (main.cpp cannot be built)."""
+        lib = OracleLib().lib
+        lib.orc_bloom.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_float)]
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        H, W = rgb.shape[:2]
+        out = np.zeros_like(rgb)
+        lib.orc_bloom(_fp(rgb), W, H, _fp(out))
+        return out
+
 
 class CpuScene:
     def __init__(self, lib, flat, lights=None):

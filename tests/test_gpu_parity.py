@@ -499,6 +499,71 @@ def test_streaming_render_equals_synchronous_render(capi, gpu):
         capi.check(lib.cgrt_host_free_pinned(p))
 
 
+def test_concurrent_host_threads_on_one_scene(capi, oracle, gpu):
+    """The reference's intersect() is const and called from every OpenMP thread (main.cpp:653-656 -> :276, :115). Eight host
+    threads issue mixed closest-hit / any-hit batches (ctypes releases the GIL inside the library) and renders on ONE scene;
+    every result must equal the one the same call gives serially."""
+    import threading
+    flat = ob.random_soup(20000, seed=5, scale=0.05, n_meshes=3)
+    lights = np.array([[0.2, 0.9, -0.3, 1, 1, 1]], np.float32)
+    s = capi.Scene(flat, lights=lights)
+    W, H = 160, 120
+    cam = capi.make_camera(W, H)
+    rays = [ob.random_rays(3000 + 1500 * k, seed=100 + k) for k in range(8)]
+    md = [np.random.default_rng(k).uniform(0, 2, len(rays[k])).astype(np.float32) for k in range(8)]
+    want_hits = [s.intersect(r) for r in rays]
+    want_any = [s.intersect_any(r, m) for r, m in zip(rays, md)]
+    want_frame, _ = s.render(cam, W, H, trace_limit=3)
+    g = oracle.scene(flat).bvh().intersect(rays[0])
+    assert hits_equal(want_hits[0], g, flat.canonical_ids())
+    errors = []
+
+    def worker(k):
+        try:
+            for it in range(6):
+                j = (k + it) % 8
+                if not hits_equal(s.intersect(rays[j]), want_hits[j]):
+                    errors.append(f"thread {k}: closest-hit batch {j} differs")
+                if not np.array_equal(s.intersect_any(rays[j], md[j]), want_any[j]):
+                    errors.append(f"thread {k}: any-hit batch {j} differs")
+                one = s.intersect(rays[j][it:it + 1])  # the scalar intersect(Ray&, HitInfo&) of the reference: a batch of one
+                if not hits_equal(one, want_hits[j][it:it + 1]):
+                    errors.append(f"thread {k}: single ray differs")
+                if k % 4 == 0:
+                    f, _ = s.render(cam, W, H, trace_limit=3)
+                    if not np.array_equal(bits(f), bits(want_frame)):
+                        errors.append(f"thread {k}: frame differs")
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"thread {k}: {type(e).__name__}: {e}")
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors[:5]
+
+
+def test_overlapped_delivery_equals_plain_copy(capi, gpu):
+    """cgrt_render into a PAGE-LOCKED frame takes the overlapped delivery (frame zeroed over PCIe while it renders, hit pixels
+    written by a kernel); into pageable memory the plain device-to-host copy. Same frame bit for bit, for both pipelines, also
+    when the destination held another image before."""
+    import ctypes as C
+    lib = capi.load_library()
+    flat, lights = ob.dragon_standin_fixture()
+    s = capi.Scene(flat, lights=lights)
+    for (W, H, L) in ((640, 360, 5), (1920, 1080, 1), (333, 201, 2)):
+        cam = capi.make_camera(W, H)
+        want, st = s.render(cam, W, H, trace_limit=L)  # numpy (pageable) destination
+        ptr = C.c_void_p()
+        capi.check(lib.cgrt_host_alloc_pinned(W * H * 12, C.byref(ptr)))
+        pinned = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(H, W, 3))
+        pinned[:] = 0.75
+        got, st2 = s.render(cam, W, H, trace_limit=L, out=pinned)
+        assert np.array_equal(bits(got), bits(want)) and st2["primary_hit"] == st["primary_hit"]
+        capi.check(lib.cgrt_host_free_pinned(ptr))
+
+
 # ---- renderRayTracing's optional passes (SURVEY.md §8 f1): anti-aliasing and motion blur around the same renderer ---------------
 def test_antialiasing_and_motion_blur_against_oracle(capi, oracle, gpu, golden):
     """cgrt_render_effects vs the oracle's frames combined exactly as src/main.cpp:663-687 (AA: the 4 pixel-corner rays of the
@@ -534,3 +599,36 @@ def test_antialiasing_and_motion_blur_against_oracle(capi, oracle, gpu, golden):
     assert st["primary"] + st["shadow"] + st["bounce"] == rays
     assert np.abs(got - want).max() <= PIXEL_TOL
     assert (bits(got) == bits(want)).all(axis=2).mean() > 0.99
+
+
+def test_bloom_against_sequential_restatement(capi, oracle, gpu):
+    """cgrt_render_effects(BLOOM) vs the oracle's literal restatement of bloomEffect (main.cpp:586-628: in-place, sequential,
+    21 x 21 clipped neighbourhood, scan order) applied to the frame the same library renders: bit for bit - the device runs the
+    recurrence as a wavefront but adds every entry's terms in the reference's order. Sizes: wider / narrower than the window,
+    non-multiples of the progress granularity, a frame with more rows than one wave of warps."""
+    flat, lights = ob.dragon_standin_fixture()
+    bright = lights.copy()
+    bright[:, 3:6] = 2.5  # light colour: enough pixels over the bloom threshold r + g + b > 1
+    s = capi.Scene(flat, lights=bright)
+    for (W, H, L) in ((200, 150, 3), (37, 29, 2), (13, 450, 1), (640, 360, 2)):
+        cam = capi.make_camera(W, H)
+        frame, st = s.render(cam, W, H, trace_limit=L)
+        got, st2 = s.render_effects(cam, W, H, trace_limit=L, bloom=True)
+        want = oracle.bloom(frame)
+        assert (frame.sum(axis=2) > 1).sum() > 20, "the test frame must have pixels over the threshold"
+        assert np.array_equal(bits(got), bits(want)), (W, H)
+        assert st2["primary"] == st["primary"] and st2["shadow"] == st["shadow"]
+    # bloom + motion blur: the running sum starts from colour + (bloom + colour), then the 15 shifted frames, / 16
+    W, H, L = 160, 100, 2
+    cam = capi.make_camera(W, H)
+    frame, _ = s.render(cam, W, H, trace_limit=L)
+    acc = frame + oracle.bloom(frame)
+    for k in range(1, 16):
+        c = capi.make_camera(W, H, look_at=(float(np.float32(float("%.2f" % (0.01 * k)))), 0.0, 0.0))
+        f, _ = s.render(c, W, H, trace_limit=L)
+        acc = acc + f
+    want = acc / np.float32(16.0)
+    got, _ = s.render_effects(cam, W, H, trace_limit=L, bloom=True, motion_blur=True)
+    assert np.array_equal(bits(got), bits(want))
+    with pytest.raises(capi.CgrtError):
+        s.render_effects(cam, W, H, trace_limit=L, bloom=True, antialias=True)
