@@ -1620,6 +1620,46 @@ __global__ void __launch_bounds__(128) k_finish(DevScene S, const FrameParams* _
     }
 }
 
+// ---- batch queries (cgrt_intersect_closest / _any) through the same split: search-only persistent kernel, flat finish ------------
+// The one-kernel form (k_closest_batch / k_any_batch: a thread follows its ray through search, certificate and replay) keeps
+// the certificate's twelve exact slab tests and the fp64 epilogue inside the divergent per-ray loop; on 16 M incoherent rays
+// of the 1 M-triangle soup it ran at 152 / 196 Mrays/s and slower than the exact traversal (profiles/r01_configs.md). Here the
+// rays are turned into the round pipeline's records, k_trace searches them, and a flat kernel certifies / replays and writes
+// the hit records.
+__global__ void __launch_bounds__(256) k_batch_prep(const float4* __restrict__ rays, const float* __restrict__ maxDist, float eps,
+                                                    int n, int any, float4* __restrict__ rec, int* __restrict__ ctl)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 r0 = __ldg(rays + 2 * (size_t)i), r1 = __ldg(rays + 2 * (size_t)i + 1);
+        rec[3 * (size_t)i] = r0;
+        rec[3 * (size_t)i + 1] = make_float4(r1.x, r1.y, r1.z, any ? __ldg(maxDist + i) : __int_as_float(0x7f800000));
+        rec[3 * (size_t)i + 2] = make_float4(i2f(i), i2f(any ? CGRT_RAY_ANY : 0), eps, 0.0f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctl[0] = n; // list length read by k_trace
+        ctl[1] = 0; // its work counter
+    }
+}
+__global__ void __launch_bounds__(128) k_batch_finish_closest(DevScene S, const float4* __restrict__ rec, const float4* __restrict__ res,
+                                                              int n, float4* __restrict__ hits)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = rec[3 * (size_t)i], b = rec[3 * (size_t)i + 1];
+        TraceResult R;
+        bool replay = false;
+        const bool hit = finishClosestRay<false>(S, a, b, res[i], R, replay);
+        writeHit(S, mk3(a), mk3(b), a.w, hit, R, hits + 2 * (size_t)i);
+    }
+}
+__global__ void __launch_bounds__(128) k_batch_finish_any(DevScene S, const float4* __restrict__ rec, const float4* __restrict__ res,
+                                                          int n, uint8_t* __restrict__ occluded)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        bool replay = false;
+        occluded[i] = finishShadowRay<false>(S, rec[3 * (size_t)i], rec[3 * (size_t)i + 1], rec[3 * (size_t)i + 2], res[i], replay) ? 1 : 0;
+    }
+}
+
 // one thread per pixel slot: direct colour of every level, then the recursion unwound innermost first (main.cpp:241-264)
 __global__ void __launch_bounds__(128) k_shade_slots(DevScene S, const FrameParams* __restrict__ Pp, const float4* __restrict__ lights,
                                                      RoundBuffers B, const int2* __restrict__ tileSeq, float* __restrict__ fb)
@@ -1975,10 +2015,50 @@ void launchSetupPlanes(const float4* v0, const float4* v1, const float4* v2, flo
     if (n > 0) k_setup_planes<<<(n + 255) / 256, 256, 0, st>>>(v0, v1, v2, pl, tri4, n);
 }
 
+#define CGRT_BATCH_CHUNK (4 << 20) // rays per pass of the split batch path: 256 MB of stream-ordered scratch
+#define CGRT_BATCH_SPLIT_MIN 8192  // smaller batches (the scalar intersect(Ray&, HitInfo&) is a batch of one) take the one-kernel form
+// the split path for one kind of query; returns false when the stream-ordered scratch is not available (the caller falls back)
+static bool launchSplitBatch(const DevScene& S, const float4* rays, const float* maxDist, float eps, size_t n, bool any,
+                             float4* hits, uint8_t* occluded, int numSMs, cudaStream_t st)
+{
+    const size_t chunk = n < CGRT_BATCH_CHUNK ? n : (size_t)CGRT_BATCH_CHUNK;
+    float4* rec = nullptr;
+    float4* res = nullptr;
+    int* ctl = nullptr;
+    if (cudaMallocAsync((void**)&rec, chunk * 3 * sizeof(float4), st) != cudaSuccess ||
+        cudaMallocAsync((void**)&res, chunk * sizeof(float4), st) != cudaSuccess ||
+        cudaMallocAsync((void**)&ctl, 2 * sizeof(int), st) != cudaSuccess) {
+        cudaGetLastError();
+        if (rec) cudaFreeAsync(rec, st);
+        if (res) cudaFreeAsync(res, st);
+        return false;
+    }
+    const int persistent = numSMs * tuning().blocks;
+    for (size_t done = 0; done < n; done += chunk) {
+        const int m = (int)(n - done < chunk ? n - done : chunk);
+        const int flat = gridFor((size_t)m, 128, numSMs * 16);
+        k_batch_prep<<<gridFor((size_t)m, 256, numSMs * 8), 256, 0, st>>>(rays + 2 * done, any ? maxDist + done : nullptr, eps, m, any ? 1 : 0, rec, ctl);
+        if (any) {
+            k_trace<<<persistent, 128, 0, st>>>(S, rec, res, ctl, 1, nullptr, nullptr, nullptr, ctl + 1, 0);
+            k_batch_finish_any<<<flat, 128, 0, st>>>(S, rec, res, m, occluded + done);
+        } else {
+            k_trace<<<persistent, 128, 0, st>>>(S, nullptr, nullptr, nullptr, 1, rec, res, ctl, ctl + 1, 0);
+            k_batch_finish_closest<<<flat, 128, 0, st>>>(S, rec, res, m, hits + 2 * done);
+        }
+    }
+    cudaFreeAsync(rec, st);
+    cudaFreeAsync(res, st);
+    cudaFreeAsync(ctl, st);
+    return true;
+}
+
 void launchClosestBatch(const DevScene& S, const float4* rays, size_t n, float4* hits, uint32_t* counts, int numSMs,
                         cudaStream_t st)
 {
     if (n == 0) return;
+    if (!counts && S.fastRoot != 0u && n >= CGRT_BATCH_SPLIT_MIN && !getenv("CGRT_BATCH_ONE_KERNEL") &&
+        launchSplitBatch(S, rays, nullptr, 0.0f, n, false, hits, nullptr, numSMs, st))
+        return;
     const int grid = gridFor(n, 128, numSMs * 16);
     if (counts) k_closest_batch<true><<<grid, 128, 0, st>>>(S, rays, n, hits, counts);
     else k_closest_batch<false><<<grid, 128, 0, st>>>(S, rays, n, hits, nullptr);
@@ -1988,6 +2068,9 @@ void launchAnyBatch(const DevScene& S, const float4* rays, const float* maxDist,
                     int numSMs, cudaStream_t st)
 {
     if (n == 0) return;
+    if (S.fastRoot != 0u && n >= CGRT_BATCH_SPLIT_MIN && !getenv("CGRT_BATCH_ONE_KERNEL") &&
+        launchSplitBatch(S, rays, maxDist, eps, n, true, nullptr, occluded, numSMs, st))
+        return;
     k_any_batch<<<gridFor(n, 128, numSMs * 16), 128, 0, st>>>(S, rays, maxDist, eps, n, occluded);
 }
 
