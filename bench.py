@@ -40,6 +40,7 @@ METRIC = "Mrays/s (primary+shadow+bounce)"
 WIDTH, HEIGHT, TRACE_LIMIT = 1920, 1080, 5
 CPU_BUDGET_S = 12.0  # cpu_baseline leg of our arm: the full frame is repeated until about this much CPU time has been spent
 B_RAY, B_BOX, B_TRI = 48, 32, 48  # algorithmic bytes: ray in + hit out, per box test, per triangle test
+L2_PEAK_GBS = 20000.0  # order of magnitude of B200's L2 bandwidth (no measured figure in MEASURED_PEAKS.json): context for l2_frac only
 
 
 # re-exported for tests/test_multirank_gloo.py
@@ -67,7 +68,9 @@ DATA = "synthetic (procedural dragon stand-in; data/dragon.obj is not in the ref
 def workload_name(n_tris):
     return (f"C3 dragon stand-in (procedural torus knot, {n_tris} triangles, mirror ks=0.5) {WIDTH}x{HEIGHT} Whitted: "
             f"1 point light, 1 shadow ray/hit/light, trace limit {TRACE_LIMIT} (<=4 mirror bounces), reference camera preset, "
-            f"reference-rule BVH depth 12, strict arithmetic (-fmad=false)")
+            f"strict arithmetic (-fmad=false); every ray is SEARCHED in an 8-wide binned-SAH tree and CERTIFIED against the "
+            f"reference-rule BVH (depth 12), results bit-identical to the reference traversal (config.exact_only_ms = the same "
+            f"frame through the exact reference-order traversal alone)")
 
 
 class ClockSampler:
@@ -260,7 +263,8 @@ def main():
     alg_bytes_class = [B_RAY * cls_rays[c] + B_BOX * st_count["box_tests"][c] + B_TRI * st_count["tri_tests"][c] for c in range(3)]
     alg_bytes_frame_local = sum(alg_bytes_class)
     names = capi.class_names(st_prof)
-    if names is capi.ROUND_CLASS_NAMES:  # round pipeline: k_trace (class 2) searches every ray of the frame
+    if names is capi.ROUND_CLASS_NAMES or names is capi.WAVE_CLASS_NAMES:
+        # round pipeline: k_trace (class 2) searches every ray of the frame; persistent wavefront: k_wave (class 2) IS the frame
         alg_bytes_class = [0, 0, alg_bytes_frame_local]
     elif st_prof["class_launches"][1] == 0:  # path pipeline: k_paths traces the primary AND the bounce rays
         alg_bytes_class = [alg_bytes_class[0] + alg_bytes_class[1], 0, alg_bytes_class[2]]
@@ -269,6 +273,17 @@ def main():
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     rays_frame, n_primary, n_shadow, n_bounce, alg_bytes_frame = [float(x) for x in tot.tolist()]
+
+    # the same frame through the exact reference-order traversal alone (no speculative search): reported next to the headline
+    exact_only_ms = None
+    if world == 1 and not os.environ.get("CGRT_BENCH_SKIP_EXACT"):
+        ex = capi.Scene(d, lights=d.lights, device=local_rank, exact_only=True)
+        ems = []
+        for _ in range(4):
+            _, est = ex.render(cam, WIDTH, HEIGHT, trace_limit=TRACE_LIMIT)
+            ems.append(est["device_ms"])
+        exact_only_ms = float(min(ems[1:]))
+        ex.close()
 
     # ---- timed: K frames, CUDA events per frame on the launching stream, L2 flushed between frames (outside the events)
     sampler = ClockSampler(local_rank)
@@ -359,12 +374,27 @@ def main():
         # algorithmic bytes of the rays this rank's launches of the dominant kernel process, averaged per launch
         dom_bytes_per_launch = alg_bytes_class[dominant] / max(st_prof["class_launches"][dominant], 1) if dominant < 3 else 0.0
         achieved = dom_bytes_per_launch / dom_avg_s / 1e9 if dom_avg_s > 0 else 0.0
-        traffic = None
+        traffic, counters = None, {}
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = prof.get(dom_name, {}).get("dram_bytes_per_launch")
+            counters = prof.get(dom_name, {})
+            traffic = counters.get("dram_bytes_per_launch")
         except Exception:
             pass
+        # what the kernel is really bound by (ncu --set full of this kernel on this frame, profiles/traffic.json): bytes it
+        # requested from L2 / L1, the fraction of the issue slots it used, active threads per warp instruction
+        sm_clock = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_clock * 1e6  # warp instructions per second: 148 SMs x 4 schedulers
+        extras = {}
+        if counters.get("warp_inst_per_launch") and dom_avg_s > 0:
+            extras["issue_frac"] = counters["warp_inst_per_launch"] / dom_avg_s / issue_peak
+            extras["warp_inst_per_ray"] = counters["warp_inst_per_launch"] / max(rays_frame / max(st_prof["class_launches"][dominant], 1), 1)
+        if counters.get("l2_bytes_per_launch") and dom_avg_s > 0:
+            extras["requested_bytes_per_launch"] = {"lts__t_bytes": counters["l2_bytes_per_launch"], "l1tex__t_bytes": counters.get("l1_bytes_per_launch")}
+            extras["l2_frac"] = counters["l2_bytes_per_launch"] / dom_avg_s / 1e9 / L2_PEAK_GBS
+        if counters.get("threads_per_warp_inst"):
+            extras["threads_per_warp_inst"] = counters["threads_per_warp_inst"]
+        extras["counters_source"] = counters.get("source")
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -375,7 +405,8 @@ def main():
                                     "nccl": "NCCL gather of tile-major buffers + assemble kernel"}[R.mode],
                        "exchange_fallback_reason": R.fallback_reason, "handoff_timeouts": timeouts, "e2e_mode": e2e_mode, "e2e_streamed_frame_equals_synchronous_frame": e2e_frames_equal,
                        "frame_equals_single_gpu": frame_equals_single,
-                       "rays_per_frame": {"primary": n_primary, "shadow": n_shadow, "bounce": n_bounce},
+                       "rays_per_frame": {"primary": n_primary, "shadow": n_shadow, "bounce": n_bounce}, "exact_only_ms": exact_only_ms,
+                       "pipeline": {0: "counting", 1: "path pipeline", 2: "round pipeline", 3: "persistent wavefront (k_wave)"}.get(st_prof.get("pipeline")),
                        "kernel_ms_per_frame_rank0": dict(zip(names, [round(v, 4) for v in st_prof["class_ms"]])),
                        "kernel_launches_per_frame": dict(zip(names, st_prof["class_launches"])),
                        "frame_roofline": {"algorithmic_bytes_per_frame": alg_bytes_frame, "bytes_per_ray": alg_bytes_frame / rays_frame,
@@ -392,12 +423,12 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes_per_launch, "avg_launch_ms": dom_avg_s * 1e3,
-                         "launches_timed": dom_launches,
+                         "launches_timed": dom_launches, "exact_only_ms": exact_only_ms, **extras,
                          "note": "algorithmic bytes = the box / triangle tests the REFERENCE traversal performs for these rays (counting "
                                  "pass, SURVEY 8d); the speculative search performs far fewer and the scene (~20 MB) is L2-resident, so "
-                                 "frac can exceed 1 and DRAM traffic is ~50x lower: the HBM roofline is the contractual denominator, "
-                                 "the practical limiters are issued instructions per ray and the latency of dependent steps in "
-                                 "launch tails (profiles/)"},
+                                 "frac can exceed 1 and DRAM traffic is far lower: the HBM roofline is the contractual denominator. The "
+                                 "physical bound is instruction issue: issue_frac = warp instructions / (148 SMs x 4 schedulers x clock x "
+                                 "time), at threads_per_warp_inst of 32 lanes (ncu, profiles/); l2_frac is against a nominal 20 TB/s"},
         }
         if timeouts:
             line["invalid"] = f"{timeouts} exchange hand-off wait(s) timed out: frames may be incomplete"

@@ -50,7 +50,11 @@ WANT = [("gpu__time_duration.sum", "time"), ("launch__registers_per_thread", "re
         ("smsp__thread_inst_executed_per_inst_executed.ratio", "threads / warp inst"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
         ("smsp__inst_executed.sum", "warp inst"), ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
-        ("lts__t_bytes.sum", "L2 bytes"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+        ("lts__t_bytes.sum", "L2 bytes"), ("l1tex__t_bytes.sum", "L1 bytes"), ("lts__t_sectors_srcunit_tex_op_read.sum", "L2 read sectors from L1"),
+        ("l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "local-memory load sectors (L1)"), ("l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum", "local-memory store sectors (L1)"),
+        ("smsp__inst_executed_op_local_ld.sum", "local loads (warp inst)"), ("smsp__inst_executed_op_local_st.sum", "local stores (warp inst)"),
+        ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+        ("smsp__cycles_active.avg", "SM sub-partition cycles active (avg)"), ("sm__cycles_elapsed.max", "SM cycles elapsed (max)"),
         ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_sb"),
         ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait"),
         ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected"),
@@ -87,7 +91,7 @@ if os.path.exists(ll):
     lines.append("")
     os.replace(ll, os.path.join(P, f"{tag}_launches.csv")) if not os.path.exists(os.path.join(P, f"{tag}_launches.csv")) else None
 traffic = {}
-for part in ("trace", "rest"):
+for part in ("wave", "trace", "rest"):
     rp = os.path.join(G, f"prof_{tag}_{part}_raw.csv")
     if not os.path.exists(rp):
         continue
@@ -97,6 +101,7 @@ for part in ("trace", "rest"):
         lines.append(f"### {k} ({len(rows)} launches)")
         lines += ["| metric | mean | min | max |", "|---|---|---|---|"]
         dram = 0.0
+        extra = {}
         for m, label in WANT:
             if m not in idx:
                 continue
@@ -107,7 +112,12 @@ for part in ("trace", "rest"):
             lines.append(f"| {label} | {mean:,.2f} {unit} | {min(vals):,.2f} | {max(vals):,.2f} |")
             if m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 dram += mean
-        traffic[k] = {"dram_bytes_per_launch": dram, "launches_captured": len(rows), "source": f"profiles/{tag}_summary.md"}
+            key = {"smsp__inst_executed.sum": "warp_inst_per_launch", "lts__t_bytes.sum": "l2_bytes_per_launch",
+                   "l1tex__t_bytes.sum": "l1_bytes_per_launch", "smsp__thread_inst_executed_per_inst_executed.ratio": "threads_per_warp_inst",
+                   "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct", "gpu__time_duration.sum": "ncu_time_us"}.get(m)
+            if key:
+                extra[key] = mean
+        traffic[k] = {"dram_bytes_per_launch": dram, "launches_captured": len(rows), "source": f"profiles/{tag}_summary.md", **extra}
         lines.append("")
 open(os.path.join(P, f"{tag}_summary.md"), "w").write("\n".join(lines) + "\n")
 if traffic:
