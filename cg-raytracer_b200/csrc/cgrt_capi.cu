@@ -1029,7 +1029,9 @@ static bool useWave(const cgrt_scene* s, const FrameParams& P)
         pref = (e && std::strcmp(e, "rounds") == 0) ? 0 : ((e && std::strcmp(e, "wave") == 0) ? 1 : 2);
     }
     if (pref == 0 || !useRounds(s, P) || P.nSlots >= (1 << 26) || P.traceLimit > 16) return false; // ray record: level << 26 | slot
-    return pref == 1 || P.traceLimit >= 3 || P.nSlots < 400000;
+    // (shares of a multi-GPU frame: the one-launch form also wins on shallow frames up to ~2 M slots per rank - C2 on 4 GPUs
+    // 0.23 vs 0.37 ms, C5 on 4 GPUs 0.58 vs 0.64 ms - where the round pipeline's per-launch floors no longer shrink with the share)
+    return pref == 1 || P.traceLimit >= 3 || P.nSlots < 400000 || (P.world > 1 && P.nSlots < 2500000);
 }
 // tickets the queue must hold: every slot can cast one closest-hit ray and one shadow ray per light at every level; plus the
 // tickets idle lanes hold beyond the last ray (one per resident lane at most)

@@ -2022,6 +2022,21 @@ static bool launchSplitBatch(const DevScene& S, const float4* rays, const float*
                              float4* hits, uint8_t* occluded, int numSMs, cudaStream_t st)
 {
     const size_t chunk = n < CGRT_BATCH_CHUNK ? n : (size_t)CGRT_BATCH_CHUNK;
+    { // keep the stream-ordered pool's memory between calls (by default it goes back to the driver at every synchronisation,
+      // and the next call pays for mapping 256 MB again)
+        static bool kept[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!kept[dev & 63]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+            kept[dev & 63] = true;
+        }
+    }
     float4* rec = nullptr;
     float4* res = nullptr;
     int* ctl = nullptr;
