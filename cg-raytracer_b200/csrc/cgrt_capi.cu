@@ -245,6 +245,10 @@ struct cgrt_scene {
     DevScene dev{};
 
     std::vector<cgrt_point_light> lights;
+    std::vector<float> sphLights; // [n][7] position, radius, colour (src/scene.h:47-51)
+    unsigned softSeed = 1u;
+    DevBuf<int> softList;
+    DevBuf<float> soft;
 
     // per-frame parameter block: pinned ring -> device block
     static const int RING = 64;
@@ -320,6 +324,7 @@ static void destroyScene(cgrt_scene* s)
     s->lit.release(); s->pathPix.release(); s->counts.release(); s->tileList.release(); s->tileSeq.release(); s->frame.release();
     s->tests.release(); s->hitRec.release(); s->hitList.release(); s->pathDepth.release(); s->replayShadow.release(); s->replayQ.release();
     for (int k = 0; k < 2; k++) { s->cRay[k].release(); s->cRes[k].release(); s->sRay[k].release(); s->sRes[k].release(); }
+    s->softList.release(); s->soft.release();
     s->waveRays.release(); s->waveFin.release(); s->waveCtl.release(); s->waveTrace.release();
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->hParamRing) cudaFreeHost(s->hParamRing);
@@ -630,6 +635,15 @@ int cgrt_scene_set_lights(cgrt_scene* s, const cgrt_point_light* lights, int32_t
     if (!s || n < 0 || (n > 0 && !lights)) return fail(CGRT_ERR_INVALID, "bad lights");
     std::lock_guard<std::mutex> lk(s->mu);
     s->lights.assign(lights, lights + n);
+    return CGRT_OK;
+}
+
+int cgrt_scene_set_spherical_lights(cgrt_scene* s, const float* lights, int32_t n, uint32_t seed)
+{
+    if (!s || n < 0 || n > 64 || (n > 0 && !lights)) return fail(CGRT_ERR_INVALID, "bad spherical lights");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->sphLights.assign(lights, lights + (size_t)n * 7);
+    s->softSeed = seed;
     return CGRT_OK;
 }
 
@@ -1029,6 +1043,7 @@ static bool useWave(const cgrt_scene* s, const FrameParams& P)
         pref = (e && std::strcmp(e, "rounds") == 0) ? 0 : ((e && std::strcmp(e, "wave") == 0) ? 1 : 2);
     }
     if (pref == 0 || !useRounds(s, P) || P.nSlots >= (1 << 26) || P.traceLimit > 16) return false; // ray record: level << 26 | slot
+    if (P.nSph > 0) return false; // spherical-light soft shadows are a pass of the round pipeline (before its shading kernel)
     // (shares of a multi-GPU frame: the one-launch form also wins on shallow frames up to ~2 M slots per rank - C2 on 4 GPUs
     // 0.23 vs 0.37 ms, C5 on 4 GPUs 0.58 vs 0.64 ms - where the round pipeline's per-launch floors no longer shrink with the share)
     return pref == 1 || P.traceLimit >= 3 || P.nSlots < 400000 || (P.world > 1 && P.nSlots < 2500000);
@@ -1119,6 +1134,7 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
     P.width = p->width;
     P.height = p->height;
     P.nLights = (int)s->lights.size();
+    P.nSph = (int)(s->sphLights.size() / 7);
     P.traceLimit = p->trace_limit;
     P.tileW = L.tileW;
     P.tileH = L.tileH;
@@ -1156,6 +1172,10 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
         RC(s->hitRec.ensure(cap * pathLevels * 3));
         RC(s->pathDepth.ensure(cap));
         RC(s->lit.ensure(cap * pathLevels * nL));
+        if (P.nSph > 0) {
+            RC(s->softList.ensure(cap * pathLevels + 1));
+            RC(s->soft.ensure(cap * pathLevels * (size_t)P.nSph));
+        }
         const size_t capR = cap + (size_t)CGRT_MAX_CHAINS * P.tileW * P.tileH; // per-chain rounding to whole tiles
         for (int k = 0; k < 2; k++) {
             RC(s->cRay[k].ensure(capR * 3));
@@ -1177,7 +1197,8 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
     RC(s->counts.ensure(CGRT_CNT_TOTAL * CGRT_MAX_CHAINS));
     RC(s->tests.ensure(6));
     // parameter block: FrameParams header + lights (2 x float4 each)
-    const size_t need = CGRT_PARAM_BLOCK_HEADER + (size_t)nL * 32;
+    if (P.nSph > 0 && !useRounds(s, P)) return fail(CGRT_ERR_INVALID, "spherical lights need a scene with a search tree (not CGRT_SCENE_EXACT_ONLY / NO_SUBTREES)");
+    const size_t need = CGRT_PARAM_BLOCK_HEADER + ((size_t)nL + (size_t)P.nSph) * 32;
     if (need > s->paramBlockBytes || !s->hParamRing) {
         CK(cudaDeviceSynchronize());
         if (s->hParamRing) cudaFreeHost(s->hParamRing);
@@ -1221,7 +1242,12 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
         hl[2 * i] = make_float4(l.position[0], l.position[1], l.position[2], 0.0f);
         hl[2 * i + 1] = make_float4(l.color[0], l.color[1], l.color[2], 0.0f);
     }
-    const size_t bytes = CGRT_PARAM_BLOCK_HEADER + s->lights.size() * 32;
+    for (int i = 0; i < P.nSph; i++) { // spherical lights follow the point lights: [position | radius] [colour | -]
+        const float* q = s->sphLights.data() + 7 * (size_t)i;
+        hl[2 * (s->lights.size() + i)] = make_float4(q[0], q[1], q[2], q[3]);
+        hl[2 * (s->lights.size() + i) + 1] = make_float4(q[4], q[5], q[6], 0.0f);
+    }
+    const size_t bytes = CGRT_PARAM_BLOCK_HEADER + (s->lights.size() + (size_t)P.nSph) * 32;
     CK(cudaMemcpyAsync(s->dParamBlock.p, slot, bytes, cudaMemcpyHostToDevice, st));
     WaveBuffers B;
     B.hitQ = s->hitQ.p;
@@ -1256,6 +1282,9 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
         RB.pathDepth = s->pathDepth.p;
         RB.counts = s->counts.p;
         RB.levels = std::max(P.traceLimit, 1);
+        RB.softList = nullptr;
+        RB.soft = nullptr;
+        RB.softSeed = 0u;
         WaveQ Q;
         Q.rays = s->waveRays.p;
         Q.fin = s->waveFin.p;
@@ -1299,6 +1328,9 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
             RB[c].pathDepth = s->pathDepth.p;
             RB[c].counts = s->counts.p + c * CGRT_CNT_TOTAL;
             RB[c].levels = std::max(P.traceLimit, 1);
+            RB[c].softList = s->softList.p;
+            RB[c].soft = s->soft.p;
+            RB[c].softSeed = s->softSeed;
         }
         launches = launchRoundPipeline(s->dev, (const FrameParams*)s->dParamBlock.p, P,
                                        (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), RB, nChains, s->chainSync,
@@ -1367,6 +1399,11 @@ int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
         for (int l = 0; l < P.traceLimit; l++) {
             stats->shadow += (uint64_t)counts[CGRT_CNT_HIT + l] * (uint64_t)P.nLights;
             if (l >= 1) stats->bounce += (uint64_t)counts[CGRT_CNT_BOUNCE + l];
+        }
+        if (P.nSph > 0) { // 200 sample rays per hit record and spherical light (main.cpp:177)
+            int nHits = 0;
+            CK(cudaMemcpy(&nHits, s->softList.p + (size_t)std::max(P.nSlots, 1) * std::max(P.traceLimit, 1), sizeof(int), cudaMemcpyDeviceToHost));
+            stats->shadow += 200ull * (uint64_t)nHits * (uint64_t)P.nSph;
         }
         stats->replayed_closest = (uint32_t)counts[CGRT_CNT_REPLAY_PATHS];
         stats->replayed_shadow = (uint32_t)counts[CGRT_CNT_REPLAY_SHADOW];

@@ -978,9 +978,11 @@ __global__ void __launch_bounds__(128, CGRT_MINBLOCKS) k_shadow_replay(DevScene 
 
 // direct colour of one hit record: shading(), src/main.cpp:160-235 (point-light loop :220-232)
 // CG: the lit flags were written by other SMs during this kernel (persistent wavefront): read them through L2
+// nSph / soft: spherical lights (main.cpp:168-218) come first in the sum: (diffuse + specular of a point light at the centre)
+// times the fraction of the light's 200 sample rays that arrive (k_soft_shadows)
 template <bool CG = false>
 RT_DEV V3 directColour(const DevScene& S, const float4* __restrict__ lights, int nL, const float4& a, const float4& b,
-                       const float4& c, const uint8_t* __restrict__ lit, V3& ks)
+                       const float4& c, const uint8_t* __restrict__ lit, V3& ks, int nSph = 0, const float* __restrict__ soft = nullptr)
 {
     const V3 P = mk3(a), N = mk3(b), D = mk3(c);
     const int mat = f2i(a.w);
@@ -990,6 +992,19 @@ RT_DEV V3 directColour(const DevScene& S, const float4* __restrict__ lights, int
     ks = mk3(m1);
     const float shininess = m0.w;
     V3 result = mk3(0.0f, 0.0f, 0.0f);
+    for (int l = 0; l < nSph; l++) {
+        const V3 lightPos = mk3(__ldg(lights + 2 * (nL + l))), lightCol = mk3(__ldg(lights + 2 * (nL + l) + 1));
+        const V3 fromPosToLight = normalize3(lightPos - P);
+        V3 diffuse = mk3(0.0f, 0.0f, 0.0f), specular = diffuse;
+        const float diffuseCos = dot3(fromPosToLight, N);
+        if (!(diffuseCos <= 0)) diffuse = (lightCol * kd) * diffuseCos;
+        const V3 reflected = normalize3(reflect3(D, N));
+        const float specularCos = dot3(reflected, fromPosToLight);
+        if (!(specularCos <= 0)) specular = (lightCol * ks) * (float)pow((double)specularCos, (double)shininess);
+        const float softShadowCounter = soft[l];
+        result = result + diffuse * softShadowCounter;
+        result = result + specular * softShadowCounter;
+    }
     for (int l = 0; l < nL; l++) {
         const V3 lightPos = mk3(__ldg(lights + 2 * l)), lightCol = mk3(__ldg(lights + 2 * l + 1));
         const V3 fromPosToLight = normalize3(lightPos - P);
@@ -1676,7 +1691,8 @@ __global__ void __launch_bounds__(128) k_shade_slots(DevScene S, const FramePara
             for (int k = 0; k < depth; k++) {
                 const int rec = slot * B.levels + k;
                 const float4* r = B.hitRec + 3 * (size_t)rec;
-                direct[k] = directColour(S, lights, nL, r[0], r[1], r[2], B.lit + (size_t)rec * nL, ksv[k]);
+                direct[k] = directColour(S, lights, nL, r[0], r[1], r[2], B.lit + (size_t)rec * nL, ksv[k], P.nSph,
+                                         P.nSph ? B.soft + (size_t)rec * P.nSph : nullptr);
             }
             int k = depth - 1;
             V3 colour = (ksv[k].z <= 0.01f) ? direct[k] : direct[k] + mk3(0.0f, 0.0f, 0.0f) * ksv[k];
@@ -1686,6 +1702,65 @@ __global__ void __launch_bounds__(128) k_shade_slots(DevScene S, const FramePara
             if (wrote) storeRGB(fb, outIdx, colour);
         }
         noteColoured(B.counts + CGRT_CNT_BBOX, wrote, x, P.height - 1 - y, P.width, P.height);
+    }
+}
+
+// ---- spherical-light soft shadows (src/main.cpp:168-218): 200 sample rays per hit and spherical light -------------------------
+// The reference draws the sample points with std::random_device (non-deterministic); here a counter-based generator keyed by
+// (hit record, light, sample, frame seed): three N(0,1) values by Box-Muller from hashed uniforms, normalised (randomUnitVector,
+// :46-59) - the same distribution, reproducible frames. Each sample is a bounded any-hit query: ray.t = distance to the sample
+// point, lit iff intersect() finds nothing closer (:181-199; the reference's `newRay.t > lightT` branch cannot fire).
+// k_soft_list compacts the frame's hit records; k_soft_shadows: one 256-thread block per (hit record, light), one thread per sample.
+__global__ void k_soft_list(const FrameParams* __restrict__ Pp, RoundBuffers B, int cap)
+{
+    const int n = Pp->nSlots;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int slot = base + threadIdx.x;
+        const int depth = slot < n ? B.pathDepth[slot] : 0;
+        for (int k = 0; k < B.levels; k++) {
+            const int q = warpPush(B.softList + cap, k < depth);
+            if (k < depth) B.softList[q] = slot * B.levels + k;
+        }
+    }
+}
+RT_DEV unsigned hash32(unsigned x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+RT_DEV float uniform01(unsigned h) { return ((h >> 8) + 0.5f) * (1.0f / 16777216.0f); } // (0, 1)
+__global__ void __launch_bounds__(256) k_soft_shadows(DevScene S, const FrameParams* __restrict__ Pp, const float4* __restrict__ lights,
+                                                      RoundBuffers B, int cap)
+{
+    __shared__ int litCount;
+    const int nSph = Pp->nSph, nL = Pp->nLights;
+    const int nHits = B.softList[cap];
+    for (int item = blockIdx.x; item < nHits * nSph; item += gridDim.x) {
+        const int rec = B.softList[item / nSph], l = item % nSph;
+        if (threadIdx.x == 0) litCount = 0;
+        __syncthreads();
+        if (threadIdx.x < 200) {
+            const float4 hp = B.hitRec[3 * (size_t)rec];
+            const V3 pointOn = mk3(hp);
+            const float4 lp = __ldg(lights + 2 * (nL + l));
+            // randomUnitVector: y, x, s ~ N(0,1)
+            const unsigned key = hash32((unsigned)rec * 0x9e3779b9u + (unsigned)l * 0x85ebca6bu + threadIdx.x * 0xc2b2ae35u + B.softSeed);
+            const float u1 = uniform01(hash32(key ^ 0x68bc21ebu)), u2 = uniform01(hash32(key ^ 0x02e5be93u));
+            const float u3 = uniform01(hash32(key ^ 0x967a889bu)), u4 = uniform01(hash32(key ^ 0x368cc8b7u));
+            const float r1 = sqrtf(-2.0f * logf(u1)), r2 = sqrtf(-2.0f * logf(u3));
+            const V3 g = mk3(r1 * cosf(6.2831853f * u2), r1 * sinf(6.2831853f * u2), r2 * cosf(6.2831853f * u4));
+            const V3 randomPointOnSphere = mk3(lp) + lp.w * normalize3(g);
+            const V3 dir = normalize3(randomPointOnSphere - pointOn);
+            const V3 org = pointOn + 0.001f * dir;
+            const float lightT = length3(org - randomPointOnSphere);
+            TraceResult R;
+            // intersect(newRay) with ray.t = lightT: true iff an acceptable triangle (or a sphere) lies closer
+            const bool blocked = traverseSpec<true>(S, org, dir, lightT, 0.0f, __int_as_float(0x7f800000), R);
+            if (!blocked) atomicAdd(&litCount, 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) B.soft[(size_t)rec * nSph + l] = (float)litCount / 200.0f;
+        __syncthreads();
     }
 }
 
@@ -2314,6 +2389,13 @@ int launchRoundPipeline(const DevScene& S, const FrameParams* dP, const FramePar
     for (int c = 1; c < nChains; c++) {
         cudaEventRecord(sync.join[c], sync.streams[c]);
         cudaStreamWaitEvent(st, sync.join[c], 0);
+    }
+    if (hP.nSph > 0) { // spherical-light soft shadows of every hit record of the frame, before the shading pass reads them
+        const int capSoft = hP.nSlots * chains[0].levels;
+        cudaMemsetAsync(chains[0].softList + capSoft, 0, sizeof(int), st);
+        k_soft_list<<<flat, 128, 0, st>>>(dP, chains[0], capSoft);
+        k_soft_shadows<<<numSMs * 8, 256, 0, st>>>(S, dP, dLights, chains[0], capSoft);
+        launches += 2;
     }
     traceBegin(tr, 3, st);
     k_shade_slots<<<flat, 128, 0, st>>>(S, dP, dLights, chains[0], dTileSeq, fb);

@@ -88,6 +88,7 @@ struct FrameParams {
     int tileW, tileH, tilesX;
     int world, rank;
     int screenLayout;       // 1: pixels are written at their Screen position (row H-1-y); 0: tile-major buffer of this rank
+    int nSph;               // spherical lights (2 x float4 each, after the point lights in the parameter block)
 };
 
 // Queues of the wavefront (all sized for the worst case `cap` = nSlots; only the used prefix is ever touched).
@@ -136,6 +137,10 @@ struct RoundBuffers {
     int* pathDepth;    // [slot] number of levels that recorded a hit (0: the pixel is already final)
     int* counts;
     int levels;
+    // spherical-light soft shadows (src/main.cpp:168-218), scenes with Scene::sphericalLight only
+    int* softList;     // hit records of the frame (slot * levels + level), compacted; softList[cap * levels] = their number
+    float* soft;       // [(slot * levels + level) * nSph + light] fraction of the 200 sample rays that reach the light
+    unsigned softSeed;
 };
 
 // ---- persistent wavefront (cgrt_wave.cuh): control block + ticket queue of the single-kernel frame ----------------------------

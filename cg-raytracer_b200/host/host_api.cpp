@@ -340,6 +340,14 @@ RenderReport renderRayTracing(const Scene& scene, const Trackball& camera, const
         lights.push_back(c);
     }
     if (cgrt_scene_set_lights(bvh.handle(), lights.data(), (int32_t)lights.size()) != CGRT_OK) throwLast("set_lights");
+    {
+        std::vector<float> sph; // Scene::sphericalLight, read live like the point lights
+        for (const SphericalLight& l : scene.sphericalLight) {
+            const float q[7] = {l.position.x, l.position.y, l.position.z, l.radius, l.color.x, l.color.y, l.color.z};
+            sph.insert(sph.end(), q, q + 7);
+        }
+        if (cgrt_scene_set_spherical_lights(bvh.handle(), sph.data(), (int32_t)(sph.size() / 7), 1u) != CGRT_OK) throwLast("set_spherical_lights");
+    }
     if (!scene.spheres.empty() || bvh.scene() == &scene) {
         // spheres are read live through the scene (bvh.cpp:878)
         std::vector<float> sp;

@@ -161,6 +161,13 @@ int cgrt_scene_create(const cgrt_scene_desc* desc, const cgrt_scene_options* opt
 void cgrt_scene_destroy(cgrt_scene* s);
 int cgrt_scene_set_lights(cgrt_scene* s, const cgrt_point_light* lights, int32_t n);
 int cgrt_scene_set_spheres(cgrt_scene* s, const float* spheres /* [n][12] */, int32_t n);
+/* Scene::sphericalLight (src/scene.h:47-51, preset CornellBoxSphericalLight src/scene.cpp:27-32) and the soft shadows of
+ * shading() (src/main.cpp:168-218): per hit and spherical light 200 sample rays towards random points of the light's sphere
+ * (randomUnitVector :46-59), the light's diffuse + specular term scaled by the fraction that arrives; spherical lights come
+ * before the point lights in the sum. The reference draws the samples from std::random_device (non-deterministic): here a
+ * counter-based generator keyed by (hit, light, sample, seed) - same distribution, reproducible frames; parity with the
+ * reference is statistical by nature. lights[n][7] = position, radius, colour; n <= 64. Read at the next render. */
+int cgrt_scene_set_spherical_lights(cgrt_scene* s, const float* lights /* [n][7] */, int32_t n, uint32_t seed);
 
 /* BoundingVolumeHierarchy::numLevels() src/bounding_volume_hierarchy.cpp:214-224 */
 int cgrt_bvh_num_levels(const cgrt_scene* s);

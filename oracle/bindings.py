@@ -216,6 +216,15 @@ class CpuScene:
         l = np.ascontiguousarray(lights, np.float32).reshape(-1, 6)
         self.lib.fn("scene_set_lights")(self.h, l.shape[0], _fp(l))
 
+    def set_spherical_lights(self, lights, seed=1):
+        """[n][7] = position, radius, colour (src/scene.h:47-51); restated in the oracle library only (main.cpp:168-218)."""
+        l = np.ascontiguousarray(lights, np.float32).reshape(-1, 7)
+        f = self.lib.lib.orc_scene_set_spherical_lights
+        f.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+        f(self.h, l.shape[0], _fp(l))
+        self.lib.lib.orc_set_soft_shadow_seed.argtypes = [C.c_uint]
+        self.lib.lib.orc_set_soft_shadow_seed(seed)
+
     def bvh(self, mode=1, max_depth=12):
         return CpuBVH(self, mode, max_depth)
 

@@ -632,3 +632,63 @@ def test_bloom_against_sequential_restatement(capi, oracle, gpu):
     assert np.array_equal(bits(got), bits(want))
     with pytest.raises(capi.CgrtError):
         s.render_effects(cam, W, H, trace_limit=L, bloom=True, antialias=True)
+
+
+def test_spherical_light_soft_shadows(capi, oracle, gpu):
+    """Scene::sphericalLight (preset CornellBoxSphericalLight, scene.cpp:27-32) and shading()'s soft shadows (main.cpp:168-218):
+    200 sample rays per hit and light. (i) radius 0: every sample is the same ray, nothing is random - frame and ray counters
+    equal the oracle's exactly (tolerance 1/255 for pow). (ii) radius 0.1: the reference itself is non-deterministic
+    (std::random_device), so parity is statistical: against the per-pixel mean and spread of 12 oracle frames with different
+    seeds, the GPU frame (its own counter-based generator) must lie within 5 standard errors of a 200-sample estimate for
+    >= 99.5 % of the pixels, with no bias in the image mean. (iii) reproducible for a fixed seed, different for another."""
+    g = load_golden("cornell")
+    W = H = 128
+    L = 2
+    cam, ocam = capi.make_camera(W, H), ob.default_camera(W, H)
+    none = np.zeros((0, 6), np.float32)
+    s = capi.Scene(g.flat, lights=none)
+    # (i) deterministic case
+    point = np.array([[0, 0.45, 0, 0.0, 1, 1, 1]], np.float32)
+    s.set_spherical_lights(point)
+    got, st = s.render(cam, W, H, trace_limit=L)
+    osc = oracle.scene(g.flat, none)
+    osc.set_spherical_lights(point, seed=1)
+    want, cnt = osc.bvh().render(ocam, W, H, trace_limit=L)
+    check_frame(got, st, want, cnt)
+    assert st["shadow"] == 200 * (st["primary_hit"] + (cnt["shadow"] // 200 - cnt["primary_hit"])) == cnt["shadow"]
+    # (ii) statistical case
+    light = np.array([[0, 0.45, 0, 0.1, 1, 1, 1]], np.float32)
+    s.set_spherical_lights(light, seed=7)
+    got, st = s.render(cam, W, H, trace_limit=L)
+    frames = []
+    for seed in range(1, 13):
+        osc.set_spherical_lights(light, seed=seed)
+        f, cnt = osc.bvh().render(ocam, W, H, trace_limit=L)
+        frames.append(f)
+    frames = np.stack(frames)
+    mean, sd = frames.mean(axis=0), frames.std(axis=0, ddof=1)
+    assert st["shadow"] == cnt["shadow"] and st["bounce"] == cnt["bounce"] and st["primary_hit"] == cnt["primary_hit"]
+    # one frame's deviation from the 12-frame mean: sd * sqrt(1 + 1/12); floor for pixels whose samples all agree
+    tol = 5.0 * sd * np.sqrt(1.0 + 1.0 / 12.0) + 2.0 / 255.0
+    inside = (np.abs(got - mean) <= tol).all(axis=2)
+    assert inside.mean() >= 0.995, inside.mean()
+    lit = mean.sum(axis=2) > 0
+    assert abs(float(got[lit].mean()) - float(mean[lit].mean())) < 0.003
+    penumbra = (sd.sum(axis=2) > 0.01).sum()
+    assert penumbra > 200, "the test frame must contain a penumbra"
+    # (iii) seeds
+    again, _ = s.render(cam, W, H, trace_limit=L)
+    assert np.array_equal(bits(again), bits(got))
+    s.set_spherical_lights(light, seed=8)
+    other, _ = s.render(cam, W, H, trace_limit=L)
+    assert not np.array_equal(bits(other), bits(got)) and np.abs(other - got).max() < 0.5
+    # spherical lights and point lights together: the point lights' part is the frame without spherical lights
+    two = np.array([[0.3, 0.2, -0.4, 0.2, 0.9, 0.4]], np.float32)
+    s.set_lights(two)
+    s.set_spherical_lights(np.zeros((0, 7), np.float32))
+    base, _ = s.render(cam, W, H, trace_limit=1)
+    s.set_spherical_lights(point)
+    both, _ = s.render(cam, W, H, trace_limit=1)
+    s.set_lights(none)
+    sph_only, _ = s.render(cam, W, H, trace_limit=1)
+    assert np.abs(both - (sph_only + base)).max() <= 2e-6

@@ -78,3 +78,45 @@ def test_primary_rays(oracle, golden):
     rays = oracle.generate_rays(cam, golden.W, golden.H)
     n = golden.W * golden.H
     assert np.array_equal(bits(rays.view(np.float32)), bits(golden.rays[:n].view(np.float32)))
+
+
+def test_bloom_restatement_against_numpy(oracle):
+    """orc_bloom (main.cpp:586-628 restated in C++) against an independent numpy transcription of the same in-place recurrence."""
+    rng = np.random.default_rng(0)
+    f = (rng.random((26, 31, 3)) * 0.8).astype(np.float32)
+    got = oracle.bloom(f)
+    H, W = f.shape[:2]
+    m = np.where((f[..., 0] + f[..., 1] + f[..., 2] > 1)[..., None], f, 0).astype(np.float32)[::-1].copy()  # rows in ray space
+    for y in range(H):
+        for x in range(W):
+            acc, cnt = m[y, x].copy(), 1
+            for i in range(-10, 11):
+                if y + i < 0 or y + i > H - 1:
+                    continue
+                for j in range(-10, 11):
+                    if (i == 0 and j == 0) or x + j < 0 or x + j > W - 1:
+                        continue
+                    acc = (acc + m[y + i, x + j]).astype(np.float32)
+                    cnt += 1
+            m[y, x] = (acc / np.float32(cnt)).astype(np.float32)
+    want = (m[::-1] + f).astype(np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_spherical_light_restatement_properties(oracle):
+    """Soft shadows in the oracle (main.cpp:168-218): 200 sample rays per hit, a zero-radius light gives all-or-nothing factors,
+    a finite one a penumbra whose mean lies between them; fixed seed -> same frame."""
+    g = load_golden("cornell")
+    none = np.zeros((0, 6), np.float32)
+    sc = oracle.scene(g.flat, none)
+    W = H = 48
+    cam = ob.default_camera(W, H)
+    sc.set_spherical_lights(np.array([[0, 0.45, 0, 0.0, 1, 1, 1]], np.float32), seed=1)
+    hard, cnt = sc.bvh().render(cam, W, H, trace_limit=1, nthreads=1)
+    assert cnt["shadow"] == 200 * cnt["primary_hit"]
+    sc.set_spherical_lights(np.array([[0, 0.45, 0, 0.15, 1, 1, 1]], np.float32), seed=1)
+    soft, _ = sc.bvh().render(cam, W, H, trace_limit=1, nthreads=1)
+    again, _ = sc.bvh().render(cam, W, H, trace_limit=1, nthreads=1)
+    assert np.array_equal(soft, again)
+    changed = np.abs(soft - hard).sum(axis=2) > 1e-4
+    assert 10 < changed.sum() < 0.6 * W * H  # a penumbra appears, most pixels keep their hard-shadow value
