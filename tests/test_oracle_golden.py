@@ -2,7 +2,7 @@
 produced for the committed golden vectors (tests/golden/*.npz, written by tests/golden/make_golden.py from oracle/_ref)."""
 import numpy as np
 
-from conftest import GOLDEN, bits, hits_equal, same_bits
+from conftest import GOLDEN, bits, hits_equal, same_bits, load_golden
 from oracle import bindings as ob
 
 
