@@ -139,8 +139,9 @@ typedef struct cgrt_render_stats {
     uint32_t replayed_closest, replayed_shadow;    /* rays the speculative traversal could not certify and handed to the
                                                       exact reference-order traversal (same results, more work) */
     uint32_t pipeline;                             /* which kernel set rendered the frame: 0 counting wavefront (CGRT_RENDER_COUNT),
-                                                      1 path pipeline (scenes without a fast tree), 2 round pipeline
-                                                      (CGRT_PIPELINE=rounds), 3 persistent wavefront k_wave (default) */
+                                                      1 path pipeline (scenes without a fast tree), 2 round pipeline,
+                                                      3 persistent wavefront k_wave (chosen per frame, DESIGN 4.4;
+                                                      CGRT_PIPELINE=wave|rounds forces one) */
 } cgrt_render_stats;
 
 typedef struct cgrt_scene cgrt_scene; /* opaque: flattened scene + BVH resident in HBM */
