@@ -268,6 +268,8 @@ struct cgrt_scene {
     DevBuf<float4> cRay[2], cRes[2], sRay[2], sRes[2];
     DevBuf<float4> waveRays, waveFin; // persistent wavefront: ticket-indexed ray records / finished-search records
     DevBuf<int> waveCtl, waveTrace;
+    DevBuf<float4> waveResume;
+    DevBuf<unsigned> waveLat;
     uint32_t waveSeq = 0;
     int lastPipeline = 0; // 0 counting wavefront, 1 path pipeline, 2 round pipeline
     int lastChains = 1;
@@ -325,7 +327,7 @@ static void destroyScene(cgrt_scene* s)
     s->tests.release(); s->hitRec.release(); s->hitList.release(); s->pathDepth.release(); s->replayShadow.release(); s->replayQ.release();
     for (int k = 0; k < 2; k++) { s->cRay[k].release(); s->cRes[k].release(); s->sRay[k].release(); s->sRes[k].release(); }
     s->softList.release(); s->soft.release();
-    s->waveRays.release(); s->waveFin.release(); s->waveCtl.release(); s->waveTrace.release();
+    s->waveRays.release(); s->waveFin.release(); s->waveCtl.release(); s->waveTrace.release(); s->waveResume.release();
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->hParamRing) cudaFreeHost(s->hParamRing);
     if (s->hFramePinned) cudaFreeHost(s->hFramePinned);
@@ -1052,15 +1054,16 @@ static bool useWave(const cgrt_scene* s, const FrameParams& P)
 // tickets idle lanes hold beyond the last ray (one per resident lane at most)
 static size_t waveTicketCap(const FrameParams& P)
 {
-    return (size_t)std::max(P.nSlots, 1) * std::max(P.traceLimit, 1) * (1 + (size_t)std::max(P.nLights, 0)) + ((size_t)1 << 19);
+    return (size_t)std::max(P.nSlots, 1) * std::max(P.traceLimit, 1) * (1 + (size_t)std::max(P.nLights, 0)) + ((size_t)1 << 19) +
+           (size_t)waveGridBlocks(1) * 128 * 160; // + the second records of rays handed over at the change-over (one per lane, <= 160 SMs)
 }
 
-// scheduling knobs / watchdog of the persistent wavefront (CGRT_WAVE="mode=0,group_below=400000,switch=0,fin=0,timeout_ms=4000"; 0 = automatic; they
+// scheduling knobs / watchdog of the persistent wavefront (CGRT_WAVE="mode=0,group_below=400000,switch=0,fin=0,handover=1,timeout_ms=4000"; 0 = automatic; they
 // change speed only, never results). mode 0: the search form follows the size of this rank's share of the frame - one lane per
 // ray for large shares (throughput), eight lanes per ray for small ones (latency)
 static void waveTuning(WaveQ& Q, int nSlots, int nLights)
 {
-    static int mode = 0, groupBelow = 400000, fin = 0, timeoutMs = 4000, switchBelow = 0;
+    static int mode = 0, groupBelow = 400000, fin = 0, timeoutMs = 4000, switchBelow = 0, handOver = 1;
     static bool loaded = false;
     if (!loaded) {
         loaded = true;
@@ -1080,6 +1083,7 @@ static void waveTuning(WaveQ& Q, int nSlots, int nLights)
                     else if (key == "fin") fin = v;
                     else if (key == "switch") switchBelow = v;
                     else if (key == "timeout_ms") timeoutMs = v;
+                    else if (key == "handover") handOver = v;
                 }
                 pos = c + 1;
             }
@@ -1093,6 +1097,7 @@ static void waveTuning(WaveQ& Q, int nSlots, int nLights)
     // frame, 60 K for smaller shares)
     Q.switchBelow = Q.mode == 2 ? 0 : (switchBelow > 0 ? switchBelow : (nSlots >= 1500000 ? 100000 : 60000));
     Q.timeoutNs = (unsigned long long)std::max(timeoutMs, 1) * 1000000ull;
+    if (!handOver) Q.resume = nullptr; // rays finish in the search form they started in
 }
 
 static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, FrameParams& P,
@@ -1168,6 +1173,7 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
             CK(cudaMemset(s->waveFin.p, 0, tickets * 2 * sizeof(float4)));
         }
         RC(s->waveCtl.ensure(WCTL_INTS));
+        RC(s->waveResume.ensure((size_t)waveGridBlocks(s->di.numSMs) * 128 * WAVE_RESUME_F4));
     } else if (useRounds(s, P)) { // round pipeline: records indexed by (pixel slot, level), two ray lists per kind
         RC(s->hitRec.ensure(cap * pathLevels * 3));
         RC(s->pathDepth.ensure(cap));
@@ -1292,8 +1298,17 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
         Q.seq = ++s->waveSeq;
         if (Q.seq == 0u) Q.seq = ++s->waveSeq;
         Q.cap = (int)std::min<size_t>(s->waveRays.n / 3, (size_t)0x3fffffff);
+        Q.resume = s->waveResume.p;
+        Q.lat = nullptr;
+#ifdef CGRT_WAVE_LAT
+        if (getenv("CGRT_WAVE_LAT")) {
+            RC(s->waveLat.ensure((size_t)Q.cap * 16));
+            CK(cudaMemsetAsync(s->waveLat.p, 0, (size_t)Q.cap * 16 * sizeof(unsigned), st));
+            Q.lat = s->waveLat.p;
+        }
+#endif
         Q.trace = nullptr;
-        if (getenv("CGRT_WAVE_TRACE")) { // timeline of the frame's counters (cgrt_debug_wave_timeline); off by default
+        if (getenv("CGRT_WAVE_TRACE") || Q.lat != nullptr) { // timeline of the frame's counters (cgrt_debug_wave_timeline); off by default
             RC(s->waveTrace.ensure((size_t)WAVE_TRACE_SAMPLES * 8));
             CK(cudaMemsetAsync(s->waveTrace.p, 0, (size_t)WAVE_TRACE_SAMPLES * 8 * sizeof(int), st));
             Q.trace = s->waveTrace.p;
@@ -1757,6 +1772,17 @@ int cgrt_debug_wave_timeline(cgrt_scene* s, int32_t* out, int32_t cap)
     return n;
 }
 
+#ifdef CGRT_WAVE_LAT
+// instrumented builds: per-ticket latency records of the last k_wave frame (layout in cgrt_wave.cuh); returns tickets copied
+int cgrt_debug_wave_latency(cgrt_scene* s, uint32_t* out, int32_t cap)
+{
+    if (!s || !out || !s->waveLat.p) return 0;
+    if (useSceneDevice(s) != CGRT_OK) return 0;
+    const int n = (int)std::min<size_t>((size_t)cap, s->waveLat.n / 16);
+    if (cudaMemcpy(out, s->waveLat.p, (size_t)n * 16 * sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+}
+#endif
 #ifdef CGRT_INSTRUMENT
 void cgrt_debug_instrumentation(unsigned long long* out, int reset) { cgrt::readInstrumentation(out, reset != 0); }
 void cgrt_debug_timeline(unsigned int* out, int reset) { cgrt::readTimeline(out, reset != 0); }

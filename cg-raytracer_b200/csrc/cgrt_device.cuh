@@ -776,6 +776,7 @@ RT_DEV bool certifyClosest(const DevScene& S, const V3& o, const V3& d, int pos,
 // reference either descends at every box - then it tests X and ends with ray.t <= tX - or it stops at a box because its ray.t
 // is already at or below that box's entry distance. Its final distance is therefore at most M = max(tX, entry distances of the
 // path's boxes), provided every box is geometrically hit; the predicate is monotone, so !(M + eps >= maxDist) proves "shadowed".
+// (A NaN entry distance stays: `m == m` below; the predicate then fails.)
 RT_DEV bool certifyAny(const DevScene& S, const V3& o, const V3& d, int pos, float tX, float eps, float maxDist)
 {
     float m = tX;
@@ -786,7 +787,7 @@ RT_DEV bool certifyAny(const DevScene& S, const V3& o, const V3& d, int pos, flo
         if (!startsInBox(o, mk3(q0), mk3(q1))) {
             float te = 0.0f;
             if (!slabTest(mk3(q0), mk3(q1), o, d, __int_as_float(0x7f800000), te)) return false;
-            if (!(te <= m)) m = te; // also taken for NaN, which then fails the predicate below
+            if (m == m && !(te <= m)) m = te;
         }
         if (node == 0) break;
         node = __ldg(S.refParent + node);

@@ -156,6 +156,7 @@ struct RoundBuffers {
 #define WCTL_FINEXIT 289  // own 128-byte line
 #define WCTL_T0 4       // low 32 bits of %globaltimer of the first CTA that started (timeline origin)
 #define WCTL_CLOSEAT 224 // 1 + the first ticket of the first part that will never be served (0 = the first part is open)
+#define WCTL_RESUME 256  // search states handed over from the LANE form to the GROUP form at the change-over (WaveQ::resume)
 #define WCTL_DONE 320   // 32 copies of the done flag, one per 128-byte line (ctl[WCTL_DONE + 32 k])
 #define WCTL_SCRATCH (WCTL_DONE + 32 * 32) // 32 words, one per 128-byte line: targets of the release reductions (waveRelease)
 #define WCTL_INTS (WCTL_SCRATCH + 32 * 32)
@@ -170,9 +171,14 @@ struct WaveQ {
     int switchBelow; // mode 1: change over to GROUP when fewer rays than this are in flight (0 = never)
     int finEvery;   // SMs with %smid % finEvery == 0 run the finish warps, the others the search warps
     unsigned long long timeoutNs;
+    float4* resume; // search states of rays handed over at the change-over: WAVE_RESUME_F4 x float4 each, one per LANE-form lane of
+                    // the grid (a lane hands over at most once per frame); nullptr = rays finish in the form they started in
+    unsigned* lat;  // instrumented builds only (-DCGRT_WAVE_LAT): 8 timestamps / counters per ray ticket (tools/wave_latency.py)
     int* trace;     // optional (CGRT_WAVE_TRACE=1): WAVE_TRACE_SAMPLES x 8 ints, one sample of the counters per 4.096 us of the frame
 };
 #define WAVE_TRACE_SAMPLES 1024
+#define WAVE_RESUME_STACK 32                        // deepest traversal stack that is handed over (deeper: the ray stays where it is)
+#define WAVE_RESUME_F4 (1 + WAVE_RESUME_STACK / 2)  // [t, tri, t2, node] + two stack entries (node, entry distance) per float4
 
 #define CGRT_TRACE_MAX_KERNELS (8 * (2 * (CGRT_MAX_LEVELS + 1) + 1) + 2) // chains x (k_gen + 2 per round) + shade
 // optional per-kernel event trace of one wavefront (classes: 0 primary, 1 bounce closest-hit, 2 shadow, 3 shade)

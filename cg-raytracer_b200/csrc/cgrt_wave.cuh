@@ -50,7 +50,7 @@ struct WaveShared {
     uint2 gstack[16][CGRT_STACK8];    // GROUP form: traversal stack of each 8-lane group
 };
 
-enum { WS_NONE = 0, WS_WAIT = 1, WS_RUN = 2 };
+enum { WS_NONE = 0, WS_WAIT = 1, WS_RUN = 2, WS_PASS = 3 };
 
 // Flags, counters and queue records are read with relaxed gpu-scope loads (served by L2, never by L1). An acquire load would
 // make the SM drop its whole L1 (CCTL.IVALL in the SASS) - and with it the BVH nodes of every warp that is searching - on every
@@ -96,8 +96,24 @@ RT_DEV unsigned smId()
     return v;
 }
 
+// instrumented builds (-DCGRT_WAVE_LAT): per ray ticket [emitted, search started, steps, search ended, finish loaded, finish done,
+// form (1 LANE, 2 GROUP, +4 resumed), -] - times in ns since the frame's origin (low 32 bits of %globaltimer - WCTL_T0)
+#ifdef CGRT_WAVE_LAT
+RT_DEV void waveLat(const WaveQ& Q, int tk, int k, unsigned v)
+{
+    if (Q.lat != nullptr && tk >= 0 && tk < Q.cap) Q.lat[16 * (size_t)tk + k] = v;
+}
+RT_DEV unsigned waveNow(const WaveQ& Q) { return (unsigned)globalTimerNs() - ldRelaxedGpu((const unsigned*)Q.ctl + WCTL_T0); }
+#define WAVE_LAT(tk, k, v) waveLat(Q, tk, k, v)
+#define WAVE_LAT_NOW(tk, k) waveLat(Q, tk, k, waveNow(Q))
+#else
+#define WAVE_LAT(tk, k, v)
+#define WAVE_LAT_NOW(tk, k)
+#endif
+
 // ---- queue primitives ---------------------------------------------------------------------------------------------------------
-// Ray record (3 chunks): [origin | tag] [direction | tag] [bound, meta, tag, tag]. tag = sequence number of the frame.
+// Ray record (3 chunks): [origin | tag] [direction | tag] [bound, meta, resume, tag]. tag = sequence number of the frame;
+// resume = 0, or (1 + index of the search state this ray continues from) | stack depth << 24 (hand-over at the change-over).
 //   closest-hit ray: meta = level << 26 | pixel slot, bound = ray.t on entry (FLT_MAX for primary rays, |D| for reflections,
 //                    main.cpp:252-256); its search range is unbounded
 //   shadow ray     : meta = CGRT_RAY_ANY | index of its lit flag, bound = distance to the light (pointInShadow casts it with
@@ -113,10 +129,12 @@ RT_DEV void waveStoreRay(const WaveQ& Q, int tk, unsigned tagBits, const V3& o, 
     const float tag = __uint_as_float(tagBits);
     st128(q, make_float4(o.x, o.y, o.z, tag));
     st128(q + 1, make_float4(d.x, d.y, d.z, tag));
-    st128(q + 2, make_float4(bound, i2f(meta), tag, tag));
+    st128(q + 2, make_float4(bound, i2f(meta), 0.0f, tag));
+    WAVE_LAT_NOW(tk, 0);
 }
 // one round trip: the record of ticket tk if it is complete. Unpacked into the (a, b, c) form the per-ray code shares with the
 // round pipeline: a = [o | tIn], b = [d | maxDist], c = [slot, level or CGRT_RAY_ANY | lit index, eps, -]
+// c.w = the record's resume word
 RT_DEV bool waveLoadRay(const WaveQ& Q, int tk, unsigned tagBits, float4& a, float4& b, float4& c)
 {
     if (tk >= Q.cap) return false; // a ticket beyond every ray the frame can produce: it is never served
@@ -125,16 +143,16 @@ RT_DEV bool waveLoadRay(const WaveQ& Q, int tk, unsigned tagBits, float4& a, flo
     b = ld128(r + 1);
     const float4 m = ld128(r + 2);
     const unsigned s = tagBits;
-    const bool ok = __float_as_uint(a.w) == s && __float_as_uint(b.w) == s && __float_as_uint(m.z) == s && __float_as_uint(m.w) == s;
+    const bool ok = __float_as_uint(a.w) == s && __float_as_uint(b.w) == s && __float_as_uint(m.w) == s;
     const int meta = f2i(m.y);
     if (meta & CGRT_RAY_ANY) {
         a.w = FLT_MAX;
         b.w = m.x;
-        c = make_float4(0.0f, m.y, 0.001f, 0.0f);
+        c = make_float4(0.0f, m.y, 0.001f, m.z);
     } else {
         a.w = m.x;
         b.w = __int_as_float(0x7f800000);
-        c = make_float4(i2f(meta & ((1 << WAVE_SLOT_BITS) - 1)), i2f(meta >> WAVE_SLOT_BITS), 0.0f, 0.0f);
+        c = make_float4(i2f(meta & ((1 << WAVE_SLOT_BITS) - 1)), i2f(meta >> WAVE_SLOT_BITS), 0.0f, m.z);
     }
     return ok;
 }
@@ -359,10 +377,16 @@ RT_DEV void waveFinishLoop(const DevScene& S, const FrameParams& P, const float4
         if (ready) {
             ftk = -1;
             float4 a, b, c;
+            WAVE_LAT_NOW(tk, 4);
             waveLoadRay(Q, tk, 0u, a, b, c); // (complete: the searcher validated it)
             const int meta = f2i(c.y);
+#ifdef CGRT_WAVE_LAT
+            if (a.x == 1e38f) return; // (keeps the loads above the time stamp)
+            WAVE_LAT_NOW(tk, 8);
+#endif
             if (meta & CGRT_RAY_ANY) { // ---- shadow ray: lit flag
                 const bool shadowed = finishShadowRay<true>(S, a, b, c, res, replayS);
+                WAVE_LAT_NOW(tk, 9);
                 B.lit[meta & 0x3fffffff] = shadowed ? 0 : 1;
             } else { // ---- closest-hit ray of `level`
                 const V3 o = mk3(a), d = mk3(b);
@@ -370,6 +394,10 @@ RT_DEV void waveFinishLoop(const DevScene& S, const FrameParams& P, const float4
                 level = meta;
                 TraceResult R;
                 hit = finishClosestRay<true>(S, a, b, res, R, replayC);
+#ifdef CGRT_WAVE_LAT
+                if (R.t == -1e38f) return;
+                WAVE_LAT_NOW(tk, 9);
+#endif
                 if (!hit) {
                     if (level == 0) { // trace(): miss -> black, src/main.cpp:288-294
                         int x, y, outIdx, local;
@@ -391,6 +419,7 @@ RT_DEV void waveFinishLoop(const DevScene& S, const FrameParams& P, const float4
                     atomicAdd(&sh.stat[WAVE_STAT_HIT + level], 1);
                     if (level == 0) atomicAdd(&sh.stat[WAVE_STAT_PATHS], 1);
                     if (bounce) atomicAdd(&sh.stat[WAVE_STAT_BOUNCE + level + 1], 1);
+                    WAVE_LAT_NOW(tk, 10);
                 }
                 if (replayC) atomicAdd(&sh.stat[WAVE_STAT_REPLAYC], 1);
             }
@@ -414,6 +443,7 @@ RT_DEV void waveFinishLoop(const DevScene& S, const FrameParams& P, const float4
         }
         base = __shfl_sync(0xffffffffu, base, 0);
         tagBits = __shfl_sync(0xffffffffu, tagBits, 0);
+        if (ready) WAVE_LAT_NOW(tk, 11);
         if (hit && nL > 0) {
             const int firstS = base + sIncl - nShadow;
             for (int l = 0; l < nL; l++) {
@@ -431,6 +461,7 @@ RT_DEV void waveFinishLoop(const DevScene& S, const FrameParams& P, const float4
         }
         // (the children are visible as soon as their records are complete; no flag, no fence. What the batch wrote for phase C -
         // hit records, lit flags, black pixels - is released once, when this warp leaves the loop.)
+        if (ready) WAVE_LAT_NOW(tk, 5);
         if (lane == 0) {
             pendNow = wavePendingIssue(Q, -(long long)n);
             havePend = true;
@@ -449,6 +480,9 @@ RT_DEV void waveFinishLoop(const DevScene& S, const FrameParams& P, const float4
 #ifndef CGRT_WAVE_REFILL
 #define CGRT_WAVE_REFILL 4
 #endif
+#ifndef CGRT_WAVE_GSTEPS
+#define CGRT_WAVE_GSTEPS 4 // GROUP form: steps per burst
+#endif
 // Returns when the frame is done (true) or when the queue has changed over and this warp holds no LANE ray any more (false).
 RT_DEV bool waveLaneLoop(const DevScene& S, const WaveQ& Q, unsigned long long t0)
 {
@@ -461,6 +495,7 @@ RT_DEV bool waveLaneLoop(const DevScene& S, const WaveQ& Q, unsigned long long t
     bool any = false;
     int idlePolls = 0;
     int closeAt = 0x7fffffff; // tickets from this value on will never be served (known once the change-over has been seen)
+    bool drained = false;     // this warp has been handed a ticket >= closeAt: the first part of the queue holds nothing for it any more
     T.t = 0.0f; T.hitTri = -1; T.node = 0u; T.sp = 0;
     K.t2 = 0.0f;
     while (true) {
@@ -473,7 +508,9 @@ RT_DEV bool waveLaneLoop(const DevScene& S, const WaveQ& Q, unsigned long long t
         const unsigned noneMask = __ballot_sync(0xffffffffu, st == WS_NONE || fin);
         const int nNone = __popc(noneMask), nFin = __popc(finMask);
         const bool open = closeAt == 0x7fffffff;
-        const int want = (open && (nNone >= CGRT_WAVE_REFILL || (runMask == 0u && nNone > 0))) ? nNone : 0;
+        // (after the change-over the warps keep taking tickets until each has been handed one beyond the closing value: every
+        // record of the first part is then held by a lane, however far the consumers were behind when the queue closed)
+        const int want = (!drained && (!open || nNone >= CGRT_WAVE_REFILL || runMask == 0u) && nNone > 0) ? nNone : 0;
         int fbase = 0, base = 0;
         unsigned ca = 0u;
         if (lane == 0) {
@@ -490,6 +527,7 @@ RT_DEV bool waveLaneLoop(const DevScene& S, const WaveQ& Q, unsigned long long t
                     st128(Q.fin + 2 * (size_t)pos, make_float4(i2f(tk), i2f(state), T.t, tag));
                     st128(Q.fin + 2 * (size_t)pos + 1, make_float4(i2f(T.hitTri), K.t2, tag, tag));
                 }
+                WAVE_LAT_NOW(tk, 3);
                 st = WS_NONE;
                 tk = -1;
             }
@@ -505,7 +543,48 @@ RT_DEV bool waveLaneLoop(const DevScene& S, const WaveQ& Q, unsigned long long t
             ca = __shfl_sync(0xffffffffu, ca, 0);
             if (ca != 0u) closeAt = (int)(ca - 1u);
         }
+        const bool closed = closeAt != 0x7fffffff;
+        if (closed && want != 0 && base + want > closeAt) drained = true;
         if (st == WS_WAIT && tk >= closeAt) { st = WS_NONE; tk = -1; } // a ticket of the closed part: it will never be served
+        // ---- 1b. after the change-over the rays this warp is still searching are handed over to the GROUP form with their
+        // search state (best candidate, runner-up, traversal stack): a LANE warp with a few long rays left costs the issue slots
+        // of a full one. The ray gets a new record in the second part of the queue that points at the saved state.
+        const bool handOver = closed && Q.resume != nullptr;
+        if (handOver) {
+            const bool mig = st == WS_RUN && state == TRAV_CONTINUE && T.sp <= WAVE_RESUME_STACK;
+            const unsigned migMask = __ballot_sync(0xffffffffu, mig);
+            if (migMask != 0u) {
+                int rbase = 0, qbase = 0;
+                if (lane == 0) {
+                    rbase = atomicAdd(Q.ctl + WCTL_RESUME, __popc(migMask));
+                    qbase = atomicAdd(Q.ctl + WCTL_TAIL2, __popc(migMask));
+                }
+                rbase = __shfl_sync(0xffffffffu, rbase, 0);
+                qbase = __shfl_sync(0xffffffffu, qbase, 0);
+                if (mig) {
+                    const int r = rbase + __popc(migMask & ltMask), ntk = closeAt + qbase + __popc(migMask & ltMask);
+                    float4* dst = Q.resume + (size_t)WAVE_RESUME_F4 * r;
+                    st128(dst, make_float4(T.t, i2f(T.hitTri), K.t2, __uint_as_float(T.node)));
+                    for (int i = 0; i < T.sp; i += 2)
+                        st128(dst + 1 + (i >> 1), make_float4(__uint_as_float(K.n[i]), K.t[i],
+                                                              i + 1 < T.sp ? __uint_as_float(K.n[i + 1]) : 0.0f, i + 1 < T.sp ? K.t[i + 1] : 0.0f));
+                    waveRelease(Q); // the state is in L2 before the record that points at it can be seen
+                    if (ntk < Q.cap) {
+                        const float4* src = Q.rays + 3 * (size_t)tk;
+                        const float4 a = ld128(src), b = ld128(src + 1), m = ld128(src + 2);
+                        const float tag = __uint_as_float(Q.seq | WAVE_TAG2);
+                        float4* q = Q.rays + 3 * (size_t)ntk;
+                        st128(q, make_float4(a.x, a.y, a.z, tag));
+                        st128(q + 1, make_float4(b.x, b.y, b.z, tag));
+                        st128(q + 2, make_float4(m.x, m.y, i2f((r + 1) | (T.sp << 24)), tag));
+                        WAVE_LAT_NOW(ntk, 0);
+                    }
+                    st = WS_NONE;
+                    tk = -1;
+                    state = TRAV_DONE;
+                }
+            }
+        }
         // ---- 2. lanes holding a ticket read their record (complete = the ray exists); a warp with nothing running looks cheaply first
         const bool look = runMask != 0u || wavePeekRay(Q, st == WS_WAIT, tk, Q.seq);
         if (look && st == WS_WAIT) {
@@ -515,12 +594,36 @@ RT_DEV bool waveLaneLoop(const DevScene& S, const WaveQ& Q, unsigned long long t
                 eps = c.z;
                 any = (f2i(c.y) & CGRT_RAY_ANY) != 0;
                 K.t2 = __int_as_float(0x7f800000);
-                state = fastBegin(S, T, mk3(a), mk3(b), a.w); // (the always-list is applied by the finish warps)
-                st = WS_RUN;
+                if (handOver) { // a ray of the first part that arrives after the change-over: passed on to the second part as it is
+                    T.o = mk3(a);
+                    T.d = mk3(b);
+                    T.t = any ? b.w : a.w;                                              // the record's bound
+                    T.node = (uint32_t)(any ? f2i(c.y) : ((f2i(c.y) << WAVE_SLOT_BITS) | f2i(c.x))); // the record's meta word
+                    st = WS_PASS;
+                } else {
+                    state = fastBegin(S, T, mk3(a), mk3(b), a.w); // (the always-list is applied by the finish warps)
+                    st = WS_RUN;
+                    WAVE_LAT_NOW(tk, 1);
+                    WAVE_LAT(tk, 6, 1u);
+                }
+            }
+        }
+        if (handOver) {
+            const unsigned passMask = __ballot_sync(0xffffffffu, st == WS_PASS);
+            if (passMask != 0u) {
+                int qbase = 0;
+                if (lane == 0) qbase = atomicAdd(Q.ctl + WCTL_TAIL2, __popc(passMask));
+                qbase = __shfl_sync(0xffffffffu, qbase, 0);
+                if (st == WS_PASS) {
+                    waveStoreRay(Q, closeAt + qbase + __popc(passMask & ltMask), Q.seq | WAVE_TAG2, T.o, T.d, T.t, (int)T.node);
+                    st = WS_NONE;
+                    tk = -1;
+                    state = TRAV_DONE;
+                }
             }
         }
         if (__ballot_sync(0xffffffffu, st == WS_RUN) == 0u) {
-            if (closeAt != 0x7fffffff && __ballot_sync(0xffffffffu, st == WS_WAIT) == 0u) return false; // nothing held: change form
+            if (drained && __ballot_sync(0xffffffffu, st == WS_WAIT) == 0u) return false; // nothing held, nothing left: change form
             if (waveDone(Q)) return true;
             waveIdle(Q, t0, idlePolls);
             continue;
@@ -560,12 +663,18 @@ RT_DEV void waveGroupLoop(const DevScene& S, const WaveQ& Q, WaveShared& sh, uns
     int hitTri = -1, tk = -1, st = WS_NONE, state = TRAV_DONE, sp = 0;
     uint32_t node = 0u;
     bool any = false;
-    int idlePolls = 0, tick = 0;
+    int idlePolls = 0;
+#ifdef CGRT_WAVE_LAT
+    int nsteps = 0;
+#endif
     while (true) {
         // ---- 1. finished groups hand in their result
         const bool fin = st == WS_RUN && state != TRAV_CONTINUE;
         if (__any_sync(0xffffffffu, fin)) {
             waveFinPush(Q, fin && j == 0, tk, state, t, hitTri, t2);
+#ifdef CGRT_WAVE_LAT
+            if (fin && j == 0) { WAVE_LAT_NOW(tk, 3); WAVE_LAT(tk, 2, (unsigned)nsteps); }
+#endif
             if (fin) { st = WS_NONE; tk = -1; }
         }
         // ---- 2. every empty group takes a ticket, also one of a ray that does not exist yet
@@ -579,13 +688,14 @@ RT_DEV void waveGroupLoop(const DevScene& S, const WaveQ& Q, WaveShared& sh, uns
         }
         // ---- 3. groups holding a ticket read their record (every lane of the group reads it - broadcast loads - and the group
         // starts when all eight have seen it complete). A poll costs the whole warp a round trip to L2: while other groups are
-        // searching, waiting groups look every 4th step
+        // searching it happens once per burst of steps; a warp with nothing running looks cheaply first
         const bool anyRun = __ballot_sync(0xffffffffu, st == WS_RUN) != 0u;
-        if (anyRun ? (__any_sync(0xffffffffu, st == WS_WAIT) && (++tick & 3) == 0) : wavePeekRay(Q, st == WS_WAIT, tk, tagBits)) {
+        if (anyRun ? __any_sync(0xffffffffu, st == WS_WAIT) : wavePeekRay(Q, st == WS_WAIT, tk, tagBits)) {
             float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b = a, c = a;
             const bool rdy = st == WS_WAIT && waveLoadRay(Q, tk, tagBits, a, b, c);
             const unsigned rm = __ballot_sync(0xffffffffu, rdy);
-            if (((rm >> (8 * g)) & 0xFFu) == 0xFFu) {
+            const bool start = ((rm >> (8 * g)) & 0xFFu) == 0xFFu;
+            if (start) {
                 o = mk3(a);
                 d = mk3(b);
                 maxDist = b.w;
@@ -600,7 +710,28 @@ RT_DEV void waveGroupLoop(const DevScene& S, const WaveQ& Q, WaveShared& sh, uns
                 sp = 0;
                 node = T0.node;
                 st = WS_RUN;
+                const int rs = f2i(c.w);
+#ifdef CGRT_WAVE_LAT
+                nsteps = 0;
+                if (j == 0) { WAVE_LAT_NOW(tk, 1); WAVE_LAT(tk, 6, rs != 0 ? 6u : 2u); }
+#endif
+                if (rs != 0) { // a search handed over by a LANE warp: continue from its state (it had passed fastBegin)
+                    const float4* src = Q.resume + (size_t)WAVE_RESUME_F4 * ((rs & 0xffffff) - 1);
+                    const float4 h = ld128(src);
+                    t = h.x;
+                    hitTri = f2i(h.y);
+                    t2 = h.z;
+                    node = __float_as_uint(h.w);
+                    sp = rs >> 24;
+                    state = TRAV_CONTINUE;
+                    for (int i = 2 * j; i < sp; i += 16) {
+                        const float4 e = ld128(src + 1 + (i >> 1));
+                        K[i] = make_uint2(__float_as_uint(e.x), __float_as_uint(e.y));
+                        if (i + 1 < sp) K[i + 1] = make_uint2(__float_as_uint(e.z), __float_as_uint(e.w));
+                    }
+                }
             }
+            __syncwarp();
         }
         if (__ballot_sync(0xffffffffu, st == WS_RUN && state == TRAV_CONTINUE) == 0u) {
             if (__ballot_sync(0xffffffffu, st == WS_RUN) == 0u) {
@@ -610,120 +741,129 @@ RT_DEV void waveGroupLoop(const DevScene& S, const WaveQ& Q, WaveShared& sh, uns
             continue;
         }
         idlePolls = 0;
-        // ---- 4. one step of every active group. The per-lane tests run in divergent code WITHOUT collectives; the group results
-        // are then combined with full-warp ballots / shuffles that all 32 lanes execute together.
-        const bool active = st == WS_RUN && state == TRAV_CONTINUE;
-        const bool isLeaf = (node & CGRT_TRI) != 0u;
-        const float bound = (any ? fminf(t, maxDist) : t) * slack;
-        int pos = -1;                            // leaf: position of this lane's triangle
-        float near = __int_as_float(0x7f800000); // leaf: distance of an acceptable triangle that does not beat the best
-        bool p = false, amb = false;     // p: this lane's child box is hit / this lane's triangle is an acceptable candidate
-        unsigned key = 0xffffffffu;      // ordering key of the lane's result (entry distance | child, or candidate distance)
-        uint32_t id = 0u;
-        float ti = 0.0f;
-        if (active) {
-            if (isLeaf) {
-                // leaf: lane j tests triangle j with the reference's accept arithmetic (cgrt_device.cuh fastStepLeafDyn)
-                const int first = (int)(node & CGRT_IDX_MASK), count = (int)((node >> CGRT_TRICNT_SHIFT) & 7u) + 1;
-                if (j < count) {
-                    const float4* tr = S.tri4f + 4 * (size_t)(first + j);
-                    const float4 pl = __ldg(tr), v0 = __ldg(tr + 1), v1 = __ldg(tr + 2), v2 = __ldg(tr + 3);
-                    pos = f2i(v2.w); // position of the triangle in the reference-ordered arrays
-                    const V3 nrm = mk3(pl);
-                    const float on = dot3(o, nrm);
-                    const bool shortcut = (on == pl.w);
-                    bool cand = true;
-                    float tt = 0.0f;
-                    if (!shortcut) {
-                        const float denominator = dot3(d, nrm);
-                        if (denominator == 0) cand = false;
-                        else {
-                            tt = (pl.w - on) / denominator;
-                            if (tt < 0) cand = false;
-                            else if (hitTri < 0 ? !(tt < t) : !(tt <= t * CGRT_NEAR)) cand = false; // `t >= ray.t` / clearly farther
+        // ---- 4. a burst of steps: the bookkeeping above (results, tickets, polls) costs as much as a step, so it runs once per
+        // burst; the burst ends as soon as a group has finished its search (its result should not wait)
+#pragma unroll 1
+        for (int it = 0; it < CGRT_WAVE_GSTEPS; it++) {
+            // one step of every active group. The per-lane tests run in divergent code WITHOUT collectives; the group results
+            // are then combined with full-warp ballots / shuffles that all 32 lanes execute together.
+            const bool active = st == WS_RUN && state == TRAV_CONTINUE;
+            const bool isLeaf = (node & CGRT_TRI) != 0u;
+#ifdef CGRT_WAVE_LAT
+            if (active) nsteps++;
+#endif
+            const float bound = (any ? fminf(t, maxDist) : t) * slack;
+            int pos = -1;                            // leaf: position of this lane's triangle
+            float near = __int_as_float(0x7f800000); // leaf: distance of an acceptable triangle that does not beat the best
+            bool p = false, amb = false;     // p: this lane's child box is hit / this lane's triangle is an acceptable candidate
+            unsigned key = 0xffffffffu;      // ordering key of the lane's result (entry distance | child, or candidate distance)
+            uint32_t id = 0u;
+            float ti = 0.0f;
+            if (active) {
+                if (isLeaf) {
+                    // leaf: lane j tests triangle j with the reference's accept arithmetic (cgrt_device.cuh fastStepLeafDyn)
+                    const int first = (int)(node & CGRT_IDX_MASK), count = (int)((node >> CGRT_TRICNT_SHIFT) & 7u) + 1;
+                    if (j < count) {
+                        const float4* tr = S.tri4f + 4 * (size_t)(first + j);
+                        const float4 pl = __ldg(tr), v0 = __ldg(tr + 1), v1 = __ldg(tr + 2), v2 = __ldg(tr + 3);
+                        pos = f2i(v2.w); // position of the triangle in the reference-ordered arrays
+                        const V3 nrm = mk3(pl);
+                        const float on = dot3(o, nrm);
+                        const bool shortcut = (on == pl.w);
+                        bool cand = true;
+                        float tt = 0.0f;
+                        if (!shortcut) {
+                            const float denominator = dot3(d, nrm);
+                            if (denominator == 0) cand = false;
+                            else {
+                                tt = (pl.w - on) / denominator;
+                                if (tt < 0) cand = false;
+                                else if (hitTri < 0 ? !(tt < t) : !(tt <= t * CGRT_NEAR)) cand = false; // `t >= ray.t` / clearly farther
+                            }
+                        }
+                        if (cand) {
+                            const V3 pt = o + d * tt;
+                            if (pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), nrm, pt)) {
+                                if (shortcut || (hitTri >= 0 && tt == t)) amb = true; // depends on the reference's visiting order
+                                else if (hitTri >= 0 && tt > t) near = tt;            // acceptable runner-up just behind the best
+                                else { p = true; key = __float_as_uint(tt + 0.0f); }
+                            }
                         }
                     }
-                    if (cand) {
-                        const V3 pt = o + d * tt;
-                        if (pointInTriangleDev(mk3(v0), mk3(v1), mk3(v2), nrm, pt)) {
-                            if (shortcut || (hitTri >= 0 && tt == t)) amb = true; // depends on the reference's visiting order
-                            else if (hitTri >= 0 && tt > t) near = tt;            // acceptable runner-up just behind the best
-                            else { p = true; key = __float_as_uint(tt + 0.0f); }
-                        }
-                    }
-                }
-            } else {
-                // 8-wide node: lane j tests child j against its pre-expanded box
-                const float4* c = S.wide8 + 16 * (size_t)(node & CGRT_IDX_MASK) + 2 * j;
-                const float4 lo = __ldg(c), hi = __ldg(c + 1);
-                id = (uint32_t)f2i(lo.w);
-                const float q0x = (lo.x - o.x) * inv.x, q1x = (hi.x - o.x) * inv.x;
-                const float q0y = (lo.y - o.y) * inv.y, q1y = (hi.y - o.y) * inv.y;
-                const float q0z = (lo.z - o.z) * inv.z, q1z = (hi.z - o.z) * inv.z;
-                ti = fmaxf(fmaxf(fminf(q0x, q1x), fminf(q0y, q1y)), fminf(q0z, q1z));
-                const float to = fminf(fminf(fmaxf(q0x, q1x), fmaxf(q0y, q1y)), fmaxf(q0z, q1z));
-                p = id != 0u && !(to < 0.0f || ti > to * slack || ti > bound);
-                if (p) key = (__float_as_uint(fmaxf(ti, 0.0f)) & ~7u) | (unsigned)j; // nearest first, ties by child index
-            }
-        }
-        // ---- combine within each group of 8 (full-warp collectives, converged)
-        const unsigned pm = (__ballot_sync(0xffffffffu, p) >> (8 * g)) & 0xFFu;
-        const unsigned ambm = (__ballot_sync(0xffffffffu, amb) >> (8 * g)) & 0xFFu;
-        unsigned mn = key;
-        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 1));
-        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 2));
-        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 4));
-        const unsigned winm = (__ballot_sync(0xffffffffu, p && key == mn) >> (8 * g)) & 0xFFu;
-        const uint32_t nextId = __shfl_sync(0xffffffffu, id, 8 * g + (int)(mn & 7u));
-        const int winPos = __shfl_sync(0xffffffffu, pos, 8 * g + (winm ? __ffs(winm) - 1 : 0)); // leaf: position of the new best
-        // leaf: smallest distance among the group's acceptable triangles that are not the new best (runner-up for the certificate)
-        float ru = (isLeaf && p && key != mn) ? __uint_as_float(key) : near;
-        ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 1));
-        ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 2));
-        ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 4));
-        if (active) {
-            bool pop = false;
-            if (isLeaf) {
-                if (ambm != 0u || __popc(winm) > 1) {
-                    state = TRAV_DEFER; // ties at the smallest distance / in-plane shortcut
                 } else {
-                    t2 = fminf(t2, ru);
-                    if (pm != 0u) {
-                        if (hitTri >= 0) t2 = fminf(t2, t); // the old best becomes the runner-up
-                        t = __uint_as_float(mn);
-                        hitTri = winPos;
+                    // 8-wide node: lane j tests child j against its pre-expanded box
+                    const float4* c = S.wide8 + 16 * (size_t)(node & CGRT_IDX_MASK) + 2 * j;
+                    const float4 lo = __ldg(c), hi = __ldg(c + 1);
+                    id = (uint32_t)f2i(lo.w);
+                    const float q0x = (lo.x - o.x) * inv.x, q1x = (hi.x - o.x) * inv.x;
+                    const float q0y = (lo.y - o.y) * inv.y, q1y = (hi.y - o.y) * inv.y;
+                    const float q0z = (lo.z - o.z) * inv.z, q1z = (hi.z - o.z) * inv.z;
+                    ti = fmaxf(fmaxf(fminf(q0x, q1x), fminf(q0y, q1y)), fminf(q0z, q1z));
+                    const float to = fminf(fminf(fmaxf(q0x, q1x), fmaxf(q0y, q1y)), fmaxf(q0z, q1z));
+                    p = id != 0u && !(to < 0.0f || ti > to * slack || ti > bound);
+                    if (p) key = (__float_as_uint(fmaxf(ti, 0.0f)) & ~7u) | (unsigned)j; // nearest first, ties by child index
+                }
+            }
+            // ---- combine within each group of 8 (full-warp collectives, converged)
+            const unsigned pm = (__ballot_sync(0xffffffffu, p) >> (8 * g)) & 0xFFu;
+            const unsigned ambm = (__ballot_sync(0xffffffffu, amb) >> (8 * g)) & 0xFFu;
+            unsigned mn = key;
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 1));
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 2));
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 4));
+            const unsigned winm = (__ballot_sync(0xffffffffu, p && key == mn) >> (8 * g)) & 0xFFu;
+            const uint32_t nextId = __shfl_sync(0xffffffffu, id, 8 * g + (int)(mn & 7u));
+            const int winPos = __shfl_sync(0xffffffffu, pos, 8 * g + (winm ? __ffs(winm) - 1 : 0)); // leaf: position of the new best
+            // leaf: smallest distance among the group's acceptable triangles that are not the new best (runner-up for the certificate)
+            float ru = (isLeaf && p && key != mn) ? __uint_as_float(key) : near;
+            ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 1));
+            ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 2));
+            ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 4));
+            if (active) {
+                bool pop = false;
+                if (isLeaf) {
+                    if (ambm != 0u || __popc(winm) > 1) {
+                        state = TRAV_DEFER; // ties at the smallest distance / in-plane shortcut
+                    } else {
+                        t2 = fminf(t2, ru);
+                        if (pm != 0u) {
+                            if (hitTri >= 0) t2 = fminf(t2, t); // the old best becomes the runner-up
+                            t = __uint_as_float(mn);
+                            hitTri = winPos;
+                        }
+                        if (any && pm != 0u && !(t + eps >= maxDist)) state = TRAV_FIRED;
+                        else pop = true;
                     }
-                    if (any && pm != 0u && !(t + eps >= maxDist)) state = TRAV_FIRED;
-                    else pop = true;
+                } else if (pm == 0u) {
+                    pop = true;
+                } else if (sp + 7 > CGRT_STACK8) {
+                    state = TRAV_DEFER; // pathological depth: the exact traversal handles the ray
+                } else {
+                    // nearest hit child next; the others go on the group's stack with their entry distance
+                    const int best = (int)(mn & 7u);
+                    if (p && j != best) {
+                        const unsigned before = pm & ((1u << j) - 1u) & ~(1u << best);
+                        K[sp + __popc(before)] = make_uint2(id, __float_as_uint(ti));
+                    }
+                    sp += __popc(pm) - 1;
+                    node = nextId;
                 }
-            } else if (pm == 0u) {
-                pop = true;
-            } else if (sp + 7 > CGRT_STACK8) {
-                state = TRAV_DEFER; // pathological depth: the exact traversal handles the ray
-            } else {
-                // nearest hit child next; the others go on the group's stack with their entry distance
-                const int best = (int)(mn & 7u);
-                if (p && j != best) {
-                    const unsigned before = pm & ((1u << j) - 1u) & ~(1u << best);
-                    K[sp + __popc(before)] = make_uint2(id, __float_as_uint(ti));
-                }
-                sp += __popc(pm) - 1;
-                node = nextId;
-            }
-            if (pop) {
-                const float b2 = (any ? fminf(t, maxDist) : t) * slack;
-                state = TRAV_DONE;
-                while (sp > 0) {
-                    sp--;
-                    const uint2 e = K[sp];
-                    if (__uint_as_float(e.y) > b2) continue;
-                    node = e.x;
-                    state = TRAV_CONTINUE;
-                    break;
+                if (pop) {
+                    const float b2 = (any ? fminf(t, maxDist) : t) * slack;
+                    state = TRAV_DONE;
+                    while (sp > 0) {
+                        sp--;
+                        const uint2 e = K[sp];
+                        if (__uint_as_float(e.y) > b2) continue;
+                        node = e.x;
+                        state = TRAV_CONTINUE;
+                        break;
+                    }
                 }
             }
+            __syncwarp();
+            if (__ballot_sync(0xffffffffu, st == WS_RUN && state == TRAV_CONTINUE) != __ballot_sync(0xffffffffu, st == WS_RUN)) break;
         }
-        __syncwarp();
     }
 }
 
