@@ -754,21 +754,65 @@ RT_DEV int fastStepLeaf(const DevScene& S, FastTrav& T, FastStack& K, float eps,
 // tSecond` prunes a pending sibling) can go against descending, whatever the order of its visits; the leaf scan then accepts
 // tri* (tStar < ray.t) and nothing acceptable is closer. Boxes that are entered exactly where the triangle is hit (axis-aligned
 // geometry lying in a box face: distance within a few ulp of tStar) pass thanks to the 5e-7 margin.
+// The reference's slabTest (ray_tracing.cpp / rt_math.cuh slabTest: six IEEE divisions) decides for every box of the path. The
+// certificates evaluate it in two stages: first with the reciprocal direction, tIn' / tOut' from (lo - o) * (1 / d). Each of
+// the six products differs from the reference's quotient by less than 3 ulp (the subtraction is the same; reciprocal, product
+// and quotient each round once), so tIn and tOut - a max and a min of them - lie within E = 4e-7 * (largest magnitude of the
+// six) + 1e-30 of tIn', tOut'. If  tIn' > E  (the reference's entry distance is positive, so it reports tIn),
+// tIn' + 2 E <= tOut'  (it reports a hit: tIn <= tOut, tOut >= 0)  the reference's distance is at most tIn' + E. Only when
+// these margins do not hold (origin on a face, grazing rays, boxes entered within a few ulp of the bound, non-finite values:
+// every comparison with a NaN fails) is the box evaluated with the reference's own arithmetic. The finish warps of the
+// persistent wavefront are bound by the latency of this walk: ~160 dependent instructions per box with the divisions, ~45 without.
+struct SlabFast {
+    V3 inv;
+};
+RT_DEV SlabFast slabFastBegin(const V3& d)
+{
+    SlabFast F;
+    // (directions whose reciprocal would lose precision - zero, denormal, beyond 1e30 - get NaN: every fast test then fails and
+    // the reference's arithmetic decides)
+    const float nan = __int_as_float(0x7fc00000);
+    F.inv.x = (fabsf(d.x) >= 1e-30f && fabsf(d.x) <= 1e30f) ? 1.0f / d.x : nan;
+    F.inv.y = (fabsf(d.y) >= 1e-30f && fabsf(d.y) <= 1e30f) ? 1.0f / d.y : nan;
+    F.inv.z = (fabsf(d.z) >= 1e-30f && fabsf(d.z) <= 1e30f) ? 1.0f / d.z : nan;
+    return F;
+}
+// true: the reference's slabTest(lo, hi, o, d, +inf) reports a hit at a distance <= teUpper (and > 0)
+RT_DEV bool slabFastHit(const SlabFast& F, const V3& lo, const V3& hi, const V3& o, float& teUpper)
+{
+    const float ax = (lo.x - o.x) * F.inv.x, bx = (hi.x - o.x) * F.inv.x;
+    const float ay = (lo.y - o.y) * F.inv.y, by = (hi.y - o.y) * F.inv.y;
+    const float az = (lo.z - o.z) * F.inv.z, bz = (hi.z - o.z) * F.inv.z;
+    const float tIn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float tOut = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    const float big = fmaxf(fmaxf(fmaxf(fabsf(ax), fabsf(bx)), fmaxf(fabsf(ay), fabsf(by))), fmaxf(fabsf(az), fabsf(bz)));
+    const float e = big * 4e-7f + 1e-30f;
+    // (fminf / fmaxf drop NaN operands, so a NaN product is caught through `big`: the sum below is then NaN or the checks on
+    // the individual products fail)
+    const bool finite = (ax == ax) && (bx == bx) && (ay == ay) && (by == by) && (az == az) && (bz == bz) && big < 1e30f;
+    teUpper = tIn + e;
+    return finite && tIn > e && tIn + 2.0f * e <= tOut;
+}
+
 RT_DEV bool certifyClosest(const DevScene& S, const V3& o, const V3& d, int pos, float tStar, float t2, float tIn)
 {
     const float lb = fminf(fminf(tIn, t2), tStar * 1.0000005f);
     if (!(lb > tStar)) return false;
+    const SlabFast F = slabFastBegin(d);
     int node = f2i(__ldg(S.triN0 + pos).w);
 #pragma unroll 1
     while (true) {
         const float4 q0 = __ldg(S.nodes + 2 * node), q1 = __ldg(S.nodes + 2 * node + 1);
+        const int parent = node != 0 ? __ldg(S.refParent + node) : 0; // (fetched beside the box, not after its test)
         if (!startsInBox(o, mk3(q0), mk3(q1))) {
             float te = 0.0f;
-            if (!slabTest(mk3(q0), mk3(q1), o, d, lb, te)) return false;
-            if (!(te < lb)) return false; // NaN distances are not certificates
+            if (!(slabFastHit(F, mk3(q0), mk3(q1), o, te) && te < lb)) {
+                if (!slabTest(mk3(q0), mk3(q1), o, d, lb, te)) return false;
+                if (!(te < lb)) return false; // NaN distances are not certificates
+            }
         }
         if (node == 0) return true;
-        node = __ldg(S.refParent + node);
+        node = parent;
     }
 }
 
@@ -779,18 +823,22 @@ RT_DEV bool certifyClosest(const DevScene& S, const V3& o, const V3& d, int pos,
 // (A NaN entry distance stays: `m == m` below; the predicate then fails.)
 RT_DEV bool certifyAny(const DevScene& S, const V3& o, const V3& d, int pos, float tX, float eps, float maxDist)
 {
-    float m = tX;
+    float m = tX; // an upper bound of the reference's final distance is enough: the predicate is monotone
+    const SlabFast F = slabFastBegin(d);
     int node = f2i(__ldg(S.triN0 + pos).w);
 #pragma unroll 1
     while (true) {
         const float4 q0 = __ldg(S.nodes + 2 * node), q1 = __ldg(S.nodes + 2 * node + 1);
+        const int parent = node != 0 ? __ldg(S.refParent + node) : 0;
         if (!startsInBox(o, mk3(q0), mk3(q1))) {
             float te = 0.0f;
-            if (!slabTest(mk3(q0), mk3(q1), o, d, __int_as_float(0x7f800000), te)) return false;
-            if (m == m && !(te <= m)) m = te;
+            if (!slabFastHit(F, mk3(q0), mk3(q1), o, te)) {
+                if (!slabTest(mk3(q0), mk3(q1), o, d, __int_as_float(0x7f800000), te)) return false;
+            }
+            if (m == m && !(te <= m)) m = te; // (a NaN stays and fails the predicate below)
         }
         if (node == 0) break;
-        node = __ldg(S.refParent + node);
+        node = parent;
     }
     return !(m + eps >= maxDist);
 }
