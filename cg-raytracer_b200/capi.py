@@ -78,7 +78,7 @@ EXPORTS = [
     "cgrt_host_alloc_pinned", "cgrt_host_free_pinned", "cgrt_memcpy_h2d", "cgrt_memcpy_d2h", "cgrt_device_synchronize",
     "cgrt_memset_device", "cgrt_memcpy_d2h_async", "cgrt_peer_export", "cgrt_peer_open", "cgrt_peer_close",
     "cgrt_flag_signal", "cgrt_flag_wait", "cgrt_bvh_fast_tree_stats", "cgrt_render_submit", "cgrt_render_wait",
-    "cgrt_render_effects", "cgrt_scene_set_spherical_lights", "cgrt_debug_wave_timeline",
+    "cgrt_render_effects", "cgrt_scene_set_spherical_lights", "cgrt_debug_wave_timeline", "cgrt_debug_wave_tuner",
 ]
 
 _lib = None
@@ -106,6 +106,7 @@ def load_library(path=None):
         "cgrt_scene_set_spheres": (C.c_int, [vp, fptr, i32]),
         "cgrt_scene_set_spherical_lights": (C.c_int, [vp, fptr, i32, C.c_uint32]),
         "cgrt_debug_wave_timeline": (C.c_int, [vp, C.POINTER(C.c_int32), i32]),
+        "cgrt_debug_wave_tuner": (C.c_int, [vp, C.POINTER(C.c_float), i32]),
         "cgrt_bvh_num_levels": (C.c_int, [vp]),
         "cgrt_bvh_num_nodes": (C.c_int, [vp]),
         "cgrt_scene_num_triangles": (C.c_int64, [vp]),

@@ -225,6 +225,22 @@ static void fastTreeSelfCheck(const std::vector<MeshView>& views, const BuiltBVH
 }
 
 // ---- the scene object --------------------------------------------------------------------------------------------------
+// Share of the SMs that finish (WaveQ::finEvery), found by measurement: how much finishing a frame needs per search step
+// depends on the scene (hit rate, lights, how long the searches are), and a wrong split leaves one of the two stages waiting.
+// Frames of one shape rendered repeatedly (the UI re-renders every frame, main.cpp:907-914) are timed on the device (an event
+// pair per frame, read back when complete - the renderer never waits for it); the neighbours of the current setting are tried
+// once each and the fastest is kept. Scheduling only: every setting renders the same pixels.
+struct WaveTuner {
+    static const int RING = 8, LO = 2, HI = 14;
+    int key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int cur = 0;                 // current setting (0 = not started)
+    float ms[HI + 2] = {0};      // best device time seen per setting, 0 = unknown
+    int pendingOf[HI + 2] = {0}; // frames in flight per setting
+    int frames = 0;
+    struct Slot { cudaEvent_t a = nullptr, b = nullptr; int setting = 0; bool busy = false; } ring[RING];
+    int next = 0, recording = -1;
+};
+
 struct cgrt_scene {
     int device = 0;
     DeviceInfo di;
@@ -298,6 +314,7 @@ struct cgrt_scene {
     size_t hFramePinnedFloats = 0;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    WaveTuner tuner;
     cudaStream_t lastStream = nullptr;
     uint64_t lastLaunches = 0;
     FrameParams lastParams{};
@@ -345,6 +362,7 @@ static void destroyScene(cgrt_scene* s)
     s->streamFrame[0].release(); s->streamFrame[1].release();
     s->zeroFrame.release();
     s->fxA.release(); s->fxB.release(); s->fxC.release(); s->fxM.release(); s->fxProg.release();
+    for (WaveTuner::Slot& sl : s->tuner.ring) { if (sl.a) cudaEventDestroy(sl.a); if (sl.b) cudaEventDestroy(sl.b); }
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -1058,12 +1076,75 @@ static size_t waveTicketCap(const FrameParams& P)
            (size_t)waveGridBlocks(1) * 128 * 160; // + the second records of rays handed over at the change-over (one per lane, <= 160 SMs)
 }
 
-// scheduling knobs / watchdog of the persistent wavefront (CGRT_WAVE="mode=0,group_below=400000,switch=0,fin=0,handover=1,timeout_ms=4000"; 0 = automatic; they
+// harvest the frames that have completed, then choose the setting of the next frame (see WaveTuner)
+static int waveTunerChoose(WaveTuner& T, const int key[8], int start)
+{
+    if (std::memcmp(key, T.key, sizeof T.key) != 0) { // another frame shape: start over (events are kept)
+        for (WaveTuner::Slot& sl : T.ring) sl.busy = false;
+        std::memcpy(T.key, key, sizeof T.key);
+        std::memset(T.ms, 0, sizeof T.ms);
+        std::memset(T.pendingOf, 0, sizeof T.pendingOf);
+        T.cur = std::min(std::max(start, (int)WaveTuner::LO), (int)WaveTuner::HI);
+        T.frames = 0;
+    }
+    for (WaveTuner::Slot& sl : T.ring) {
+        if (!sl.busy || cudaEventQuery(sl.b) != cudaSuccess) continue;
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, sl.a, sl.b) == cudaSuccess && ms > 0.0f)
+            T.ms[sl.setting] = T.ms[sl.setting] == 0.0f ? ms : std::min(T.ms[sl.setting], ms);
+        T.pendingOf[sl.setting]--;
+        sl.busy = false;
+    }
+    (void)cudaGetLastError(); // (cudaErrorNotReady of the queries is not an error)
+    T.frames++;
+    if ((T.frames & 255) == 0) { // look at the neighbours again now and then (the camera or the lights may have moved)
+        for (int f = WaveTuner::LO; f <= WaveTuner::HI; f++) if (f != T.cur) T.ms[f] = 0.0f;
+        T.ms[T.cur] *= 1.05f;
+    }
+    const int c = T.cur;
+    if (T.frames <= 2 || T.ms[c] == 0.0f) return c; // (the first frame of a shape pays for allocations and cold caches)
+    for (int f : {c - 1, c + 1}) {
+        if (f < WaveTuner::LO || f > WaveTuner::HI) continue;
+        if (T.ms[f] == 0.0f) return T.pendingOf[f] > 0 ? c : f; // try it once; while that frame is in flight, carry on
+    }
+    int best = c;
+    for (int f : {c - 1, c + 1})
+        if (f >= WaveTuner::LO && f <= WaveTuner::HI && T.ms[f] < 0.98f * T.ms[best]) best = f;
+    T.cur = best;
+    return best;
+}
+static int waveTunerBegin(WaveTuner& T, int setting, cudaStream_t st)
+{
+    T.recording = -1;
+    for (int k = 0; k < WaveTuner::RING; k++) {
+        WaveTuner::Slot& sl = T.ring[(T.next + k) % WaveTuner::RING];
+        if (sl.busy) continue;
+        if (!sl.a && (cudaEventCreate(&sl.a) != cudaSuccess || cudaEventCreate(&sl.b) != cudaSuccess)) return 0;
+        sl.setting = setting;
+        if (cudaEventRecord(sl.a, st) != cudaSuccess) return 0;
+        T.recording = (T.next + k) % WaveTuner::RING;
+        T.next = (T.recording + 1) % WaveTuner::RING;
+        return 1;
+    }
+    return 0; // every slot still in flight: this frame is not timed
+}
+static void waveTunerEnd(WaveTuner& T, cudaStream_t st)
+{
+    if (T.recording < 0) return;
+    WaveTuner::Slot& sl = T.ring[T.recording];
+    if (cudaEventRecord(sl.b, st) == cudaSuccess) {
+        sl.busy = true;
+        T.pendingOf[sl.setting]++;
+    }
+    T.recording = -1;
+}
+
+// scheduling knobs / watchdog of the persistent wavefront (CGRT_WAVE="mode=0,group_below=400000,switch=0,fin=0,tune=1,handover=1,timeout_ms=4000"; 0 = automatic; they
 // change speed only, never results). mode 0: the search form follows the size of this rank's share of the frame - one lane per
 // ray for large shares (throughput), eight lanes per ray for small ones (latency)
-static void waveTuning(WaveQ& Q, int nSlots, int nLights)
+static bool waveTuning(WaveQ& Q, int nSlots, int nLights)
 {
-    static int mode = 0, groupBelow = 400000, fin = 0, timeoutMs = 4000, switchBelow = 0, handOver = 1;
+    static int mode = 0, groupBelow = 400000, fin = 0, timeoutMs = 4000, switchBelow = 0, handOver = 1, tune = 1;
     static bool loaded = false;
     if (!loaded) {
         loaded = true;
@@ -1084,6 +1165,7 @@ static void waveTuning(WaveQ& Q, int nSlots, int nLights)
                     else if (key == "switch") switchBelow = v;
                     else if (key == "timeout_ms") timeoutMs = v;
                     else if (key == "handover") handOver = v;
+                    else if (key == "tune") tune = v;
                 }
                 pos = c + 1;
             }
@@ -1099,6 +1181,7 @@ static void waveTuning(WaveQ& Q, int nSlots, int nLights)
     Q.switchBelow = Q.mode == 2 ? 0 : (switchBelow > 0 ? switchBelow : (nSlots >= 1500000 ? 100000 : 60000));
     Q.timeoutNs = (unsigned long long)std::max(timeoutMs, 1) * 1000000ull;
     if (!handOver) Q.resume = nullptr; // rays finish in the search form they started in
+    return fin <= 0 && tune != 0;      // the finisher share may be tuned by measurement (WaveTuner)
 }
 
 static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params* p, FrameParams& P,
@@ -1314,10 +1397,16 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
             CK(cudaMemsetAsync(s->waveTrace.p, 0, (size_t)WAVE_TRACE_SAMPLES * 8 * sizeof(int), st));
             Q.trace = s->waveTrace.p;
         }
-        waveTuning(Q, P.nSlots, P.nLights);
+        const bool tuned = waveTuning(Q, P.nSlots, P.nLights) && !(p->flags & CGRT_RENDER_PROFILE_ALL);
+        if (tuned) {
+            const int key[8] = {P.width, P.height, P.nSlots, P.traceLimit, P.nLights, P.world, P.rank, Q.mode};
+            Q.finEvery = waveTunerChoose(s->tuner, key, Q.finEvery);
+            waveTunerBegin(s->tuner, Q.finEvery, st);
+        }
         launches = launchWavePipeline(s->dev, (const FrameParams*)s->dParamBlock.p, P,
                                       (const float4*)(s->dParamBlock.p + CGRT_PARAM_BLOCK_HEADER), RB, Q, dSeq, d_out,
                                       s->di.numSMs, &s->trace, st);
+        if (tuned) waveTunerEnd(s->tuner, st);
         s->lastChains = 1;
         s->lastPipeline = 3;
     } else if (useRounds(s, P)) {
@@ -1771,6 +1860,18 @@ int cgrt_debug_wave_timeline(cgrt_scene* s, int32_t* out, int32_t cap)
     const int n = std::min<int>(cap, WAVE_TRACE_SAMPLES);
     if (cudaMemcpy(out, s->waveTrace.p, (size_t)n * 8 * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     return n;
+}
+
+// the finisher share the persistent wavefront currently uses for this scene's frames (WaveTuner; 0 before the first frame) and
+// the device times it has measured per setting: out[0] = current setting, out[f] = ms of setting f (f = 2..14), 0 = not tried
+int cgrt_debug_wave_tuner(cgrt_scene* s, float* out, int32_t cap)
+{
+    if (!s || !out || cap < WaveTuner::HI + 1) return 0;
+    std::lock_guard<std::mutex> lk(s->mu);
+    out[0] = (float)s->tuner.cur;
+    out[1] = (float)s->tuner.frames;
+    for (int f = WaveTuner::LO; f <= WaveTuner::HI; f++) out[f] = s->tuner.ms[f];
+    return WaveTuner::HI + 1;
 }
 
 #ifdef CGRT_WAVE_LAT

@@ -520,8 +520,7 @@ struct FastTrav {
 #define CGRT_PREFETCH 0 // measured slower on B200 (k_trace 1.82 -> 2.08 ms/frame): the steps are issue-bound, not fetch-bound
 #endif
 struct FastStack {
-    uint32_t n[CGRT_FASTSTACK];
-    float t[CGRT_FASTSTACK];
+    uint2 e[CGRT_FASTSTACK]; // (node id, entry distance): one 8-byte local-memory access per push / pop
     float t2; // smallest distance of any OTHER acceptable triangle met so far (runner-up), +inf none: see certifyClosest. Lives
               // here (local memory) because it is touched only when a candidate is accepted; a register in the hot loop is not
 };
@@ -582,8 +581,9 @@ RT_DEV int fastPop(const DevScene& S, FastTrav& T, FastStack& K, float bound)
 {
     while (T.sp > 0) {
         T.sp--;
-        if (K.t[T.sp] > bound) continue;
-        T.node = K.n[T.sp];
+        const uint2 e = K.e[T.sp];
+        if (__uint_as_float(e.y) > bound) continue;
+        T.node = e.x;
         fastPrefetch(S, T.node);
         return TRAV_CONTINUE;
     }
@@ -640,8 +640,7 @@ RT_DEV int fastStepWideDyn(const DevScene& S, FastTrav& T, FastStack& K, bool an
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         if ((hitMask >> c & 1u) && c != best) {
-            K.n[T.sp] = cid[c];
-            K.t[T.sp] = tin[c];
+            K.e[T.sp] = make_uint2(cid[c], __float_as_uint(tin[c]));
             T.sp++;
         }
     }

@@ -569,8 +569,9 @@ RT_DEV bool waveLaneLoop(const DevScene& S, const WaveQ& Q, unsigned long long t
                     float4* dst = Q.resume + (size_t)WAVE_RESUME_F4 * r;
                     st128(dst, make_float4(T.t, i2f(T.hitTri), K.t2, __uint_as_float(T.node)));
                     for (int i = 0; i < T.sp; i += 2)
-                        st128(dst + 1 + (i >> 1), make_float4(__uint_as_float(K.n[i]), K.t[i],
-                                                              i + 1 < T.sp ? __uint_as_float(K.n[i + 1]) : 0.0f, i + 1 < T.sp ? K.t[i + 1] : 0.0f));
+                        st128(dst + 1 + (i >> 1), make_float4(__uint_as_float(K.e[i].x), __uint_as_float(K.e[i].y),
+                                                              i + 1 < T.sp ? __uint_as_float(K.e[i + 1].x) : 0.0f,
+                                                              i + 1 < T.sp ? __uint_as_float(K.e[i + 1].y) : 0.0f));
                     waveRelease(Q); // the state is in L2 before the record that points at it can be seen
                     if (ntk < Q.cap) {
                         const float4* src = Q.rays + 3 * (size_t)tk;

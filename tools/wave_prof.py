@@ -30,3 +30,8 @@ for _ in range(frames):
     _, st = s.render(cam, W, H, trace_limit=L, rank=rank, world=world, out=out)
     ms.append(round(st["device_ms"], 4))
 print(name, W, H, L, "rank", rank, "of", world, "pipeline", st["pipeline"], "device ms", ms, "rays", st["primary"] + st["shadow"] + st["bounce"])
+import ctypes as C  # noqa: E402
+buf = (C.c_float * 16)()
+if capi.load_library().cgrt_debug_wave_tuner(s.h, buf, 16):
+    print("  finisher share: 1/%d of the SMs after %d frames; measured ms per setting %s" % (
+        int(buf[0]), int(buf[1]), {f: round(buf[f], 4) for f in range(2, 15) if buf[f] > 0}))
