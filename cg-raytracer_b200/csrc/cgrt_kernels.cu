@@ -2411,7 +2411,8 @@ int waveGridBlocks(int numSMs)
     cudaGetDevice(&dev);
     dev &= 63;
     if (perSM[dev] == 0) {
-        cudaFuncSetAttribute(k_wave, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        const char* cv = getenv("CGRT_WAVE_CARVEOUT"); // % of the SM's 228 KB configured as shared memory (the rest is L1)
+        cudaFuncSetAttribute(k_wave, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : 25);
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave, 128, 0) != cudaSuccess || nb < 1) nb = 1;
         perSM[dev] = nb;

@@ -481,7 +481,10 @@ RT_DEV void waveFinishLoop(const DevScene& S, const FrameParams& P, const float4
 #define CGRT_WAVE_STEPS 8
 #endif
 #ifndef CGRT_WAVE_REFILL
-#define CGRT_WAVE_REFILL 4
+#define CGRT_WAVE_REFILL 16 // lanes that must be free before a warp refills (4 / 8 / 16 / 24 / 32: 1.22 / 1.17 / 1.06 / 1.06 / 1.16 ms on C3: a refill is two L2 round trips for the whole warp)
+#endif
+#ifndef CGRT_WAVE_GFIN
+#define CGRT_WAVE_GFIN 1 // GROUP form: finished groups that end a burst early
 #endif
 #ifndef CGRT_WAVE_GSTEPS
 #define CGRT_WAVE_GSTEPS 8 // GROUP form: steps per burst (measured 2 / 4 / 8: 0.44 / 0.415 / 0.40 ms on a 1/8 share of C3)
@@ -866,7 +869,11 @@ RT_DEV void waveGroupLoop(const DevScene& S, const WaveQ& Q, WaveShared& sh, uns
                 }
             }
             __syncwarp();
-            if (__ballot_sync(0xffffffffu, st == WS_RUN && state == TRAV_CONTINUE) != __ballot_sync(0xffffffffu, st == WS_RUN)) break;
+            {
+                const unsigned runG = __ballot_sync(0xffffffffu, st == WS_RUN && j == 0);
+                const unsigned actG = __ballot_sync(0xffffffffu, st == WS_RUN && state == TRAV_CONTINUE && j == 0);
+                if (actG == 0u || __popc(runG ^ actG) >= CGRT_WAVE_GFIN) break;
+            }
         }
     }
 }
