@@ -564,6 +564,74 @@ def test_overlapped_delivery_equals_plain_copy(capi, gpu):
         capi.check(lib.cgrt_host_free_pinned(ptr))
 
 
+_SCHED_WORKER = r"""
+import hashlib, json, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import __graft_entry__ as ge
+from oracle import bindings as ob
+capi = ge.load_package().capi
+flat, lights = ob.dragon_standin_fixture()
+s = capi.Scene(flat, lights=lights)
+out = {}
+for (W, H, L) in ((480, 270, 5), (960, 540, 3)):
+    cam = capi.make_camera(W, H)
+    frames = [s.render(cam, W, H, trace_limit=L) for _ in range(3)]
+    sha = {hashlib.sha1(np.ascontiguousarray(f).tobytes()).hexdigest() for f, _ in frames}
+    st = frames[-1][1]
+    out[f"{W}x{H}"] = dict(sha=sorted(sha), rays=[st[k] for k in ("primary", "primary_hit", "shadow", "bounce")], pipeline=st["pipeline"])
+print("RESULT " + json.dumps(out))
+"""
+
+
+def test_scheduling_variants_render_the_same_frame(gpu):
+    """The persistent wavefront's scheduling - search form, change-over point (also one that closes the queue while it still has
+    a backlog: the drain + pass-on + hand-over paths), hand-over of search states, finisher share - must not change a bit of the
+    frame or a ray count. The knobs are read once per process, so every variant renders in its own subprocess."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    variants = [("rounds", {"CGRT_PIPELINE": "rounds"}),
+                ("wave default", {"CGRT_PIPELINE": "wave"}),
+                ("lane, early change-over", {"CGRT_PIPELINE": "wave", "CGRT_WAVE": "mode=1,switch=400000,fin=3"}),
+                ("lane, late change-over, no hand-over", {"CGRT_PIPELINE": "wave", "CGRT_WAVE": "mode=1,switch=2000,handover=0,fin=9"}),
+                ("lane only", {"CGRT_PIPELINE": "wave", "CGRT_WAVE": "mode=1,switch=0"}),
+                ("group only", {"CGRT_PIPELINE": "wave", "CGRT_WAVE": "mode=2,fin=12"})]
+    res = {}
+    for label, env in variants:
+        e = dict(os.environ)
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", _SCHED_WORKER, root], env=e, capture_output=True, text=True, timeout=300)
+        line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+        assert r.returncode == 0 and line, (label, r.stdout[-800:], r.stderr[-2000:])
+        res[label] = json.loads(line[0][7:])
+    base = res["rounds"]
+    for label, r in res.items():
+        for case, v in r.items():
+            assert len(v["sha"]) == 1, (label, case, "frames of one process differ")
+            assert v["sha"] == base[case]["sha"] and v["rays"] == base[case]["rays"], (label, case)
+        assert all(v["pipeline"] == (2 if label == "rounds" else 3) for v in r.values()), label
+
+
+def test_finisher_share_tuner_keeps_the_frame(capi, gpu):
+    """Repeated frames of one shape: the measured tuning of the finisher share (WaveTuner) tries neighbouring settings; every
+    frame must be the first frame bit for bit, and the tuner must report a setting inside its range."""
+    import ctypes as C
+    flat, lights = ob.dragon_standin_fixture()
+    s = capi.Scene(flat, lights=lights)
+    W, H, L = 640, 360, 5
+    cam = capi.make_camera(W, H)
+    first, st0 = s.render(cam, W, H, trace_limit=L)
+    if st0["pipeline"] != 3:
+        pytest.skip("frame not rendered by the persistent wavefront")
+    for _ in range(12):
+        f, st = s.render(cam, W, H, trace_limit=L)
+        assert np.array_equal(bits(f), bits(first)) and st["shadow"] == st0["shadow"] and st["bounce"] == st0["bounce"]
+    buf = (C.c_float * 16)()
+    assert capi.load_library().cgrt_debug_wave_tuner(s.h, buf, 16) == 15
+    assert 2 <= int(buf[0]) <= 14 and int(buf[1]) >= 12
+    assert sum(1 for f in range(2, 15) if buf[f] > 0) >= 2  # at least one neighbour was measured
+
+
 # ---- renderRayTracing's optional passes (SURVEY.md §8 f1): anti-aliasing and motion blur around the same renderer ---------------
 def test_antialiasing_and_motion_blur_against_oracle(capi, oracle, gpu, golden):
     """cgrt_render_effects vs the oracle's frames combined exactly as src/main.cpp:663-687 (AA: the 4 pixel-corner rays of the
