@@ -1174,8 +1174,9 @@ static bool waveTuning(WaveQ& Q, int nSlots, int nLights)
     Q.mode = mode == 1 || mode == 2 ? mode : (nSlots < groupBelow ? 2 : 1);
     // share of the SMs that run the finish warps: every hit costs one hit epilogue plus one shadow ray to emit and to finish per
     // light (measured with the two-stage certificates, profiles/r02_tuning.md: C3, 1 light: 1/6 of the SMs, 1/8 for the
-    // GROUP-only frames; 3 lights: 1/4)
-    Q.finEvery = fin > 0 ? std::max(fin, 2) : (nLights >= 3 ? 4 : (nLights == 2 ? 5 : (Q.mode == 2 ? 8 : 6)));
+    // GROUP-only share of C3 - but 1/5 for the Cornell box, and too few finishers cost more than too many; 3 lights: 1/4).
+    // This is the STARTING value: WaveTuner moves it by measurement
+    Q.finEvery = fin > 0 ? std::max(fin, 2) : (nLights >= 3 ? 4 : (nLights == 2 ? 5 : 6));
     // (GROUP-only frames never change over; measured on the C3 frame and its 1/2, 1/4 shares: 100 K in flight for a whole 1080p
     // frame, 60 K for smaller shares)
     Q.switchBelow = Q.mode == 2 ? 0 : (switchBelow > 0 ? switchBelow : (nSlots >= 1500000 ? 100000 : 60000));

@@ -55,7 +55,11 @@ def main():
     steps = int(os.environ.get("CONFIG_STEPS", 20))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    only = [t for t in os.environ.get("CONFIG_ONLY", "").split(",") if t]  # e.g. CONFIG_ONLY=C1,C3
+
     def frame_config(name, flat, lights, W, H, L, modes):
+        if only and name.split()[0] not in only:
+            return
         scene = capi.Scene(flat, lights=lights, device=local)
         cam = capi.make_camera(W, H)
         for mode in modes if world > 1 else [None]:
@@ -112,6 +116,10 @@ def main():
     frame_config("C5 dodgeColorTest 3840x2160, 3 lights, limit 2", g.flat, g.lights, 3840, 2160, 2, ["p2p", "nccl"])
 
     # ---- C4: contiguous 1/world chunks of the 16 M rays, full scene replica per rank, no exchange
+    if only and "C4" not in only:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     n = 16 * 1024 * 1024
     per = n // world
     flat = ob.random_soup(1_000_000, seed=1234, scale=0.01, smooth_normals=False)
