@@ -1087,8 +1087,10 @@ static int waveTunerChoose(WaveTuner& T, const int key[8], int start)
         T.cur = std::min(std::max(start, (int)WaveTuner::LO), (int)WaveTuner::HI);
         T.frames = 0;
     }
-    for (WaveTuner::Slot& sl : T.ring) {
-        if (!sl.busy || cudaEventQuery(sl.b) != cudaSuccess) continue;
+    for (int k = 0; k < WaveTuner::RING; k++) { // oldest first; frames complete in order, so the first one still running ends the look
+        WaveTuner::Slot& sl = T.ring[(T.next + k) % WaveTuner::RING];
+        if (!sl.busy) continue;
+        if (cudaEventQuery(sl.b) != cudaSuccess) break;
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, sl.a, sl.b) == cudaSuccess && ms > 0.0f)
             T.ms[sl.setting] = T.ms[sl.setting] == 0.0f ? ms : std::min(T.ms[sl.setting], ms);
