@@ -609,7 +609,8 @@ def test_scheduling_variants_render_the_same_frame(gpu):
         for case, v in r.items():
             assert len(v["sha"]) == 1, (label, case, "frames of one process differ")
             assert v["sha"] == base[case]["sha"] and v["rays"] == base[case]["rays"], (label, case)
-        assert all(v["pipeline"] == (2 if label == "rounds" else 3) for v in r.values()), label
+        if os.environ.get("CGRT_EXACT_ONLY", "0") != "1":  # (exact-only scenes have no search tree: path pipeline throughout)
+            assert all(v["pipeline"] == (2 if label == "rounds" else 3) for v in r.values()), label
 
 
 def test_finisher_share_tuner_keeps_the_frame(capi, gpu):
