@@ -16,6 +16,7 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
 static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 
 #include "../../cg-raytracer_b200/csrc/cgrt_device.cuh"
 #include "../../cg-raytracer_b200/csrc/bvh_build.h"
