@@ -28,15 +28,20 @@
 // (gridDim.x << 32) raises the done flags every waiting warp polls.
 //
 // Two search forms:
-//   LANE   one lane per ray with refill (k_trace's loop): highest throughput, ~1.5 us per dependent step
-//   GROUP  eight lanes per ray (k_trace8's step): one child box / one triangle per lane, ~5x lower latency per step
+//   LANE   one lane per ray (k_trace's loop): highest throughput. A warp refills when CGRT_WAVE_REFILL of its lanes are free:
+//          a refill is two L2 round trips (tickets + finish-queue positions, then the records) for the whole warp
+//   GROUP  eight lanes per ray (k_trace8's step): one child box / one triangle per lane, ~5x lower latency per step; bursts of
+//          CGRT_WAVE_GSTEPS steps between bookkeeping rounds
 // Small frames (WaveQ::mode 2, chosen on the host from the size of the rank's share of the frame) use GROUP throughout. Large
 // frames start in LANE form and change over ONCE, when the number of rays in flight has fallen below WaveQ::switchBelow: the
-// ray queue is closed (a bit in its tail counter; the tickets handed out beyond the closing value will never be served and
-// are dropped by their holders), later rays go to a second part of the same array with its own counters and a different tag,
-// and search warps join the GROUP form as soon as their last LANE ray is done - so the long tail of a frame (few rays, each
-// many dependent steps) runs in the low-latency form while the bulk runs in the high-throughput one.
-// Results do not depend on the form or on which warp handles a ray (same search, same certificate), only the time does.
+// ray queue is closed (a bit in its tail counter), later rays go to a second part of the same array with its own counters and
+// a different tag. The LANE warps then (a) keep taking tickets until each has been handed one beyond the closing value - every
+// record of the first part is held by a lane, however far the consumers were behind -, (b) pass rays that arrive late on to
+// the second part, (c) hand the rays they are still searching over WITH their search state (best candidate, runner-up, stack:
+// WaveQ::resume), and join the GROUP form - so the long tail of a frame (few rays, each many dependent steps) runs in the
+// low-latency form without repeating work, while the bulk runs in the high-throughput one.
+// Results do not depend on the form, on which warp handles a ray or on WaveQ::finEvery (same search, same certificate), only
+// the time does: tests/test_gpu_parity.py test_scheduling_variants_render_the_same_frame, tools/wave_check.py.
 #pragma once
 
 #define WAVE_NSTAT 40
