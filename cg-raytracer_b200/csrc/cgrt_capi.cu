@@ -319,6 +319,8 @@ struct cgrt_scene {
     uint64_t lastLaunches = 0;
     FrameParams lastParams{};
     bool haveLast = false;
+    int* hStats = nullptr;       // page-locked: the frame's counters + the wavefront's watchdog word, copied behind a synchronous
+    bool statsOnHost = false;    // frame on its own stream so that collecting the statistics costs no further round trips
 };
 
 static int useSceneDevice(const cgrt_scene* s)
@@ -348,6 +350,7 @@ static void destroyScene(cgrt_scene* s)
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->hParamRing) cudaFreeHost(s->hParamRing);
     if (s->hFramePinned) cudaFreeHost(s->hFramePinned);
+    if (s->hStats) cudaFreeHost(s->hStats);
     if (s->chainSync.fork) {
         cudaEventDestroy(s->chainSync.fork);
         for (int c = 1; c < CGRT_MAX_CHAINS; c++) {
@@ -1468,6 +1471,7 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
     s->lastCounted = countTests;
     CK(cudaGetLastError());
     s->lastStream = st;
+    s->statsOnHost = false;
     s->lastLaunches = (uint64_t)launches;
     s->lastParams = P;
     s->haveLast = true;
@@ -1483,10 +1487,12 @@ int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
     if (!s->haveLast) return fail(CGRT_ERR_INVALID, "no frame rendered yet");
     CK(cudaStreamSynchronize(s->lastStream));
     int counts[CGRT_CNT_TOTAL];
+    const bool onHost = s->statsOnHost && s->hStats != nullptr;
     {
         const int nc = s->lastPipeline == 2 ? s->lastChains : 1;
         std::vector<int> all((size_t)CGRT_CNT_TOTAL * nc);
-        CK(cudaMemcpy(all.data(), s->counts.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        if (onHost) std::memcpy(all.data(), s->hStats, all.size() * sizeof(int));
+        else CK(cudaMemcpy(all.data(), s->counts.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost));
         for (int k = 0; k < CGRT_CNT_TOTAL; k++) {
             counts[k] = 0;
             for (int c = 0; c < nc; c++) counts[k] += all[(size_t)c * CGRT_CNT_TOTAL + k];
@@ -1498,7 +1504,8 @@ int cgrt_render_collect_stats(cgrt_scene* s, cgrt_render_stats* stats)
     stats->primary = primary;
     if (s->lastPipeline == 3) { // persistent wavefront: the watchdog of k_wave (a warp waited for seconds) invalidates the frame
         int err = 0;
-        CK(cudaMemcpy(&err, s->waveCtl.p + WCTL_ERR, sizeof(int), cudaMemcpyDeviceToHost));
+        if (onHost) err = s->hStats[CGRT_CNT_TOTAL * CGRT_MAX_CHAINS];
+        else CK(cudaMemcpy(&err, s->waveCtl.p + WCTL_ERR, sizeof(int), cudaMemcpyDeviceToHost));
         if (err) return fail(CGRT_ERR_CUDA, "k_wave watchdog: the persistent wavefront did not complete; the frame is invalid");
     }
     stats->pipeline = (uint32_t)s->lastPipeline;
@@ -1628,7 +1635,27 @@ int cgrt_render(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params*
         CK(cudaStreamWaitEvent(s->stream, s->copyDone[0], 0));
         launchDeliverBox(s->counts.p + CGRT_CNT_BBOX, p->width, p->height, s->frame.p, dHost, s->di.numSMs, s->stream);
         CK(cudaGetLastError());
+        bool fetched = false;
+        if (stats) { // the statistics ride behind the frame: one synchronisation for both
+            std::lock_guard<std::mutex> lk(s->mu);
+            if (!s->hStats && cudaHostAlloc((void**)&s->hStats, sizeof(int) * (CGRT_CNT_TOTAL * CGRT_MAX_CHAINS + 1), cudaHostAllocDefault) != cudaSuccess) {
+                s->hStats = nullptr;
+                cudaGetLastError();
+            }
+            if (s->hStats) {
+                const int nc = s->lastPipeline == 2 ? s->lastChains : 1;
+                CK(cudaMemcpyAsync(s->hStats, s->counts.p, sizeof(int) * CGRT_CNT_TOTAL * nc, cudaMemcpyDeviceToHost, s->stream));
+                s->hStats[CGRT_CNT_TOTAL * CGRT_MAX_CHAINS] = 0;
+                if (s->lastPipeline == 3)
+                    CK(cudaMemcpyAsync(s->hStats + CGRT_CNT_TOTAL * CGRT_MAX_CHAINS, s->waveCtl.p + WCTL_ERR, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+                fetched = true;
+            }
+        }
         CK(cudaStreamSynchronize(s->stream));
+        if (fetched) {
+            std::lock_guard<std::mutex> lk(s->mu);
+            s->statsOnHost = true;
+        }
     } else if (p->world == 1) {
         CK(cudaMemcpyAsync(rgb, s->frame.p, frameFloats * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));

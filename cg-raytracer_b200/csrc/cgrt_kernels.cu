@@ -1865,10 +1865,19 @@ __global__ void __launch_bounds__(256) k_deliver_box(const int* __restrict__ bbo
     const int f0 = (3 * x0) & ~31, f1 = 3 * x1 + 3; // floats of a row, start rounded down to a 128-byte run
     const int perRow = f1 - f0;
     const long long total = (long long)perRow * (r1 - r0 + 1);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int row = r0 + (int)(i / perRow), f = f0 + (int)(i % perRow);
-        const size_t o = (size_t)row * W * 3 + f;
-        hostFrame[o] = frame[o];
+    // (the destination is blank already: a warp whose 32 floats are all +0.0 has nothing to send over PCIe - inside the box
+    // most of a frame still is background)
+    for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) & ~31ll; base < total; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + (threadIdx.x & 31);
+        const bool in = i < total;
+        size_t o = 0;
+        float v = 0.0f;
+        if (in) {
+            const int row = r0 + (int)(i / perRow), f = f0 + (int)(i % perRow);
+            o = (size_t)row * W * 3 + f;
+            v = frame[o];
+        }
+        if (__ballot_sync(0xffffffffu, in && __float_as_uint(v) != 0u) != 0u && in) hostFrame[o] = v;
     }
 }
 void launchDeliverBox(const int* bbox, int W, int H, const float* frame, float* hostFrame, int numSMs, cudaStream_t st)
