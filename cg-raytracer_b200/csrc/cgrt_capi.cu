@@ -1389,6 +1389,7 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
         if (Q.seq == 0u) Q.seq = ++s->waveSeq;
         Q.cap = (int)std::min<size_t>(s->waveRays.n / 3, (size_t)0x3fffffff);
         Q.resume = s->waveResume.p;
+        Q.resumeCap = (int)std::min<size_t>(s->waveResume.n / WAVE_RESUME_F4, (size_t)0xffffff);
         Q.lat = nullptr;
 #ifdef CGRT_WAVE_LAT
         if (getenv("CGRT_WAVE_LAT")) {

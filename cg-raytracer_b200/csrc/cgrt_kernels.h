@@ -171,6 +171,7 @@ struct WaveQ {
     int switchBelow; // mode 1: change over to GROUP when fewer rays than this are in flight (0 = never)
     int finEvery;   // SMs with %smid % finEvery == 0 run the finish warps, the others the search warps
     unsigned long long timeoutNs;
+    int resumeCap;  // states the side array holds
     float4* resume; // search states of rays handed over at the change-over: WAVE_RESUME_F4 x float4 each, one per LANE-form lane of
                     // the grid (a lane hands over at most once per frame); nullptr = rays finish in the form they started in
     unsigned* lat;  // instrumented builds only (-DCGRT_WAVE_LAT): 8 timestamps / counters per ray ticket (tools/wave_latency.py)

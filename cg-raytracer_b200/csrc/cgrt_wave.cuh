@@ -574,9 +574,10 @@ RT_DEV bool waveLaneLoop(const DevScene& S, const WaveQ& Q, unsigned long long t
                 qbase = __shfl_sync(0xffffffffu, qbase, 0);
                 if (mig) {
                     const int r = rbase + __popc(migMask & ltMask), ntk = closeAt + qbase + __popc(migMask & ltMask);
-                    float4* dst = Q.resume + (size_t)WAVE_RESUME_F4 * r;
-                    st128(dst, make_float4(T.t, i2f(T.hitTri), K.t2, __uint_as_float(T.node)));
-                    for (int i = 0; i < T.sp; i += 2)
+                    const bool room = r < Q.resumeCap; // (always: a lane hands over at most once; without room the ray starts over)
+                    float4* dst = Q.resume + (size_t)WAVE_RESUME_F4 * (room ? r : 0);
+                    if (room) st128(dst, make_float4(T.t, i2f(T.hitTri), K.t2, __uint_as_float(T.node)));
+                    for (int i = 0; room && i < T.sp; i += 2)
                         st128(dst + 1 + (i >> 1), make_float4(__uint_as_float(K.e[i].x), __uint_as_float(K.e[i].y),
                                                               i + 1 < T.sp ? __uint_as_float(K.e[i + 1].x) : 0.0f,
                                                               i + 1 < T.sp ? __uint_as_float(K.e[i + 1].y) : 0.0f));
@@ -588,7 +589,7 @@ RT_DEV bool waveLaneLoop(const DevScene& S, const WaveQ& Q, unsigned long long t
                         float4* q = Q.rays + 3 * (size_t)ntk;
                         st128(q, make_float4(a.x, a.y, a.z, tag));
                         st128(q + 1, make_float4(b.x, b.y, b.z, tag));
-                        st128(q + 2, make_float4(m.x, m.y, i2f((r + 1) | (T.sp << 24)), tag));
+                        st128(q + 2, make_float4(m.x, m.y, i2f(room ? ((r + 1) | (T.sp << 24)) : 0), tag));
                         WAVE_LAT_NOW(ntk, 0);
                     }
                     st = WS_NONE;
