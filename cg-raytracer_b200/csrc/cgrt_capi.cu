@@ -229,6 +229,13 @@ static void fastTreeSelfCheck(const std::vector<MeshView>& views, const BuiltBVH
 // depends on the scene (hit rate, lights, how long the searches are), and a wrong split leaves one of the two stages waiting.
 // Frames of one shape rendered repeatedly (the UI re-renders every frame, main.cpp:907-914) are timed on the device (an event
 // pair per frame, read back when complete - the renderer never waits for it); the neighbours of the current setting are tried
+// NOTE on synchronous copies: cudaMemcpy from PAGEABLE host memory returns when the data has been staged, not when the DMA
+// has landed, and cudaMemset is asynchronous as well; both run on the legacy default stream, which the scene's NON-BLOCKING
+// streams (and the callers' own) are not ordered with. Every upload a later kernel depends on is therefore followed by
+// uploadsDone() before anything is launched (found by tools/wave_soak.py: a frame of another shape rendered with the previous
+// shape's tile list once in ~3000 shape changes).
+static cudaError_t uploadsDone() { return cudaDeviceSynchronize(); }
+
 // once each and the fastest is kept. Scheduling only: every setting renders the same pixels.
 struct WaveTuner {
     static const int RING = 8, LO = 2, HI = 14;
@@ -384,6 +391,7 @@ static int uploadSpheres(cgrt_scene* s, const float* spheres, int n)
     int rc = s->spheres.ensure(h.size());
     if (rc) return rc;
     if (n > 0) CK(cudaMemcpy(s->spheres.p, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CK(uploadsDone());
     s->dev.spheres = s->spheres.p;
     s->dev.nSpheres = n;
     return CGRT_OK;
@@ -621,6 +629,8 @@ int cgrt_scene_create(const cgrt_scene_desc* d, const cgrt_scene_options* opt, c
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
     if (e != cudaSuccess) { destroyScene(s); return fail(CGRT_ERR_CUDA, cudaGetErrorString(e)); }
 
+    e = uploadsDone(); // (see the note on synchronous copies)
+    if (e != cudaSuccess) { destroyScene(s); return fail(CGRT_ERR_CUDA, cudaGetErrorString(e)); }
     launchSetupPlanes(s->triV0.p, s->triV1.p, s->triV2.p, s->triPl.p, s->tri4.p, (int)T, s->stream);
     launchPermuteTri4(s->tri4.p, s->bvh.fastOrder.size() == T ? s->fastOrder.p : nullptr, s->tri4f.p, (int)T, s->stream);
     e = cudaStreamSynchronize(s->stream);
@@ -1221,6 +1231,7 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
             CK(cudaMemcpy(s->tileList.p, mine.data(), mine.size() * sizeof(int), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(s->tileSeq.p, seq.data(), seq.size() * sizeof(int2), cudaMemcpyHostToDevice));
         }
+        CK(uploadsDone());
         std::memcpy(s->tileKey, key, sizeof key);
     }
     const TileLayout& L = s->layout;
@@ -1261,6 +1272,7 @@ static int prepareFrame(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render
             CK(cudaMemset(s->waveRays.p, 0, tickets * 3 * sizeof(float4)));
             RC(s->waveFin.ensure(tickets * 2));
             CK(cudaMemset(s->waveFin.p, 0, tickets * 2 * sizeof(float4)));
+            CK(uploadsDone());
         }
         RC(s->waveCtl.ensure(WCTL_INTS));
         RC(s->waveResume.ensure((size_t)waveGridBlocks(s->di.numSMs) * 128 * WAVE_RESUME_F4));
@@ -1622,6 +1634,7 @@ int cgrt_render(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_params*
         if (!s->zeroFrame.p || s->zeroFrame.n < frameFloats) {
             RC(s->zeroFrame.ensure(frameFloats));
             CK(cudaMemset(s->zeroFrame.p, 0, frameFloats * sizeof(float)));
+            CK(uploadsDone());
         }
         CK(cudaMemcpyAsync(rgb, s->zeroFrame.p, frameFloats * sizeof(float), cudaMemcpyDeviceToHost, s->copyStream));
         CK(cudaEventRecord(s->copyDone[0], s->copyStream));
@@ -1863,6 +1876,7 @@ int cgrt_assemble_tiles(int device, const cgrt_render_params* p, const float* d_
         CK(cudaMalloc((void**)&c.dCounts, counts.size() * sizeof(int)));
         CK(cudaMemcpy(c.dLists, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c.dCounts, counts.data(), counts.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(uploadsDone());
         std::memcpy(c.key, key, sizeof key);
         c.L = L;
     }
@@ -2008,6 +2022,7 @@ int cgrt_memcpy_h2d(int device, void* dst, const void* src, size_t bytes)
 {
     RC(useDevice(device));
     CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    CK(uploadsDone()); // (the caller launches on streams of its own next)
     return CGRT_OK;
 }
 int cgrt_memcpy_d2h(int device, void* dst, const void* src, size_t bytes)

@@ -2451,7 +2451,7 @@ int launchWavePipeline(const DevScene& S, const FrameParams* dP, const FramePara
     // every CTA must be resident at once: warps wait for rays that other CTAs produce
     const int grid = waveGridBlocks(numSMs);
     traceBegin(tr, 2, st);
-    k_wave<<<grid, 128, 0, st>>>(S, dP, dLights, Q, B, dTileSeq, fb);
+    k_wave<<<grid, 128, 0, st>>>(S, hP, dLights, Q, B, dTileSeq, fb);
     traceEnd(tr, 2, st);
     return 1;
 }

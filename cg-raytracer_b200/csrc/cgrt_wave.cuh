@@ -889,7 +889,8 @@ RT_DEV void waveGroupLoop(const DevScene& S, const WaveQ& Q, WaveShared& sh, uns
 #ifndef CGRT_WAVE_MINBLOCKS
 #define CGRT_WAVE_MINBLOCKS 8
 #endif
-__global__ void __launch_bounds__(128, CGRT_WAVE_MINBLOCKS) k_wave(DevScene S, const FrameParams* __restrict__ Pp,
+// (the frame's parameters travel as a kernel argument: the kernel then depends on nothing but its own launch)
+__global__ void __launch_bounds__(128, CGRT_WAVE_MINBLOCKS) k_wave(DevScene S, const FrameParams Pv,
                                                                   const float4* __restrict__ lights, WaveQ Q, RoundBuffers B,
                                                                   const int2* __restrict__ tileSeq, float* __restrict__ fb)
 {
@@ -897,7 +898,7 @@ __global__ void __launch_bounds__(128, CGRT_WAVE_MINBLOCKS) k_wave(DevScene S, c
     __shared__ FrameParams Psh;
     __shared__ int genCount;
     if (threadIdx.x == 0) {
-        Psh = *Pp;
+        Psh = Pv;
         genCount = 0;
     }
     if (threadIdx.x < WAVE_NSTAT) sh.stat[threadIdx.x] = 0;

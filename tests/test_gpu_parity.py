@@ -613,6 +613,17 @@ def test_scheduling_variants_render_the_same_frame(gpu):
             assert all(v["pipeline"] == (2 if label == "rounds" else 3) for v in r.values()), label
 
 
+def test_mixed_frame_shapes_soak(gpu):
+    """Frames of eight shapes (sizes, trace limits, rank / world shares, two scenes) in random order: every frame must equal
+    the first frame of its shape bit for bit. Guards the per-frame host state - tile lists, queues, parameter upload - against
+    ordering mistakes between the legacy default stream and the scene's non-blocking streams (tools/wave_soak.py found one)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "wave_soak.py"), "500"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert "0 differing" in r.stdout
+
+
 def test_finisher_share_tuner_keeps_the_frame(capi, gpu):
     """Repeated frames of one shape: the measured tuning of the finisher share (WaveTuner) tries neighbouring settings; every
     frame must be the first frame bit for bit, and the tuner must report a setting inside its range."""
