@@ -25,7 +25,8 @@ def main():
     d = capi.dragon_standin()
     scene = capi.Scene(d, lights=d.lights, device=local)
     ok = True
-    for (W, H, L) in ((1920, 1080, 5), (333, 201, 2), (64, 64, 0)):
+    rounds = int(os.environ.get("MULTI_CHECK_ROUNDS", "1"))  # > 1: soak (renderers opened and closed again, shapes alternating)
+    for (W, H, L) in ((1920, 1080, 5), (333, 201, 2), (64, 64, 0), (1280, 720, 3)) * rounds:
         cam = capi.make_camera(W, H)
         ref = None
         if rank == 0:
