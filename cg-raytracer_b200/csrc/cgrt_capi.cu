@@ -1157,7 +1157,7 @@ static void waveTunerEnd(WaveTuner& T, cudaStream_t st)
 // scheduling knobs / watchdog of the persistent wavefront (CGRT_WAVE="mode=0,group_below=400000,switch=0,fin=0,tune=1,handover=1,timeout_ms=4000"; 0 = automatic; they
 // change speed only, never results). mode 0: the search form follows the size of this rank's share of the frame - one lane per
 // ray for large shares (throughput), eight lanes per ray for small ones (latency)
-static bool waveTuning(WaveQ& Q, int nSlots, int nLights)
+static bool waveTuning(WaveQ& Q, int nSlots, int nLights, int world)
 {
     static int mode = 0, groupBelow = 400000, fin = 0, timeoutMs = 4000, switchBelow = 0, handOver = 1, tune = 1;
     static bool loaded = false;
@@ -1191,7 +1191,8 @@ static bool waveTuning(WaveQ& Q, int nSlots, int nLights)
     // light (measured with the two-stage certificates, profiles/r02_tuning.md: C3, 1 light: 1/6 of the SMs, 1/8 for the
     // GROUP-only share of C3 - but 1/5 for the Cornell box, and too few finishers cost more than too many; 3 lights: 1/4).
     // This is the STARTING value: WaveTuner moves it by measurement
-    Q.finEvery = fin > 0 ? std::max(fin, 2) : (nLights >= 3 ? 4 : (nLights == 2 ? 5 : 6));
+    // (shares of a multi-GPU frame are rendered back to back, where the tuner gets no samples: small C3 shares want 1/8-1/9)
+    Q.finEvery = fin > 0 ? std::max(fin, 2) : (nLights >= 3 ? 4 : (nLights == 2 ? 5 : (Q.mode == 2 && world > 1 ? 8 : 6)));
     // (GROUP-only frames never change over; measured on the C3 frame and its 1/2, 1/4 shares: 100 K in flight for a whole 1080p
     // frame, 60 K for smaller shares)
     Q.switchBelow = Q.mode == 2 ? 0 : (switchBelow > 0 ? switchBelow : (nSlots >= 1500000 ? 100000 : 60000));
@@ -1416,7 +1417,7 @@ int cgrt_render_device(cgrt_scene* s, const cgrt_camera* cam, const cgrt_render_
             CK(cudaMemsetAsync(s->waveTrace.p, 0, (size_t)WAVE_TRACE_SAMPLES * 8 * sizeof(int), st));
             Q.trace = s->waveTrace.p;
         }
-        const bool tuned = waveTuning(Q, P.nSlots, P.nLights) && !(p->flags & CGRT_RENDER_PROFILE_ALL);
+        const bool tuned = waveTuning(Q, P.nSlots, P.nLights, P.world) && !(p->flags & CGRT_RENDER_PROFILE_ALL);
         if (tuned) {
             const int key[8] = {P.width, P.height, P.nSlots, P.traceLimit, P.nLights, P.world, P.rank, Q.mode};
             Q.finEvery = waveTunerChoose(s->tuner, key, Q.finEvery);
