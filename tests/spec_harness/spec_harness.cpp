@@ -262,4 +262,60 @@ int spec_run(const cgrt_scene_desc* d, int max_depth, int sah, const float* rays
     return 0;
 }
 
+// Property check of the certificates' first stage (cgrt_device.cuh slabFastHit): whenever it claims a hit, the reference's own
+// slabTest (six IEEE divisions) must report a hit for an unbounded ray, at a distance no larger than the claimed upper bound.
+// Inputs: n random (box, ray) pairs from a generator that favours the hard cases - origins on / next to faces, grazing rays,
+// tiny and huge direction components, flat boxes, far origins. out[4] = cases, fast-stage claims, violations, fast-stage
+// claims whose bound is more than 1e-5 (relative) above the reference's distance (looseness, not an error).
+int spec_slab_fast_check(int64_t n, uint64_t seed, int64_t* out)
+{
+    int64_t claims = 0, bad = 0, loose = 0;
+#pragma omp parallel for schedule(static) reduction(+ : claims, bad, loose)
+    for (int64_t i = 0; i < n; i++) {
+        uint64_t x = seed * 0x9E3779B97F4A7C15ull + (uint64_t)i * 0xD1B54A32D192ED03ull + 1;
+        auto next = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+        auto uni = [&]() { return (float)((next() >> 40) * (1.0 / 16777216.0)); };
+        auto mag = [&]() { // a magnitude across many decades
+            static const float dec[] = {1e-12f, 1e-6f, 1e-3f, 0.1f, 1.0f, 1.0f, 1.0f, 10.0f, 1e3f, 1e6f};
+            return dec[next() % 10] * (0.1f + uni());
+        };
+        const float scale = mag();
+        V3 lo, hi, o, d;
+        float* L = &lo.x; float* Hh = &hi.x; float* O = &o.x; float* D = &d.x;
+        for (int k = 0; k < 3; k++) {
+            const float c = (uni() - 0.5f) * 4.0f * scale, e = (next() % 8 == 0) ? 0.0f : uni() * scale;
+            L[k] = c - e;
+            Hh[k] = c + e;
+            const unsigned pick = (unsigned)(next() % 10);
+            if (pick == 0) O[k] = L[k];                                  // on a face
+            else if (pick == 1) O[k] = Hh[k];
+            else if (pick == 2) O[k] = std::nextafter(L[k], -1e30f);     // one ulp outside / inside
+            else if (pick == 3) O[k] = std::nextafter(Hh[k], 1e30f);
+            else if (pick == 4) O[k] = c + (uni() - 0.5f) * 1e3f * scale; // far away
+            else O[k] = c + (uni() - 0.5f) * 6.0f * scale;
+            const unsigned dp = (unsigned)(next() % 12);
+            float dv = (uni() - 0.5f) * 2.0f;
+            if (dp == 0) dv = 0.0f;
+            else if (dp == 1) dv *= 1e-20f;
+            else if (dp == 2) dv *= 1e-35f;
+            else if (dp == 3) dv *= 1e20f;
+            else if (dp == 4) dv *= 1e-7f;
+            D[k] = dv;
+        }
+        if (next() % 4 == 0) { // aim at the box, so that hits are common
+            const V3 tgt = mk3(lo.x + (hi.x - lo.x) * uni(), lo.y + (hi.y - lo.y) * uni(), lo.z + (hi.z - lo.z) * uni());
+            d = tgt - o;
+        }
+        const SlabFast F = slabFastBegin(d);
+        float up = 0.0f;
+        if (!slabFastHit(F, lo, hi, o, up)) continue;
+        claims++;
+        float te = 0.0f;
+        if (!slabTest(lo, hi, o, d, __int_as_float(0x7f800000), te) || !(te <= up)) bad++;
+        else if (up > te * 1.00001f + 1e-30f) loose++;
+    }
+    out[0] = n; out[1] = claims; out[2] = bad; out[3] = loose;
+    return 0;
+}
+
 } // extern "C"

@@ -255,3 +255,19 @@ def test_special_float_values(harness, kind):
         for mode in (1, 3):
             _, _, _, st = run(harness, flat, rays, mode=mode, max_dist=md, sah=sah)
             assert st["mismatch"] == 0, (mode, st)
+
+
+def test_first_stage_slab_test_is_sound(harness):
+    """The certificates' first stage (reciprocal-direction slab test with margins, cgrt_device.cuh slabFastHit) may only claim
+    what the reference's own slabTest confirms: a hit of the unbounded ray at a distance <= the claimed bound. 40 M generated
+    (box, ray) pairs weighted towards the hard cases; the stage must also decide most ordinary cases (otherwise it is useless)."""
+    import ctypes as C
+    harness.spec_slab_fast_check.restype = C.c_int
+    out = (C.c_int64 * 4)()
+    tot = [0, 0, 0, 0]
+    for seed in (1, 2, 3, 4):
+        assert harness.spec_slab_fast_check(C.c_int64(10_000_000), C.c_uint64(seed), out) == 0
+        tot = [a + int(b) for a, b in zip(tot, out)]
+    assert tot[2] == 0, f"{tot[2]} claims of the fast stage contradicted by the reference's slabTest (of {tot[1]} claims)"
+    # (looseness: the bound is relative to the largest of the six slab distances, so far-away slabs widen it - by design)
+    assert tot[1] > tot[0] // 50 and tot[3] < tot[1] // 5, tot
